@@ -1,0 +1,22 @@
+"""3dinfomax_b200 — B200-native hot path of 3DInfomax pre-training (PNA + Net3D + NTXent).
+
+The directory name starts with a digit, so import it with ``importlib.import_module("3dinfomax_b200")``.
+Public surface = the reference's plugin names (train.py:167-208 looks classes up by name):
+
+    PNA, Net3D                              model_type / model3d_type      (models/pna.py, models/net3d.py)
+    NTXent, NTXentMultiplePositives         loss_func                      (commons/losses.py)
+    SelfSupervisedTrainer                   trainer: 'contrastive'         (trainer/self_supervised_trainer.py)
+
+Everything computes through lib3dinfomax_b200.so (hand-written sm_100a kernels, C ABI in include/i3d.h).
+There is no CPU fallback: constructing modules works anywhere, running them needs a CUDA device.
+"""
+from .graph import GraphBatch, GraphStructure, batch_from_numpy, graph_structure  # noqa: F401
+from .losses import NTXent, NTXentMultiplePositives  # noqa: F401
+from .net3d import Net3D  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
+from .pna import PNA  # noqa: F401
+from .trainer import CapturedStep, SelfSupervisedTrainer  # noqa: F401
+from . import lib, synthetic  # noqa: F401
+
+__all__ = ["PNA", "Net3D", "NTXent", "NTXentMultiplePositives", "SelfSupervisedTrainer", "CapturedStep", "FusedAdam",
+           "GraphBatch", "GraphStructure", "batch_from_numpy", "graph_structure", "lib", "synthetic"]

@@ -1,0 +1,410 @@
+// FCLayer tail kernels: activation + train-mode BatchNorm1d statistics / apply / backward
+// (models/base_layers.py:100-111: Linear -> activation -> BatchNorm, statistics over ALL rows of the batch).
+//
+// Column statistics are accumulated in fp64: Net3D's BN inputs have mean^2 >> var,
+// where an fp32 E[x^2]-E[x]^2 loses the variance.  All kernels are HBM-bound row streams: a thread owns one
+// 16-byte column group and walks rows with a fixed stride, so column partials stay in registers.
+#include <initializer_list>
+
+#include "i3d_vec.cuh"
+
+namespace i3d {
+
+constexpr int kColThreads = 256;
+
+// thread -> (column group cg, row phase rg); rows visited: blockIdx*RP + rg, += gridDim*RP
+struct ColMap {
+  int cg, rg, RP;
+  bool active;
+};
+__device__ __forceinline__ ColMap col_map(int FV) {
+  ColMap m;
+  m.RP = kColThreads / FV;
+  m.cg = threadIdx.x % FV;
+  m.rg = threadIdx.x / FV;
+  m.active = m.rg < m.RP;
+  return m;
+}
+
+// block-reduce NV*V doubles per column group over the row phases, then atomically add to global
+template <int V, int NV>
+__device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const ColMap& m, int FV, int F,
+                                                     double* __restrict__ gsum) {
+  extern __shared__ double sh[];  // [NV][V][kColThreads]
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[(a * V + i) * kColThreads + threadIdx.x] = m.active ? acc[a][i] : 0.0;
+  __syncthreads();
+  if (m.active && m.rg == 0) {
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        double s = 0.0;
+        for (int r = 0; r < m.RP; ++r) s += sh[(a * V + i) * kColThreads + r * FV + m.cg];
+        atomicAdd(gsum + (int64_t)a * F + m.cg * V + i, s);
+      }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kColThreads)
+    act_colstats_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, double* __restrict__ sums) {
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  double acc[2][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = 0.0, acc[1][i] = 0.0;
+  if (m.active) {
+    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
+      Vec<V> y;
+      y.load(Y + r * ldy + m.cg * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const double h = (double)act_apply(y.v[i], act);
+        acc[0][i] += h;
+        acc[1][i] += h * h;
+      }
+    }
+  }
+  block_col_reduce_f64<V, 2>(acc, m, FV, F, sums);
+}
+
+// per-column (alpha, beta) with O = h*alpha + beta, exactly the folded form PyTorch's CPU batch_norm uses
+__device__ __forceinline__ void bn_column_terms(int c, int64_t M, int F, const double* __restrict__ sums,
+                                                const float* __restrict__ running_mean,
+                                                const float* __restrict__ running_var,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                float eps, int training, float* mean_out, float* rstd_out,
+                                                double* var_biased) {
+  double mean, var;
+  if (training) {
+    mean = sums[c] / (double)M;
+    var = sums[F + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+  } else {
+    mean = (double)running_mean[c];
+    var = (double)running_var[c];
+  }
+  *mean_out = (float)mean;
+  *rstd_out = (float)(1.0 / sqrt(var + (double)eps));
+  *var_biased = var;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+    bn_apply_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, const double* __restrict__ sums,
+                    float* __restrict__ running_mean, float* __restrict__ running_var,
+                    int64_t* __restrict__ num_batches_tracked, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float momentum, float eps, int training,
+                    float* __restrict__ save_mean_rstd, const float* __restrict__ residual, float* __restrict__ O,
+                    int ldo) {
+  extern __shared__ float shf[];  // alpha[F], beta[F]
+  float* s_alpha = shf;
+  float* s_beta = shf + F;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float mean, rstd;
+    double var;
+    bn_column_terms(c, M, F, sums, running_mean, running_var, gamma, beta, eps, training, &mean, &rstd, &var);
+    const float a = rstd * gamma[c];
+    s_alpha[c] = a;
+    s_beta[c] = beta[c] - mean * a;
+    if (blockIdx.x == 0) {
+      save_mean_rstd[c] = mean;
+      save_mean_rstd[F + c] = rstd;
+      if (training) {
+        const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+  __syncthreads();
+  const int FV = F / V;
+  const int64_t total = M * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / FV;
+    const int c0 = (int)(t - r * FV) * V;
+    Vec<V> y, o;
+    y.load(Y + r * ldy + c0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.v[i] = act_apply(y.v[i], act) * s_alpha[c0 + i] + s_beta[c0 + i];
+    if (residual) {
+      Vec<V> rr;
+      rr.load(residual + r * ldo + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.v[i] = __fadd_rn(o.v[i], rr.v[i]);
+    }
+    o.store(O + r * ldo + c0);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kColThreads)
+    bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
+                         int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2) {
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  double acc[2][V];
+  float mean[V], rstd[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    acc[0][i] = 0.0, acc[1][i] = 0.0;
+    mean[i] = m.active ? save_mean_rstd[m.cg * V + i] : 0.f;
+    rstd[i] = m.active ? save_mean_rstd[F + m.cg * V + i] : 0.f;
+  }
+  if (m.active) {
+    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
+      Vec<V> y, d;
+      y.load(Y + r * ldy + m.cg * V);
+      d.load(dO + r * ldd + m.cg * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xhat = (act_apply(y.v[i], act) - mean[i]) * rstd[i];
+        acc[0][i] += (double)d.v[i];
+        acc[1][i] += (double)d.v[i] * (double)xhat;
+      }
+    }
+  }
+  block_col_reduce_f64<V, 2>(acc, m, FV, F, sums2);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kColThreads)
+    bn_bwd_apply_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M, int F,
+                        int act, int has_bn, int training, const float* __restrict__ save_mean_rstd,
+                        const float* __restrict__ gamma, const double* __restrict__ sums2, float* __restrict__ dY,
+                        int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  float mean[V], rstd[V], k1[V], k2[V], gr[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    db[i] = 0.f;
+    mean[i] = 0.f, rstd[i] = 1.f, k1[i] = 0.f, k2[i] = 0.f, gr[i] = 1.f;
+    if (m.active && has_bn) {
+      const int c = m.cg * V + i;
+      mean[i] = save_mean_rstd[c];
+      rstd[i] = save_mean_rstd[F + c];
+      gr[i] = gamma[c] * rstd[i];
+      if (training) {
+        k1[i] = (float)(sums2[c] / (double)M);
+        k2[i] = (float)(sums2[F + c] / (double)M);
+      }
+      if (blockIdx.x == 0 && m.rg == 0) {
+        dbeta[c] = (float)sums2[c];
+        dgamma[c] = (float)sums2[F + c];
+      }
+    }
+  }
+  if (m.active) {
+    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
+      Vec<V> y, d, o;
+      y.load(Y + r * ldy + m.cg * V);
+      d.load(dO + r * ldd + m.cg * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float dh = d.v[i];
+        if (has_bn) {
+          const float xhat = (act_apply(y.v[i], act) - mean[i]) * rstd[i];
+          dh = gr[i] * (d.v[i] - k1[i] - xhat * k2[i]);
+        }
+        const float dy = dh * act_grad(y.v[i], act);
+        o.v[i] = dy;
+        db[i] += dy;
+      }
+      o.store(dY + r * lddy + m.cg * V);
+    }
+  }
+  if (dbias) {
+    extern __shared__ double shd[];
+    float* sh = reinterpret_cast<float*>(shd);  // [V][kColThreads]
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[i * kColThreads + threadIdx.x] = m.active ? db[i] : 0.f;
+    __syncthreads();
+    if (m.active && m.rg == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float s = 0.f;
+        for (int r = 0; r < m.RP; ++r) s += sh[i * kColThreads + r * FV + m.cg];
+        atomicAdd(dbias + m.cg * V + i, s);
+      }
+    }
+  }
+}
+
+__global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = act_apply(x[i], act);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, int64_t n, int act,
+                               float* __restrict__ gx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    gx[i] = gy[i] * act_grad(x[i], act);
+}
+
+// column sums in fp32 (bias gradients of layers without BN, node_embedding gradient)
+template <int V>
+__global__ void __launch_bounds__(kColThreads)
+    colsum_kernel(const float* __restrict__ x, int ldx, int64_t M, int F, float* __restrict__ out) {
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (m.active) {
+    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
+      Vec<V> v;
+      v.load(x + r * ldx + m.cg * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += v.v[i];
+    }
+  }
+  extern __shared__ double shd[];
+  float* sh = reinterpret_cast<float*>(shd);
+#pragma unroll
+  for (int i = 0; i < V; ++i) sh[i * kColThreads + threadIdx.x] = m.active ? acc[i] : 0.f;
+  __syncthreads();
+  if (m.active && m.rg == 0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float s = 0.f;
+      for (int r = 0; r < m.RP; ++r) s += sh[i * kColThreads + r * FV + m.cg];
+      atomicAdd(out + m.cg * V + i, s);
+    }
+  }
+}
+
+static inline int col_grid(int64_t M, int FV) {
+  const int RP = kColThreads / FV;
+  int64_t need = (M + (int64_t)RP * 16 - 1) / ((int64_t)RP * 16);  // >= 16 rows per thread before adding CTAs
+  int64_t cap = (int64_t)sm_count() * 4;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace i3d
+
+using namespace i3d;
+
+extern "C" {
+
+int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double* sums, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && sums && (M == 0 || Y), "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  I3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({Y}, {F, ldy});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  I3D_REQUIRE(FV <= kColThreads, "feature width too large (F <= 1024 when 16B-aligned, else F <= 256)");
+  const size_t smem = sizeof(double) * 2 * V * kColThreads;
+  if (v4)
+    act_colstats_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(Y, M, F, ldy, act, sums);
+  else
+    act_colstats_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(Y, M, F, ldy, act, sums);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const double* sums, float* running_mean,
+                 float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
+                 float momentum, float eps, int training, float* save_mean_rstd, const float* residual, float* O,
+                 int ldo, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldo >= F && gamma && beta && save_mean_rstd && running_mean &&
+                  running_var && (!training || sums) && (M == 0 || (Y && O)),
+              "invalid argument");
+  I3D_REQUIRE(!(training && M < 2), "Expected more than 1 value per channel when training");
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({Y, O, residual}, {F, ldy, ldo});
+  const int64_t work = M * (F / (v4 ? 4 : 1));
+  const size_t smem = sizeof(float) * 2 * F;
+  cudaStream_t s = as_stream(stream);
+  if (v4)
+    bn_apply_kernel<4><<<grid_for(work, 256), 256, smem, s>>>(Y, M, F, ldy, act, sums, running_mean, running_var,
+                                                              num_batches_tracked, gamma, beta, momentum, eps,
+                                                              training, save_mean_rstd, residual, O, ldo);
+  else
+    bn_apply_kernel<1><<<grid_for(work, 256), 256, smem, s>>>(Y, M, F, ldy, act, sums, running_mean, running_var,
+                                                              num_batches_tracked, gamma, beta, momentum, eps,
+                                                              training, save_mean_rstd, residual, O, ldo);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                      const float* save_mean_rstd, double* sums2, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && sums2 && save_mean_rstd && (M == 0 || (Y && dO)),
+              "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F, s));
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({Y, dO}, {F, ldy, ldd});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  I3D_REQUIRE(FV <= kColThreads, "feature width too large");
+  const size_t smem = sizeof(double) * 2 * V * kColThreads;
+  if (v4)
+    bn_bwd_reduce_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+                                                                      sums2);
+  else
+    bn_bwd_reduce_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+                                                                      sums2);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
+                     int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
+                     int lddy, float* dbias, float* dgamma, float* dbeta, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && (M == 0 || (Y && dO && dY)), "invalid argument");
+  I3D_REQUIRE(!has_bn || (save_mean_rstd && gamma && sums2 && dgamma && dbeta), "BN tensors missing");
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({Y, dO, dY}, {F, ldy, ldd, lddy});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  I3D_REQUIRE(FV <= kColThreads, "feature width too large");
+  const size_t smem = sizeof(float) * V * kColThreads;
+  cudaStream_t s = as_stream(stream);
+  if (v4)
+    bn_bwd_apply_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, has_bn, training,
+                                                                     save_mean_rstd, gamma, sums2, dY, lddy, dbias,
+                                                                     dgamma, dbeta);
+  else
+    bn_bwd_apply_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, has_bn, training,
+                                                                     save_mean_rstd, gamma, sums2, dY, lddy, dbias,
+                                                                     dgamma, dbeta);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream) {
+  I3D_REQUIRE(n >= 0 && (n == 0 || (x && y)), "invalid argument");
+  if (n == 0) return I3D_OK;
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, act, y);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_act_bwd(const float* gy, const float* x, int64_t n, int act, float* gx, void* stream) {
+  I3D_REQUIRE(n >= 0 && (n == 0 || (gy && x && gx)), "invalid argument");
+  if (n == 0) return I3D_OK;
+  act_bwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(gy, x, n, act, gx);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_colsum(const float* x, int ldx, int64_t M, int F, float* out, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldx >= F && out && (M == 0 || x), "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  I3D_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * F, s));
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({x}, {F, ldx});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  I3D_REQUIRE(FV <= kColThreads, "feature width too large");
+  const size_t smem = sizeof(float) * V * kColThreads;
+  if (v4)
+    colsum_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(x, ldx, M, F, out);
+  else
+    colsum_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(x, ldx, M, F, out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+}

@@ -1,0 +1,326 @@
+// Segmented "virtual operand" GEMM, fp32 SIMT path.
+//
+//   C[m,n] (+)= bias[n] + sum_s sum_k  scale_s(.) * A_s(gather) * B_s(gather)
+//
+// The K dimension is a list of segments so the reference's torch.cat([h[src], h[dst], e]) (models/pna.py:249),
+// torch.cat([h, agg, agg*amp, agg*att]) (models/pna.py:207,232) and the index_select gathers behind DGL's
+// edges.src / edges.dst never hit HBM: the tile loader gathers rows and applies the per-row degree scaler
+// while staging tiles into shared memory.
+//
+// Tiling: 128x64x16 CTA tile, 256 threads, 8x4 register micro-tile, double-buffered shared memory with
+// register prefetch.  TN (weight-gradient) mode splits K over gridDim.z and reduces with fp32 atomics
+// because M,N are a few hundred while K is the edge / node count.
+#include "i3d_common.cuh"
+
+namespace i3d {
+
+constexpr int BM = 128, BN = 64, BK = 16, GEMM_THREADS = 256;
+
+struct GemmParams {
+  i3d_gemm_seg seg[4];
+  int n_seg;
+  int64_t M;
+  int N;
+  float* C;
+  int ldc;
+  const float* bias;
+  int accumulate;
+  int kchunk;  // TN split-K chunk (multiple of BK)
+  int splits;
+};
+
+__device__ __forceinline__ bool is_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmParams p) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t M = p.M;
+  const int N = p.N;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int s = 0; s < p.n_seg; ++s) {
+    const float* __restrict__ A = p.seg[s].A;
+    const float* __restrict__ B = p.seg[s].B;
+    const int32_t* __restrict__ a_idx = p.seg[s].a_idx;
+    const int32_t* __restrict__ b_idx = p.seg[s].b_idx;
+    const float* __restrict__ scale = p.seg[s].scale;
+    const int lda = p.seg[s].lda, ldb = p.seg[s].ldb;
+    int kbeg = 0, kend = p.seg[s].K;
+    if (MODE == I3D_GEMM_TN) {
+      kbeg = blockIdx.z * p.kchunk;
+      kend = min(kend, kbeg + p.kchunk);
+    }
+    const int ntile = (kend - kbeg + BK - 1) / BK;
+    if (ntile <= 0) continue;
+    const bool vecA = ((lda & 3) == 0) && is_al16(A);
+    const bool vecB = ((ldb & 3) == 0) && is_al16(B);
+
+    // per-thread fixed row bookkeeping for k-contiguous operands
+    int64_t a_row[2] = {-1, -1};
+    float a_sc[2] = {1.f, 1.f};
+    int64_t b_row = -1;
+    if (MODE != I3D_GEMM_TN) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t gm = m0 + ((tid + i * GEMM_THREADS) >> 2);
+        if (gm < M) {
+          a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : gm;
+          if (scale) a_sc[i] = __ldg(scale + gm);
+        }
+      }
+    }
+    if (MODE == I3D_GEMM_NT) {
+      const int gn = n0 + (tid >> 2);
+      if (gn < N) b_row = gn;
+    }
+
+    float4 ra[2], rb;
+
+    auto load_tile = [&](int k0) {
+      // ---- A ----
+      if (MODE != I3D_GEMM_TN) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int kq = ((tid + i * GEMM_THREADS) & 3) << 2;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a_row[i] >= 0) {
+            const float* src = A + a_row[i] * lda + k0 + kq;
+            if (vecA && k0 + kq + 3 < kend) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (k0 + kq + 0 < kend) v.x = __ldg(src + 0);
+              if (k0 + kq + 1 < kend) v.y = __ldg(src + 1);
+              if (k0 + kq + 2 < kend) v.z = __ldg(src + 2);
+              if (k0 + kq + 3 < kend) v.w = __ldg(src + 3);
+            }
+            const float sc = a_sc[i];
+            v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+          }
+          ra[i] = v;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = tid + i * GEMM_THREADS;
+          const int kk = c >> 5, mq = (c & 31) << 2;
+          const int gk = k0 + kk;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gk < kend) {
+            const int64_t row = a_idx ? (int64_t)__ldg(a_idx + gk) : (int64_t)gk;
+            const float* src = A + row * lda + m0 + mq;
+            if (vecA && m0 + mq + 3 < M) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (m0 + mq + 0 < M) v.x = __ldg(src + 0);
+              if (m0 + mq + 1 < M) v.y = __ldg(src + 1);
+              if (m0 + mq + 2 < M) v.z = __ldg(src + 2);
+              if (m0 + mq + 3 < M) v.w = __ldg(src + 3);
+            }
+            if (scale) {
+              const float sc = __ldg(scale + gk);
+              v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+            }
+          }
+          ra[i] = v;
+        }
+      }
+      // ---- B ----
+      if (MODE == I3D_GEMM_NT) {
+        const int kq = (tid & 3) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b_row >= 0) {
+          const float* src = B + b_row * ldb + k0 + kq;
+          if (vecB && k0 + kq + 3 < kend) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (k0 + kq + 0 < kend) v.x = __ldg(src + 0);
+            if (k0 + kq + 1 < kend) v.y = __ldg(src + 1);
+            if (k0 + kq + 2 < kend) v.z = __ldg(src + 2);
+            if (k0 + kq + 3 < kend) v.w = __ldg(src + 3);
+          }
+        }
+        rb = v;
+      } else {
+        const int kk = tid >> 4, nq = (tid & 15) << 2;
+        const int gk = k0 + kk;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gk < kend) {
+          const int64_t row = (MODE == I3D_GEMM_TN && b_idx) ? (int64_t)__ldg(b_idx + gk) : (int64_t)gk;
+          const float* src = B + row * ldb + n0 + nq;
+          if (vecB && n0 + nq + 3 < N) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (n0 + nq + 0 < N) v.x = __ldg(src + 0);
+            if (n0 + nq + 1 < N) v.y = __ldg(src + 1);
+            if (n0 + nq + 2 < N) v.z = __ldg(src + 2);
+            if (n0 + nq + 3 < N) v.w = __ldg(src + 3);
+          }
+        }
+        rb = v;
+      }
+    };
+
+    auto store_tile = [&](int buf) {
+      if (MODE != I3D_GEMM_TN) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = tid + i * GEMM_THREADS;
+          const int row = c >> 2, kq = (c & 3) << 2;
+          As[buf][kq + 0][row] = ra[i].x;
+          As[buf][kq + 1][row] = ra[i].y;
+          As[buf][kq + 2][row] = ra[i].z;
+          As[buf][kq + 3][row] = ra[i].w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = tid + i * GEMM_THREADS;
+          const int kk = c >> 5, mq = (c & 31) << 2;
+          *reinterpret_cast<float4*>(&As[buf][kk][mq]) = ra[i];
+        }
+      }
+      if (MODE == I3D_GEMM_NT) {
+        const int row = tid >> 2, kq = (tid & 3) << 2;
+        Bs[buf][kq + 0][row] = rb.x;
+        Bs[buf][kq + 1][row] = rb.y;
+        Bs[buf][kq + 2][row] = rb.z;
+        Bs[buf][kq + 3][row] = rb.w;
+      } else {
+        const int kk = tid >> 4, nq = (tid & 15) << 2;
+        *reinterpret_cast<float4*>(&Bs[buf][kk][nq]) = rb;
+      }
+    };
+
+    load_tile(kbeg);
+    store_tile(0);
+    __syncthreads();
+    for (int t = 0; t < ntile; ++t) {
+      const int cur = t & 1;
+      if (t + 1 < ntile) load_tile(kbeg + (t + 1) * BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 8 + 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (t + 1 < ntile) store_tile(cur ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const bool split = (MODE == I3D_GEMM_TN) && p.splits > 1;
+  const int n = n0 + tx * 4;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias && !(split && blockIdx.z != 0)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < N) bv[j] = __ldg(p.bias + n + j);
+  }
+  const bool vecC = ((p.ldc & 3) == 0) && is_al16(p.C) && (n + 3 < N);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+    float* c = p.C + m * p.ldc + n;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = acc[i][j] + bv[j];
+    if (split) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < N) atomicAdd(c + j, o[j]);
+    } else if (vecC) {
+      float4 v = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(c);
+        v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
+      }
+      *reinterpret_cast<float4*>(c) = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < N) c[j] = p.accumulate ? c[j] + o[j] : o[j];
+    }
+  }
+}
+
+__global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
+  const int64_t total = M * N;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / N;
+    C[m * ldc + (t - m * N)] = 0.f;
+  }
+}
+
+}  // namespace i3d
+
+using namespace i3d;
+
+extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                        const float* bias, int accumulate, void* stream) {
+  I3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be NT, NN or TN");
+  I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N, "invalid shape");
+  if (M == 0 || N == 0) return I3D_OK;
+  I3D_REQUIRE(C != nullptr, "C is null");
+  I3D_REQUIRE(mode != I3D_GEMM_TN || n_seg == 1, "TN mode takes exactly one segment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_seg; ++s) {
+    I3D_REQUIRE(segs[s].K >= 0 && (segs[s].K == 0 || (segs[s].A && segs[s].B)), "segment operand is null");
+    I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
+    p.seg[s] = segs[s];
+  }
+  p.n_seg = n_seg;
+  p.M = M;
+  p.N = N;
+  p.C = C;
+  p.ldc = ldc;
+  p.bias = bias;
+  p.accumulate = accumulate;
+  p.kchunk = 0;
+  p.splits = 1;
+  cudaStream_t s = as_stream(stream);
+  const int64_t gx = (M + BM - 1) / BM;
+  const int gy = (N + BN - 1) / BN;
+  I3D_REQUIRE(gx < (1ll << 31) && gy <= 65535, "problem too large");
+  if (mode == I3D_GEMM_TN) {
+    const int K = segs[0].K;
+    const int64_t tiles = gx * gy;
+    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    int64_t max_splits = (K + 63) / 64;
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    int kchunk = (int)((K + want - 1) / want);
+    kchunk = ((kchunk + BK - 1) / BK) * BK;
+    if (kchunk < BK) kchunk = BK;
+    p.kchunk = kchunk;
+    p.splits = K > 0 ? (K + kchunk - 1) / kchunk : 1;
+    if (p.splits > 1 && !accumulate) {
+      zero_block_kernel<<<grid_for(M * N, 256), 256, 0, s>>>(C, M, N, ldc);
+      I3D_LAUNCHED();
+    }
+    gemm_kernel<I3D_GEMM_TN><<<dim3((unsigned)gx, gy, p.splits), GEMM_THREADS, 0, s>>>(p);
+  } else if (mode == I3D_GEMM_NT) {
+    gemm_kernel<I3D_GEMM_NT><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
+  } else {
+    gemm_kernel<I3D_GEMM_NN><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
+  }
+  I3D_LAUNCHED();
+  return I3D_OK;
+}

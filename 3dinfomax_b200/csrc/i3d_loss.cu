@@ -1,0 +1,262 @@
+// NTXent / NTXentMultiplePositives row kernels (commons/losses.py:143-155, 225-246) and the optimizer step.
+// The similarity matrix itself comes from i3d_gemm (z1 z2^T); these kernels turn it into exp(sim/tau),
+// the per-row positives / negatives sums, the loss rows, and in backward d loss / d dot plus the norm terms.
+#include <initializer_list>
+
+#include "i3d_vec.cuh"
+
+namespace i3d {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  t = sh[0];
+  __syncthreads();
+  return t;
+}
+
+__global__ void row_norms_kernel(const float* __restrict__ z, int64_t R, int D, float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = w; r < R; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float x = __ldg(z + r * D + c);
+      s = fmaf(x, x, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) norms[r] = sqrtf(s);
+  }
+}
+
+// one CTA per local row i
+__global__ void __launch_bounds__(256)
+    ntxent_rows_fwd_kernel(float* __restrict__ P, int64_t B, int64_t Bc, int C, const float* __restrict__ n1,
+                           const float* __restrict__ n2, int norm, float eps, float tau, int64_t row_offset,
+                           float* __restrict__ rowstats, float* __restrict__ loss_rows) {
+  __shared__ float sh[32];
+  const int64_t ncol = Bc * C;
+  for (int64_t i = blockIdx.x; i < B; i += gridDim.x) {
+    float* row = P + i * ncol;
+    const float a = norm ? n1[i] : 0.f;
+    const int64_t pb = (row_offset + i) * C, pe = pb + C;
+    float tot = 0.f, pos = 0.f;
+    for (int64_t j = threadIdx.x; j < ncol; j += blockDim.x) {
+      float s = row[j];
+      if (norm) s = __fdiv_rn(s, __fadd_rn(__fmul_rn(a, __ldg(n2 + j)), eps));
+      const float pv = expf(__fdiv_rn(s, tau));
+      row[j] = pv;
+      tot += pv;
+      if (j >= pb && j < pe) pos += pv;
+    }
+    tot = block_sum(tot, sh);
+    pos = block_sum(pos, sh);
+    if (threadIdx.x == 0) {
+      const float neg = tot - pos;
+      rowstats[2 * i] = pos;
+      rowstats[2 * i + 1] = neg;
+      loss_rows[i] = -logf(pos / neg);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    ntxent_rows_bwd_kernel(float* __restrict__ P, int64_t B, int64_t Bc, int C, const float* __restrict__ n1,
+                           const float* __restrict__ n2, int norm, float eps, float tau, int64_t row_offset,
+                           const float* __restrict__ rowstats, const float* __restrict__ gout, float inv_B,
+                           float* __restrict__ dn1, float* __restrict__ dn2) {
+  __shared__ float sh[32];
+  const int64_t ncol = Bc * C;
+  const float gl = gout[0] * inv_B;
+  for (int64_t i = blockIdx.x; i < B; i += gridDim.x) {
+    float* row = P + i * ncol;
+    const float a = norm ? n1[i] : 0.f;
+    const int64_t pb = (row_offset + i) * C, pe = pb + C;
+    const float pos = rowstats[2 * i], neg = rowstats[2 * i + 1];
+    const float c_pos = -gl / pos, c_neg = gl / neg;
+    float acc1 = 0.f;
+    for (int64_t j = threadIdx.x; j < ncol; j += blockDim.x) {
+      const float pv = row[j];
+      const float ds = ((j >= pb && j < pe) ? c_pos : c_neg) * pv / tau;
+      float dd = ds;
+      if (norm) {
+        const float b = __ldg(n2 + j);
+        const float den = a * b + eps;
+        const float s = tau * logf(pv);  // sim recovered from p = exp(sim/tau)
+        dd = ds / den;
+        const float t = -ds * s / den;   // d/d den
+        acc1 += t * b;
+        atomicAdd(dn2 + j, t * a);
+      }
+      row[j] = dd;
+    }
+    if (norm) {
+      acc1 = block_sum(acc1, sh);
+      if (threadIdx.x == 0) dn1[i] = acc1;
+    }
+  }
+}
+
+__global__ void sum_scaled_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+__global__ void norm_bwd_accum_kernel(const float* __restrict__ z, const float* __restrict__ norms,
+                                      const float* __restrict__ dn, int64_t R, int D, float* __restrict__ dz) {
+  const int64_t total = R * D;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / D;
+    dz[t] += dn[r] * z[t] / norms[r];
+  }
+}
+
+// hyper (host or device copy): [lr, beta1, beta2, eps, weight_decay, grad_scale] in fp64, exactly the Python
+// floats torch.optim.Adam computes its bias corrections from.
+struct AdamHyper {
+  double lr, beta1, beta2, eps, weight_decay, grad_scale;
+};
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, AdamHyper h, int64_t step,
+                            const double* __restrict__ hyper_dev, const int64_t* __restrict__ step_dev) {
+  __shared__ float sc[7];
+  if (threadIdx.x == 0) {
+    if (hyper_dev) {
+      h.lr = hyper_dev[0], h.beta1 = hyper_dev[1], h.beta2 = hyper_dev[2];
+      h.eps = hyper_dev[3], h.weight_decay = hyper_dev[4], h.grad_scale = hyper_dev[5];
+    }
+    if (step_dev) step = step_dev[0];
+    const double bc1 = 1.0 - pow(h.beta1, (double)step);
+    const double bc2 = 1.0 - pow(h.beta2, (double)step);
+    sc[0] = (float)(h.lr / bc1);
+    sc[1] = (float)sqrt(bc2);
+    sc[2] = (float)h.beta1;
+    sc[3] = (float)h.beta2;
+    sc[4] = (float)h.eps;
+    sc[5] = (float)h.weight_decay;
+    sc[6] = (float)h.grad_scale;
+  }
+  __syncthreads();
+  const float step_size = sc[0], bc2_sqrt = sc[1], beta1 = sc[2], beta2 = sc[3], eps = sc[4], wd = sc[5], gs = sc[6];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+__global__ void add_i64_kernel(int64_t* x, int64_t d) { x[0] += d; }
+
+__global__ void multi_copy_kernel(const uint64_t* __restrict__ ptrs, const int64_t* __restrict__ off,
+                                  const int64_t* __restrict__ len, float* __restrict__ flat, int to_flat) {
+  const int t = blockIdx.y;
+  float* tp = reinterpret_cast<float*>(ptrs[t]);
+  float* fp = flat + off[t];
+  const int64_t n = len[t];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (to_flat) fp[i] = tp[i];
+    else tp[i] = fp[i];
+  }
+}
+
+}  // namespace i3d
+
+using namespace i3d;
+
+extern "C" {
+
+int i3d_row_norms(const float* z, int64_t R, int D, float* norms, void* stream) {
+  I3D_REQUIRE(R >= 0 && D > 0 && (R == 0 || (z && norms)), "invalid argument");
+  if (R == 0) return I3D_OK;
+  row_norms_kernel<<<grid_for(R * 32, 256), 256, 0, as_stream(stream)>>>(z, R, D, norms);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1, const float* n2, int norm,
+                        float eps, float tau, int64_t row_offset, float* rowstats, float* loss_rows, void* stream) {
+  I3D_REQUIRE(B >= 0 && Bc >= 0 && C >= 1 && tau > 0.f && row_offset >= 0 && row_offset + B <= Bc &&
+                  (!norm || (n1 && n2)) && (B == 0 || (P && rowstats && loss_rows)),
+              "invalid argument");
+  if (B == 0) return I3D_OK;
+  const int grid = (int)(B < 65535 ? B : 65535);
+  ntxent_rows_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
+                                                              rowstats, loss_rows);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_sum_scaled(const float* x, int64_t n, float scale, float* out, void* stream) {
+  I3D_REQUIRE(n >= 0 && out && (n == 0 || x), "invalid argument");
+  sum_scaled_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, scale, out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_ntxent_rows_bwd(float* P, int64_t B, int64_t Bc, int C, const float* n1, const float* n2, int norm,
+                        float eps, float tau, int64_t row_offset, const float* rowstats, const float* gout,
+                        float inv_B, float* dn1, float* dn2, void* stream) {
+  I3D_REQUIRE(B >= 0 && Bc >= 0 && C >= 1 && tau > 0.f && gout && (!norm || (n1 && n2 && dn1 && dn2)) &&
+                  (B == 0 || (P && rowstats)),
+              "invalid argument");
+  if (B == 0) return I3D_OK;
+  const int grid = (int)(B < 65535 ? B : 65535);
+  ntxent_rows_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
+                                                              rowstats, gout, inv_B, dn1, dn2);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_norm_bwd_accum(const float* z, const float* norms, const float* dn, int64_t R, int D, float* dz,
+                       void* stream) {
+  I3D_REQUIRE(R >= 0 && D > 0 && (R == 0 || (z && norms && dn && dz)), "invalid argument");
+  if (R == 0) return I3D_OK;
+  norm_bwd_accum_kernel<<<grid_for(R * D, 256), 256, 0, as_stream(stream)>>>(z, norms, dn, R, D, dz);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, double grad_scale, int64_t step, const double* hyper_dev,
+                  const int64_t* step_dev, void* stream) {
+  I3D_REQUIRE(n >= 0 && (step_dev || step >= 1) && (n == 0 || (p && g && m && v)), "invalid argument");
+  if (n == 0) return I3D_OK;
+  AdamHyper h{lr, beta1, beta2, eps, weight_decay, grad_scale};
+  adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, h, step, hyper_dev, step_dev);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_add_i64(int64_t* x, int64_t delta, void* stream) {
+  I3D_REQUIRE(x != nullptr, "invalid argument");
+  add_i64_kernel<<<1, 1, 0, as_stream(stream)>>>(x, delta);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len, int T, float* flat, int to_flat,
+                   void* stream) {
+  I3D_REQUIRE(T >= 0 && T <= 65535 && (T == 0 || (ptrs && off && len && flat)), "invalid argument");
+  if (T == 0) return I3D_OK;
+  multi_copy_kernel<<<dim3(16, T, 1), 256, 0, as_stream(stream)>>>(ptrs, off, len, flat, to_flat);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+}

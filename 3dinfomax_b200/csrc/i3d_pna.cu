@@ -1,0 +1,464 @@
+// PNA hot-path kernels: categorical embedding sums, the fused multi-aggregator segmented reduction
+// (mean | max | min | std) with its backward, per-graph readouts, generic segment sums.
+//
+// All of them are HBM-bound streaming kernels: one thread owns one (row-segment, 16-byte column group)
+// pair, a warp reads 512 contiguous bytes per message row, neighbour rows of a node are contiguous
+// because messages are produced in CSR order (see DESIGN.md "data layout").
+#include <initializer_list>
+
+#include "i3d_vec.cuh"
+
+namespace i3d {
+
+// ------------------------------------------------------------------------------------------------
+// AtomEncoder / BondEncoder (commons/mol_encoder.py:34-42,65-73)
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void embed_sum_fwd_kernel(const int64_t* __restrict__ idx, int64_t R, int C,
+                                     const int32_t* __restrict__ col_off, const int32_t* __restrict__ perm,
+                                     const float* __restrict__ table, int F, float* __restrict__ out) {
+  const int FV = F / V;
+  const int64_t total = R * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / FV;
+    const int c0 = (int)(t - r * FV) * V;
+    const int64_t rr = perm ? (int64_t)perm[r] : r;
+    Vec<V> acc;
+    acc.fill(0.f);
+    for (int c = 0; c < C; ++c) {
+      const int64_t row = (int64_t)col_off[c] + idx[rr * C + c];
+      Vec<V> e;
+      e.load(table + row * F + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] = __fadd_rn(acc.v[i], e.v[i]);
+    }
+    acc.store(out + r * F + c0);
+  }
+}
+
+template <int V>
+__global__ void embed_sum_bwd_kernel(const int64_t* __restrict__ idx, int64_t R, int C,
+                                     const int32_t* __restrict__ col_off, const int32_t* __restrict__ perm,
+                                     const float* __restrict__ gout, int F, float* __restrict__ gtable) {
+  const int FV = F / V;
+  const int64_t total = R * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / FV;
+    const int c0 = (int)(t - r * FV) * V;
+    const int64_t rr = perm ? (int64_t)perm[r] : r;
+    Vec<V> g;
+    g.load(gout + r * F + c0);
+    for (int c = 0; c < C; ++c) {
+      const int64_t row = (int64_t)col_off[c] + idx[rr * C + c];
+      float* dst = gtable + row * F + c0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(dst + i, g.v[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PNA aggregation forward (models/pna.py:17-37,221-235).  One thread = one node x one column group.
+// Arithmetic is written with explicit round-to-nearest intrinsics so that nvcc does not contract
+// mean(x^2) - mean(x)^2 into an FMA: the relu gate of the variance must see the same sign as PyTorch.
+// ------------------------------------------------------------------------------------------------
+constexpr float kAggEps = 1e-5f;  // EPS, models/pna.py:14
+
+template <int V>
+__global__ void __launch_bounds__(256)
+    pna_aggregate_fwd_kernel(const float* __restrict__ msg, const int32_t* __restrict__ rowptr, int64_t N, int F,
+                             float* __restrict__ out, int ldo) {
+  const int FV = F / V;
+  const int64_t total = N * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / FV;
+    const int c0 = (int)(t - v * FV) * V;
+    const int32_t b = __ldg(rowptr + v), e = __ldg(rowptr + v + 1);
+    const int D = e - b;
+    float* o = out + v * (int64_t)ldo + c0;
+    Vec<V> s, q, mx, mn;
+    if (D <= 0) {
+      s.fill(0.f);
+      s.store_cs(o), s.store_cs(o + F), s.store_cs(o + 2 * F), s.store_cs(o + 3 * F);
+      continue;
+    }
+    s.fill(0.f), q.fill(0.f), mx.fill(-INFINITY), mn.fill(INFINITY);
+    const float* p = msg + (int64_t)b * F + c0;
+    int k = 0;
+    // 4 independent 16-byte loads in flight per thread (bond graphs have D <= 4 almost always)
+    for (; k + 4 <= D; k += 4) {
+      Vec<V> x0, x1, x2, x3;
+      x0.load(p + (int64_t)(k + 0) * F), x1.load(p + (int64_t)(k + 1) * F);
+      x2.load(p + (int64_t)(k + 2) * F), x3.load(p + (int64_t)(k + 3) * F);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s.v[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.v[i], x0.v[i]), x1.v[i]), x2.v[i]), x3.v[i]);
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x0.v[i], x0.v[i]));
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x1.v[i], x1.v[i]));
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x2.v[i], x2.v[i]));
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x3.v[i], x3.v[i]));
+        mx.v[i] = fmaxf(fmaxf(mx.v[i], x0.v[i]), fmaxf(x1.v[i], fmaxf(x2.v[i], x3.v[i])));
+        mn.v[i] = fminf(fminf(mn.v[i], x0.v[i]), fminf(x1.v[i], fminf(x2.v[i], x3.v[i])));
+      }
+    }
+    for (; k < D; ++k) {
+      Vec<V> x;
+      x.load(p + (int64_t)k * F);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s.v[i] = __fadd_rn(s.v[i], x.v[i]);
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x.v[i], x.v[i]));
+        mx.v[i] = fmaxf(mx.v[i], x.v[i]);
+        mn.v[i] = fminf(mn.v[i], x.v[i]);
+      }
+    }
+    const float fd = (float)D;
+    Vec<V> mean, sd;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      mean.v[i] = __fdiv_rn(s.v[i], fd);
+      const float msq = __fdiv_rn(q.v[i], fd);
+      const float var = fmaxf(__fsub_rn(msq, __fmul_rn(mean.v[i], mean.v[i])), 0.f);
+      sd.v[i] = __fsqrt_rn(__fadd_rn(var, kAggEps));
+    }
+    mean.store_cs(o), mx.store_cs(o + F), mn.store_cs(o + 2 * F), sd.store_cs(o + 3 * F);
+  }
+}
+
+// backward: g = [g_mean | g_max | g_min | g_std] already folded over the degree scalers by the GEMM backward
+template <int V>
+__global__ void __launch_bounds__(256)
+    pna_aggregate_bwd_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ msg,
+                             const float* __restrict__ out, int ldo, const int32_t* __restrict__ rowptr, int64_t N,
+                             int F, float* __restrict__ dmsg) {
+  const int FV = F / V;
+  const int64_t total = N * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / FV;
+    const int c0 = (int)(t - v * FV) * V;
+    const int32_t b = __ldg(rowptr + v), e = __ldg(rowptr + v + 1);
+    const int D = e - b;
+    if (D <= 0) continue;
+    const float* gp = g + v * (int64_t)ldg + c0;
+    const float* op = out + v * (int64_t)ldo + c0;
+    Vec<V> gmean, gmax, gmin, gstd, mean, mx, mn, sd;
+    gmean.load(gp), gmax.load(gp + F), gmin.load(gp + 2 * F), gstd.load(gp + 3 * F);
+    mean.load(op), mx.load(op + F), mn.load(op + 2 * F), sd.load(op + 3 * F);
+    const float* p = msg + (int64_t)b * F + c0;
+    float* dp = dmsg + (int64_t)b * F + c0;
+    // pass 1: sum of squares (same order as forward -> same relu gate), first arg-max / arg-min
+    Vec<V> q;
+    q.fill(0.f);
+    int imax[V], imin[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) imax[i] = -1, imin[i] = -1;
+    for (int k = 0; k < D; ++k) {
+      Vec<V> x;
+      x.load(p + (int64_t)k * F);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x.v[i], x.v[i]));
+        if (imax[i] < 0 && x.v[i] == mx.v[i]) imax[i] = k;
+        if (imin[i] < 0 && x.v[i] == mn.v[i]) imin[i] = k;
+      }
+    }
+    const float fd = (float)D;
+    Vec<V> base, cs;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float msq = __fdiv_rn(q.v[i], fd);
+      const float var = __fsub_rn(msq, __fmul_rn(mean.v[i], mean.v[i]));
+      base.v[i] = gmean.v[i] / fd;
+      cs.v[i] = var > 0.f ? gstd.v[i] / (fd * sd.v[i]) : 0.f;
+    }
+    // pass 2 (rows are L1/L2 resident from pass 1)
+    for (int k = 0; k < D; ++k) {
+      Vec<V> x, d;
+      x.load(p + (int64_t)k * F);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float r = base.v[i] + cs.v[i] * (x.v[i] - mean.v[i]);
+        if (k == imax[i]) r += gmax.v[i];
+        if (k == imin[i]) r += gmin.v[i];
+        d.v[i] = r;
+      }
+      d.store_cs(dp + (int64_t)k * F);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dgl.readout_nodes(graph, 'feat', op)  (models/pna.py:133, models/net3d.py:73)
+// ------------------------------------------------------------------------------------------------
+struct RoOps {
+  int n;
+  int op[4];
+};
+
+template <int V>
+__global__ void segment_readout_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ ptr,
+                                           int64_t B, int F, RoOps ops, float* __restrict__ out) {
+  const int FV = F / V;
+  const int64_t total = B * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = t / FV;
+    const int c0 = (int)(t - g * FV) * V;
+    const int32_t b = ptr[g], e = ptr[g + 1];
+    Vec<V> s, mx, mn;
+    s.fill(0.f), mx.fill(-INFINITY), mn.fill(INFINITY);
+    for (int32_t r = b; r < e; ++r) {
+      Vec<V> v;
+      v.load(x + (int64_t)r * ldx + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s.v[i] = __fadd_rn(s.v[i], v.v[i]);
+        mx.v[i] = fmaxf(mx.v[i], v.v[i]);
+        mn.v[i] = fminf(mn.v[i], v.v[i]);
+      }
+    }
+    const float cnt = (float)(e - b);
+    for (int j = 0; j < ops.n; ++j) {
+      Vec<V> o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float r;
+        if (e <= b) r = 0.f;
+        else if (ops.op[j] == I3D_RO_SUM) r = s.v[i];
+        else if (ops.op[j] == I3D_RO_MEAN) r = __fdiv_rn(s.v[i], cnt);
+        else if (ops.op[j] == I3D_RO_MAX) r = mx.v[i];
+        else r = mn.v[i];
+        o.v[i] = r;
+      }
+      o.store(out + g * (int64_t)(ops.n * F) + (int64_t)j * F + c0);
+    }
+  }
+}
+
+template <int V>
+__global__ void segment_readout_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, int ldx,
+                                           const float* __restrict__ out, const int32_t* __restrict__ ptr, int64_t B,
+                                           int F, RoOps ops, float* __restrict__ dx, int lddx) {
+  const int FV = F / V;
+  const int64_t total = B * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gi = t / FV;
+    const int c0 = (int)(t - gi * FV) * V;
+    const int32_t b = ptr[gi], e = ptr[gi + 1];
+    if (e <= b) continue;
+    const float cnt = (float)(e - b);
+    Vec<V> base, gmx, gmn, vmx, vmn;
+    base.fill(0.f), gmx.fill(0.f), gmn.fill(0.f), vmx.fill(0.f), vmn.fill(0.f);
+    bool has_max = false, has_min = false;
+    for (int j = 0; j < ops.n; ++j) {
+      Vec<V> gj, oj;
+      const int64_t off = gi * (int64_t)(ops.n * F) + (int64_t)j * F + c0;
+      gj.load(g + off);
+      oj.load(out + off);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if (ops.op[j] == I3D_RO_SUM) base.v[i] += gj.v[i];
+        else if (ops.op[j] == I3D_RO_MEAN) base.v[i] += gj.v[i] / cnt;
+        else if (ops.op[j] == I3D_RO_MAX) gmx.v[i] += gj.v[i], vmx.v[i] = oj.v[i];
+        else gmn.v[i] += gj.v[i], vmn.v[i] = oj.v[i];
+      }
+      has_max |= ops.op[j] == I3D_RO_MAX;
+      has_min |= ops.op[j] == I3D_RO_MIN;
+    }
+    bool done_max[V], done_min[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) done_max[i] = !has_max, done_min[i] = !has_min;
+    for (int32_t r = b; r < e; ++r) {
+      Vec<V> v, d;
+      v.load(x + (int64_t)r * ldx + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float acc = base.v[i];
+        if (!done_max[i] && v.v[i] == vmx.v[i]) acc += gmx.v[i], done_max[i] = true;
+        if (!done_min[i] && v.v[i] == vmn.v[i]) acc += gmn.v[i], done_min[i] = true;
+        d.v[i] = acc;
+      }
+      d.store(dx + (int64_t)r * lddx + c0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic CSR segment sum / mean with optional row indirection and addend
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void segment_sum_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rowptr,
+                                       const int32_t* __restrict__ idx, int64_t N, int F, int mean,
+                                       const float* __restrict__ addend, int lda, float* __restrict__ out, int ldo) {
+  const int FV = F / V;
+  const int64_t total = N * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / FV;
+    const int c0 = (int)(t - v * FV) * V;
+    const int32_t b = __ldg(rowptr + v), e = __ldg(rowptr + v + 1);
+    Vec<V> s;
+    s.fill(0.f);
+    for (int32_t k = b; k < e; ++k) {
+      const int64_t row = idx ? (int64_t)__ldg(idx + k) : (int64_t)k;
+      Vec<V> xv;
+      xv.load(x + row * ldx + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s.v[i] = __fadd_rn(s.v[i], xv.v[i]);
+    }
+    if (mean) {
+      const float d = (float)max(e - b, 1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s.v[i] = __fdiv_rn(s.v[i], d);
+    }
+    if (addend) {
+      Vec<V> a;
+      a.load(addend + v * (int64_t)lda + c0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s.v[i] = __fadd_rn(s.v[i], a.v[i]);
+    }
+    s.store(out + v * (int64_t)ldo + c0);
+  }
+}
+
+template <int V>
+__global__ void segment_sum_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ rowptr,
+                                       const int32_t* __restrict__ rowid, int64_t E, int F, int mean,
+                                       float* __restrict__ gx) {
+  const int FV = F / V;
+  const int64_t total = E * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = t / FV;
+    const int c0 = (int)(t - k * FV) * V;
+    const int32_t v = __ldg(rowid + k);
+    Vec<V> gv;
+    gv.load(g + (int64_t)v * F + c0);
+    if (mean) {
+      const float d = (float)max(__ldg(rowptr + v + 1) - __ldg(rowptr + v), 1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) gv.v[i] = __fdiv_rn(gv.v[i], d);
+    }
+    gv.store(gx + k * F + c0);
+  }
+}
+
+}  // namespace i3d
+
+using namespace i3d;
+
+#define I3D_DISPATCH_VEC(vec_ok, KERNEL, grid, block, stream, ...)          \
+  do {                                                                       \
+    if (vec_ok)                                                              \
+      KERNEL<4><<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
+    else                                                                     \
+      KERNEL<1><<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
+  } while (0)
+
+extern "C" {
+
+int i3d_embed_sum_fwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
+                      const float* table, int F, float* out, void* stream) {
+  I3D_REQUIRE(R >= 0 && C > 0 && F > 0 && col_off && table && (R == 0 || (idx && out)), "invalid argument");
+  if (R == 0) return I3D_OK;
+  const bool v4 = can_vec4({table, out}, {F});
+  const int64_t work = R * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, embed_sum_fwd_kernel, grid_for(work, 256), 256, as_stream(stream), idx, R, C, col_off, perm,
+                   table, F, out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_embed_sum_bwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
+                      const float* gout, int F, float* gtable, void* stream) {
+  I3D_REQUIRE(R >= 0 && C > 0 && F > 0 && col_off && gtable && (R == 0 || (idx && gout)), "invalid argument");
+  if (R == 0) return I3D_OK;
+  const bool v4 = can_vec4({gout}, {F});
+  const int64_t work = R * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, embed_sum_bwd_kernel, grid_for(work, 256), 256, as_stream(stream), idx, R, C, col_off, perm,
+                   gout, F, gtable);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_pna_aggregate_fwd(const float* msg, const int32_t* rowptr, int64_t N, int F, float* out, int ldo,
+                          void* stream) {
+  I3D_REQUIRE(N >= 0 && F > 0 && ldo >= 4 * F && rowptr && (N == 0 || out), "invalid argument");
+  if (N == 0) return I3D_OK;
+  const bool v4 = can_vec4({msg, out}, {F, ldo});
+  const int64_t work = N * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, pna_aggregate_fwd_kernel, grid_for(work, 256, 8), 256, as_stream(stream), msg, rowptr, N, F, out,
+                   ldo);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_pna_aggregate_bwd(const float* g, int ldg, const float* msg, const float* out, int ldo,
+                          const int32_t* rowptr, int64_t N, int F, float* dmsg, void* stream) {
+  I3D_REQUIRE(N >= 0 && F > 0 && ldo >= 4 * F && ldg >= 4 * F && rowptr && (N == 0 || (g && out)),
+              "invalid argument");
+  if (N == 0) return I3D_OK;
+  const bool v4 = can_vec4({g, msg, out, dmsg}, {F, ldo, ldg});
+  const int64_t work = N * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, pna_aggregate_bwd_kernel, grid_for(work, 256, 8), 256, as_stream(stream), g, ldg, msg, out, ldo,
+                   rowptr, N, F, dmsg);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+static int make_ops(int n_ops, const int32_t* ops, RoOps* r) {
+  if (n_ops < 1 || n_ops > 4 || !ops) return -1;
+  r->n = n_ops;
+  for (int i = 0; i < 4; ++i) r->op[i] = i < n_ops ? ops[i] : 0;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i] < 0 || ops[i] > 3) return -1;
+  return 0;
+}
+
+int i3d_segment_readout_fwd(const float* x, int ldx, const int32_t* ptr, int64_t B, int F, int n_ops,
+                            const int32_t* ops, float* out, void* stream) {
+  RoOps r;
+  I3D_REQUIRE(B >= 0 && F > 0 && ldx >= F && ptr && make_ops(n_ops, ops, &r) == 0, "invalid argument");
+  if (B == 0) return I3D_OK;
+  const bool v4 = can_vec4({x, out}, {F, ldx});
+  const int64_t work = B * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, segment_readout_fwd_kernel, grid_for(work, 128), 128, as_stream(stream), x, ldx, ptr, B, F, r,
+                   out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_segment_readout_bwd(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
+                            int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, void* stream) {
+  RoOps r;
+  I3D_REQUIRE(B >= 0 && F > 0 && ldx >= F && lddx >= F && ptr && make_ops(n_ops, ops, &r) == 0, "invalid argument");
+  if (B == 0) return I3D_OK;
+  const bool v4 = can_vec4({g, x, out, dx}, {F, ldx, lddx});
+  const int64_t work = B * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, segment_readout_bwd_kernel, grid_for(work, 128), 128, as_stream(stream), g, x, ldx, out, ptr, B,
+                   F, r, dx, lddx);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_segment_sum_fwd(const float* x, int ldx, const int32_t* rowptr, const int32_t* idx, int64_t N, int F,
+                        int mean, const float* addend, int lda, float* out, int ldo, void* stream) {
+  I3D_REQUIRE(N >= 0 && F > 0 && ldx >= F && ldo >= F && rowptr && (N == 0 || out), "invalid argument");
+  if (N == 0) return I3D_OK;
+  const bool v4 = can_vec4({x, addend, out}, {F, ldx, ldo, addend ? lda : 0});
+  const int64_t work = N * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, segment_sum_fwd_kernel, grid_for(work, 256), 256, as_stream(stream), x, ldx, rowptr, idx, N, F,
+                   mean, addend, lda, out, ldo);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_segment_sum_bwd(const float* g, const int32_t* rowptr, const int32_t* rowid, int64_t E, int F, int mean,
+                        float* gx, void* stream) {
+  I3D_REQUIRE(E >= 0 && F > 0 && rowptr && (E == 0 || (g && rowid && gx)), "invalid argument");
+  if (E == 0) return I3D_OK;
+  const bool v4 = can_vec4({g, gx}, {F});
+  const int64_t work = E * (F / (v4 ? 4 : 1));
+  I3D_DISPATCH_VEC(v4, segment_sum_bwd_kernel, grid_for(work, 256), 256, as_stream(stream), g, rowptr, rowid, E, F,
+                   mean, gx);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+}

@@ -1,0 +1,368 @@
+"""Typed tensor-level wrappers around the C ABI (one Python function per entry point of include/i3d.h).
+
+torch is used here for what the task calls plumbing only: device allocations (``torch.empty``),
+the current CUDA stream and raw ``data_ptr()``s.  No wrapper computes anything with torch ops.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+ACT = {"none": 0, "relu": 1, "silu": 2}
+RO = {"sum": 0, "mean": 1, "max": 2, "min": 3}
+NT, NN, TN = 0, 1, 2
+
+
+def _L():
+    return _lib.load()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the 3dinfomax_b200 path has no CPU fallback" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _mat(t, name):
+    """2-D fp32 tensor with unit inner stride -> (ptr, ld)."""
+    _req(t, torch.float32, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("%s must be 2-D with unit inner stride" % name)
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def _vec(t, dtype, name):
+    _req(t, dtype, name)
+    if t is not None and not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return _p(t)
+
+
+# ---------------------------------------------------------------------------------------- graph
+def csr_build(key, other, n_rows):
+    """Stable CSR by ``key``.  Returns (rowptr[N+1], col[E], rowid[E], eid[E]) int32."""
+    E = key.numel()
+    dev = key.device
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    rowid = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+    if key.dtype == torch.int64:
+        fn = _L().i3d_csr_build
+        _vec(key, torch.int64, "key"), _vec(other, torch.int64, "other")
+    else:
+        fn = _L().i3d_csr_build_i32
+        _vec(key, torch.int32, "key"), _vec(other, torch.int32, "other")
+    _lib.check(fn(_p(key), _p(other), E, n_rows, _p(rowptr), _p(col), _p(rowid), _p(eid), _p(ws), _s()),
+               "i3d_csr_build")
+    return rowptr, col, rowid, eid
+
+
+def segment_ptr(counts):
+    _vec(counts, torch.int64, "counts")
+    B = counts.numel()
+    ptr = torch.empty(B + 1, dtype=torch.int32, device=counts.device)
+    _lib.check(_L().i3d_segment_ptr(_p(counts), B, _p(ptr), _s()), "i3d_segment_ptr")
+    return ptr
+
+
+def degree_scalers(rowptr):
+    N = rowptr.numel() - 1
+    amp = torch.empty(N, dtype=torch.float32, device=rowptr.device)
+    att = torch.empty(N, dtype=torch.float32, device=rowptr.device)
+    _lib.check(_L().i3d_degree_scalers(_p(rowptr), N, _p(amp), _p(att), _s()), "i3d_degree_scalers")
+    return amp, att
+
+
+# ------------------------------------------------------------------------------------ embedding
+def embed_sum_fwd(idx, col_off, perm, table):
+    _vec(idx, torch.int64, "idx"), _vec(col_off, torch.int32, "col_off"), _vec(perm, torch.int32, "perm")
+    _vec(table, torch.float32, "table")
+    R = idx.shape[0] if perm is None else perm.numel()
+    C, F = idx.shape[1], table.shape[1]
+    out = torch.empty(R, F, dtype=torch.float32, device=table.device)
+    _lib.check(_L().i3d_embed_sum_fwd(_p(idx), R, C, _p(col_off), _p(perm), _p(table), F, _p(out), _s()),
+               "i3d_embed_sum_fwd")
+    return out
+
+
+def embed_sum_bwd(idx, col_off, perm, gout, n_table_rows):
+    gout = gout.contiguous()
+    R, F = gout.shape
+    C = idx.shape[1]
+    gtable = torch.zeros(n_table_rows, F, dtype=torch.float32, device=gout.device)
+    _lib.check(_L().i3d_embed_sum_bwd(_p(idx), R, C, _p(col_off), _p(perm), _p(gout), F, _p(gtable), _s()),
+               "i3d_embed_sum_bwd")
+    return gtable
+
+
+# ----------------------------------------------------------------------------------------- gemm
+def gemm(mode, M, N, segs, C, bias=None, accumulate=False):
+    """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld)."""
+    arr = (_lib.gemm_seg * len(segs))()
+    keep = []
+    for i, s in enumerate(segs):
+        pa, lda = _mat(s["A"], "A")
+        pb, ldb = _mat(s["B"], "B")
+        arr[i].A, arr[i].B = pa, pb
+        arr[i].a_idx = _vec(s.get("a_idx"), torch.int32, "a_idx")
+        arr[i].b_idx = _vec(s.get("b_idx"), torch.int32, "b_idx")
+        arr[i].scale = _vec(s.get("scale"), torch.float32, "scale")
+        arr[i].K, arr[i].lda, arr[i].ldb = int(s["K"]), int(lda), int(ldb)
+        keep.append(s)
+    pc, ldc = _mat(C, "C")
+    _lib.check(_L().i3d_gemm(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                             1 if accumulate else 0, _s()), "i3d_gemm")
+    return C
+
+
+# ------------------------------------------------------------------------------ FC tail (act+BN)
+def act_colstats(Y, act):
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    sums = torch.empty(2 * F, dtype=torch.float64, device=Y.device)
+    _lib.check(_L().i3d_act_colstats(py, M, F, ldy, act, _p(sums), _s()), "i3d_act_colstats")
+    return sums
+
+
+def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum, eps, training, residual, out=None):
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    O = torch.empty(M, F, dtype=torch.float32, device=Y.device) if out is None else out
+    po, ldo = _mat(O, "O")
+    if residual is not None:
+        pr, ldr = _mat(residual, "residual")
+        if ldr != ldo:
+            raise ValueError("residual must share the output's leading dimension")
+    else:
+        pr = None
+    save = torch.empty(2 * F, dtype=torch.float32, device=Y.device)
+    _lib.check(_L().i3d_bn_apply(py, M, F, ldy, act, _p(sums), _p(running_mean), _p(running_var), _p(nbt),
+                                 _p(gamma), _p(beta), float(momentum), float(eps), 1 if training else 0, _p(save),
+                                 pr, po, ldo, _s()), "i3d_bn_apply")
+    return O, save
+
+
+def bn_bwd_reduce(dO, Y, act, save):
+    pd, ldd = _mat(dO, "dO")
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    sums2 = torch.empty(2 * F, dtype=torch.float64, device=Y.device)
+    _lib.check(_L().i3d_bn_bwd_reduce(pd, ldd, py, ldy, M, F, act, _p(save), _p(sums2), _s()), "i3d_bn_bwd_reduce")
+    return sums2
+
+
+def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True):
+    pd, ldd = _mat(dO, "dO")
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    dev = Y.device
+    dY = torch.empty(M, F, dtype=torch.float32, device=dev)
+    dbias = torch.zeros(F, dtype=torch.float32, device=dev) if want_dbias else None
+    dgamma = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
+    dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
+    _lib.check(_L().i3d_bn_bwd_apply(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,
+                                     _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), _p(dgamma), _p(dbeta),
+                                     _s()), "i3d_bn_bwd_apply")
+    return dY, dbias, dgamma, dbeta
+
+
+def act_fwd(x, act):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_L().i3d_act_fwd(_p(x), x.numel(), act, _p(y), _s()), "i3d_act_fwd")
+    return y
+
+
+def act_bwd(gy, x, act):
+    gy = gy.contiguous()
+    gx = torch.empty_like(x)
+    _lib.check(_L().i3d_act_bwd(_p(gy), _p(x), x.numel(), act, _p(gx), _s()), "i3d_act_bwd")
+    return gx
+
+
+# ------------------------------------------------------------------------------------ aggregation
+def pna_aggregate_fwd(msg, rowptr):
+    _vec(msg, torch.float32, "msg")
+    N = rowptr.numel() - 1
+    F = msg.shape[1]
+    out = torch.empty(N, 4 * F, dtype=torch.float32, device=msg.device)
+    _lib.check(_L().i3d_pna_aggregate_fwd(_p(msg), _p(rowptr), N, F, _p(out), 4 * F, _s()), "i3d_pna_aggregate_fwd")
+    return out
+
+
+def pna_aggregate_bwd(g, msg, out, rowptr):
+    pg, ldg = _mat(g, "g")
+    N = rowptr.numel() - 1
+    F = msg.shape[1]
+    dmsg = torch.empty_like(msg)
+    _lib.check(_L().i3d_pna_aggregate_bwd(pg, ldg, _p(msg), _p(out), 4 * F, _p(rowptr), N, F, _p(dmsg), _s()),
+               "i3d_pna_aggregate_bwd")
+    return dmsg
+
+
+def _ops_arr(ops):
+    return (ctypes.c_int32 * len(ops))(*ops)
+
+
+def segment_readout_fwd(x, ptr, ops):
+    px, ldx = _mat(x, "x")
+    B = ptr.numel() - 1
+    F = x.shape[1]
+    out = torch.empty(B, len(ops) * F, dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_segment_readout_fwd(px, ldx, _p(ptr), B, F, len(ops), ctypes.cast(_ops_arr(ops), ctypes.c_void_p),
+                                            _p(out), _s()), "i3d_segment_readout_fwd")
+    return out
+
+
+def segment_readout_bwd(g, x, out, ptr, ops):
+    g = g.contiguous()
+    px, ldx = _mat(x, "x")
+    B = ptr.numel() - 1
+    F = x.shape[1]
+    dx = torch.empty(x.shape[0], F, dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_segment_readout_bwd(_p(g), px, ldx, _p(out), _p(ptr), B, F, len(ops),
+                                            ctypes.cast(_ops_arr(ops), ctypes.c_void_p), _p(dx), F, _s()),
+               "i3d_segment_readout_bwd")
+    return dx
+
+
+def segment_sum_fwd(x, rowptr, idx=None, mean=False, addend=None):
+    px, ldx = _mat(x, "x")
+    N = rowptr.numel() - 1
+    F = x.shape[1]
+    out = torch.empty(N, F, dtype=torch.float32, device=x.device)
+    pa, lda = (None, 0) if addend is None else _mat(addend, "addend")
+    _lib.check(_L().i3d_segment_sum_fwd(px, ldx, _p(rowptr), _vec(idx, torch.int32, "idx"), N, F, 1 if mean else 0,
+                                        pa, lda, _p(out), F, _s()), "i3d_segment_sum_fwd")
+    return out
+
+
+def segment_sum_bwd(g, rowptr, rowid, mean=False):
+    g = g.contiguous()
+    E = rowid.numel()
+    F = g.shape[1]
+    gx = torch.empty(E, F, dtype=torch.float32, device=g.device)
+    _lib.check(_L().i3d_segment_sum_bwd(_p(g), _p(rowptr), _p(rowid), E, F, 1 if mean else 0, _p(gx), _s()),
+               "i3d_segment_sum_bwd")
+    return gx
+
+
+# ----------------------------------------------------------------------------------------- net3d
+def fourier_encode(dist, perm, k):
+    _vec(dist, torch.float32, "dist")
+    E = dist.numel() if perm is None else perm.numel()
+    out = torch.empty(E, 2 * k + 1, dtype=torch.float32, device=dist.device)
+    _lib.check(_L().i3d_fourier_encode(_p(dist), _vec(perm, torch.int32, "perm"), E, k, _p(out), _s()),
+               "i3d_fourier_encode")
+    return out
+
+
+def soft_gate_fwd(msg, ws, bs):
+    _vec(msg, torch.float32, "msg"), _vec(ws, torch.float32, "ws"), _vec(bs, torch.float32, "bs")
+    E, H = msg.shape
+    m = torch.empty_like(msg)
+    w = torch.empty(E, dtype=torch.float32, device=msg.device)
+    _lib.check(_L().i3d_soft_gate_fwd(_p(msg), E, H, _p(ws), _p(bs), _p(m), _p(w), _s()), "i3d_soft_gate_fwd")
+    return m, w
+
+
+def soft_gate_bwd(gm, msg, w, ws):
+    gm = gm.contiguous()
+    E, H = msg.shape
+    gmsg = torch.empty_like(msg)
+    gws = torch.zeros(H, dtype=torch.float32, device=msg.device)
+    gbs = torch.zeros(1, dtype=torch.float32, device=msg.device)
+    _lib.check(_L().i3d_soft_gate_bwd(_p(gm), _p(msg), _p(w), E, H, _p(ws), _p(gmsg), _p(gws), _p(gbs), _s()),
+               "i3d_soft_gate_bwd")
+    return gmsg, gws, gbs
+
+
+def broadcast_rows(vec, M):
+    _vec(vec, torch.float32, "vec")
+    F = vec.numel()
+    out = torch.empty(M, F, dtype=torch.float32, device=vec.device)
+    _lib.check(_L().i3d_broadcast_rows(_p(vec), M, F, _p(out), _s()), "i3d_broadcast_rows")
+    return out
+
+
+def colsum(x):
+    px, ldx = _mat(x, "x")
+    M, F = x.shape
+    out = torch.empty(F, dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_colsum(px, ldx, M, F, _p(out), _s()), "i3d_colsum")
+    return out
+
+
+def add(a, b):
+    a, b = a.contiguous(), b.contiguous()
+    y = torch.empty_like(a)
+    _lib.check(_L().i3d_add(_p(a), _p(b), a.numel(), _p(y), _s()), "i3d_add")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ loss
+def row_norms(z):
+    _vec(z, torch.float32, "z")
+    R, D = z.shape
+    out = torch.empty(R, dtype=torch.float32, device=z.device)
+    _lib.check(_L().i3d_row_norms(_p(z), R, D, _p(out), _s()), "i3d_row_norms")
+    return out
+
+
+def ntxent_rows_fwd(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset):
+    rowstats = torch.empty(B, 2, dtype=torch.float32, device=P.device)
+    loss_rows = torch.empty(B, dtype=torch.float32, device=P.device)
+    _lib.check(_L().i3d_ntxent_rows_fwd(_p(P), B, Bc, C, _p(n1), _p(n2), 1 if norm else 0, float(eps), float(tau),
+                                        int(row_offset), _p(rowstats), _p(loss_rows), _s()), "i3d_ntxent_rows_fwd")
+    return rowstats, loss_rows
+
+
+def sum_scaled(x, scale):
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_sum_scaled(_p(x), x.numel(), float(scale), _p(out), _s()), "i3d_sum_scaled")
+    return out
+
+
+def ntxent_rows_bwd(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset, rowstats, gout, inv_B):
+    dn1 = torch.empty(B, dtype=torch.float32, device=P.device) if norm else None
+    dn2 = torch.zeros(Bc * C, dtype=torch.float32, device=P.device) if norm else None
+    _lib.check(_L().i3d_ntxent_rows_bwd(_p(P), B, Bc, C, _p(n1), _p(n2), 1 if norm else 0, float(eps), float(tau),
+                                        int(row_offset), _p(rowstats), _p(gout), float(inv_B), _p(dn1), _p(dn2),
+                                        _s()), "i3d_ntxent_rows_bwd")
+    return dn1, dn2
+
+
+def norm_bwd_accum(z, norms, dn, dz):
+    R, D = z.shape
+    _lib.check(_L().i3d_norm_bwd_accum(_p(z), _p(norms), _p(dn), R, D, _p(dz), _s()), "i3d_norm_bwd_accum")
+    return dz
+
+
+# ------------------------------------------------------------------------------------- optimizer
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, grad_scale, step, hyper_dev=None, step_dev=None):
+    _lib.check(_L().i3d_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                  float(eps), float(weight_decay), float(grad_scale), int(step), _p(hyper_dev),
+                                  _p(step_dev), _s()), "i3d_adam_step")
+
+
+def add_i64(x, delta):
+    _lib.check(_L().i3d_add_i64(_p(x), int(delta), _s()), "i3d_add_i64")
+
+
+def multi_copy(ptrs, off, length, flat, to_flat):
+    _lib.check(_L().i3d_multi_copy(_p(ptrs), _p(off), _p(length), ptrs.numel(), _p(flat), 1 if to_flat else 0, _s()),
+               "i3d_multi_copy")

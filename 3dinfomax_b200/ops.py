@@ -1,0 +1,320 @@
+"""Differentiable operators of the hot path: ``torch.autograd.Function`` shells whose forward AND backward
+are sequences of lib3dinfomax_b200 kernel launches (3dinfomax_b200/kernels.py).  autograd is used as the tape only.
+
+The central one is ``fc``: the reference's FCLayer (models/base_layers.py:100-111) applied to a *virtual*
+concatenation of K-segments, each optionally row-gathered and row-scaled, so that
+``cat([h[src], h[dst], e])`` (models/pna.py:249) and ``cat([h, agg, agg*amp, agg*att])``
+(models/pna.py:207,232) are never materialised.
+"""
+import torch
+
+from . import kernels as K
+
+
+class Seg:
+    """One K-segment of an FC input.
+
+    x            [R, K] fp32
+    idx          optional int32 [M]: output row m reads x[idx[m]]
+    scale        optional fp32 [M]: per-output-row multiplier (degree scaler)
+    inv_rowptr   for gathered segments: CSR over R whose row r lists the output rows m with idx[m]==r
+    inv_idx      optional position map of that CSR (None: the output rows of r are contiguous)
+    """
+    __slots__ = ("x", "idx", "scale", "inv_rowptr", "inv_idx")
+
+    def __init__(self, x, idx=None, scale=None, inv_rowptr=None, inv_idx=None):
+        if idx is not None and inv_rowptr is None:
+            raise ValueError("a gathered segment needs its inverse CSR for the backward pass")
+        if idx is not None and scale is not None:
+            raise ValueError("gather and scale cannot be combined on one segment")
+        self.x, self.idx, self.scale, self.inv_rowptr, self.inv_idx = x, idx, scale, inv_rowptr, inv_idx
+
+
+class FCConfig:
+    __slots__ = ("segs", "act", "has_bn", "training", "running_mean", "running_var", "nbt", "momentum", "eps")
+
+    def __init__(self, segs, act, has_bn, training, running_mean=None, running_var=None, nbt=None, momentum=0.1,
+                 eps=1e-5):
+        self.segs, self.act, self.has_bn, self.training = segs, act, has_bn, training
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
+        self.momentum, self.eps = momentum, eps
+
+
+class _FC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, W, b, gamma, beta, residual, *xs):
+        segs = cfg.segs
+        M = segs[0].idx.numel() if segs[0].idx is not None else xs[0].shape[0]
+        Fout = W.shape[0]
+        Y = torch.empty(M, Fout, dtype=torch.float32, device=W.device)
+        gsegs, off = [], 0
+        for s, x in zip(segs, xs):
+            k = x.shape[1]
+            gsegs.append({"A": x, "B": W[:, off:off + k], "K": k, "a_idx": s.idx, "scale": s.scale})
+            off += k
+        if off != W.shape[1]:
+            raise ValueError("segment widths %d do not add up to the weight's in_features %d" % (off, W.shape[1]))
+        K.gemm(K.NT, M, Fout, gsegs, Y, bias=b)
+        save = None
+        if cfg.has_bn:
+            sums = K.act_colstats(Y, cfg.act) if cfg.training else None
+            O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
+                                 cfg.momentum, cfg.eps, cfg.training, residual)
+        else:
+            O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
+            if residual is not None:
+                O = K.add(O, residual)
+        ctx.cfg = cfg
+        ctx.M = M
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(W, Y, save, gamma, *xs)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        cfg = ctx.cfg
+        W, Y, save, gamma = ctx.saved_tensors[:4]
+        xs = ctx.saved_tensors[4:]
+        segs = cfg.segs
+        M, Fout = ctx.M, W.shape[0]
+        if dO.dim() != 2 or dO.stride(1) != 1:
+            dO = dO.contiguous()
+        need_b = ctx.needs_input_grad[2]
+        dgamma = dbeta = None
+        if cfg.has_bn:
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save)
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b)
+        elif cfg.act != 0:
+            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
+        else:
+            dY = dO
+            db = K.colsum(dO) if need_b else None
+        # weight gradient, one column block per segment: dW[:, off:off+k] = dY^T (scale * gather(x))
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            off = 0
+            for s, x in zip(segs, xs):
+                k = x.shape[1]
+                K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
+                       dW[:, off:off + k])
+                off += k
+        # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
+        dxs = [None] * len(xs)
+        groups = {}
+        off = 0
+        for i, (s, x) in enumerate(zip(segs, xs)):
+            k = x.shape[1]
+            if ctx.needs_input_grad[6 + i]:
+                groups.setdefault(x.data_ptr(), []).append((i, s, x, off))
+            off += k
+        for members in groups.values():
+            x0 = members[0][2]
+            R, k = x0.shape
+            dx = torch.empty(R, k, dtype=torch.float32, device=W.device)
+            nn = []
+            for (_i, s, _x, o) in members:
+                if s.idx is None:
+                    a = dY
+                else:
+                    a = K.segment_sum_fwd(dY, s.inv_rowptr, s.inv_idx)
+                nn.append({"A": a, "B": W[:, o:o + k], "K": Fout, "scale": s.scale})
+            K.gemm(K.NN, R, k, nn, dx)
+            dxs[members[0][0]] = dx
+        dres = dO if (ctx.has_res and ctx.needs_input_grad[5]) else None
+        return (None, dW, db, dgamma, dbeta, dres) + tuple(dxs)
+
+
+def fc(segs, W, b, act, bn=None, training=True, residual=None):
+    """FCLayer over a virtual concat.  ``bn``: None or (gamma, beta, running_mean, running_var, nbt, momentum, eps)."""
+    if bn is None:
+        cfg = FCConfig(segs, act, False, training)
+        gamma = beta = None
+    else:
+        gamma, beta, rm, rv, nbt, mom, eps = bn
+        cfg = FCConfig(segs, act, True, training, rm, rv, nbt, mom, eps)
+    return _FC.apply(cfg, W, b, gamma, beta, residual, *[s.x for s in segs])
+
+
+class _EmbedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, col_off, perm, table):
+        ctx.save_for_backward(idx, col_off, perm)
+        ctx.rows = table.shape[0]
+        return K.embed_sum_fwd(idx, col_off, perm, table)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, col_off, perm = ctx.saved_tensors
+        return None, None, None, K.embed_sum_bwd(idx, col_off, perm, g, ctx.rows)
+
+
+def embed_sum(idx, col_off, perm, table):
+    return _EmbedSum.apply(idx, col_off, perm, table)
+
+
+class _PNAAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, msg, rowptr):
+        out = K.pna_aggregate_fwd(msg, rowptr)
+        ctx.save_for_backward(msg, out, rowptr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        msg, out, rowptr = ctx.saved_tensors
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        return K.pna_aggregate_bwd(g, msg, out, rowptr), None
+
+
+def pna_aggregate(msg, rowptr):
+    """[E,F] CSR-ordered messages -> [N,4F] = [mean|max|min|std] (models/pna.py:17-37,221-235)."""
+    return _PNAAggregate.apply(msg, rowptr)
+
+
+class _Readout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ptr, ops):
+        out = K.segment_readout_fwd(x, ptr, ops)
+        ctx.ops = ops
+        ctx.save_for_backward(x, out, ptr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, ptr = ctx.saved_tensors
+        return K.segment_readout_bwd(g, x, out, ptr, ctx.ops), None, None
+
+
+def readout(x, graph_ptr, ops):
+    """cat([dgl.readout_nodes(g,'feat',op) for op in ops]) (models/pna.py:133-134)."""
+    return _Readout.apply(x, graph_ptr, tuple(K.RO[o] for o in ops))
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rowptr, rowid, mean, addend):
+        ctx.mean = mean
+        ctx.has_add = addend is not None
+        ctx.save_for_backward(rowptr, rowid)
+        return K.segment_sum_fwd(x, rowptr, None, mean, addend)
+
+    @staticmethod
+    def backward(ctx, g):
+        rowptr, rowid = ctx.saved_tensors
+        g = g.contiguous()
+        return K.segment_sum_bwd(g, rowptr, rowid, ctx.mean), None, None, None, (g if ctx.has_add else None)
+
+
+def segment_reduce(x_csr, rowptr, rowid, mean, addend=None):
+    """fn.sum / fn.mean over in-edges (models/net3d.py:94-96) fused with the ``m_sum + feat`` add (net3d.py:122)."""
+    return _SegmentReduce.apply(x_csr, rowptr, rowid, bool(mean), addend)
+
+
+class _SoftGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, msg, ws, bs):
+        m, w = K.soft_gate_fwd(msg, ws, bs)
+        ctx.save_for_backward(msg, w, ws)
+        return m
+
+    @staticmethod
+    def backward(ctx, gm):
+        msg, w, ws = ctx.saved_tensors
+        gmsg, gws, gbs = K.soft_gate_bwd(gm, msg, w, ws)
+        return gmsg, gws.view_as(ws), gbs
+
+
+def soft_gate(msg, weight, bias):
+    """message * sigmoid(soft_edge_network(message)) (models/net3d.py:117-118)."""
+    return _SoftGate.apply(msg, weight, bias)
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        ctx.act = act
+        ctx.save_for_backward(x)
+        return K.act_fwd(x, act)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return K.act_bwd(g, x, ctx.act), None
+
+
+def activation(x, name):
+    return _Act.apply(x, K.ACT[name])
+
+
+class _Broadcast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, M):
+        return K.broadcast_rows(vec, M)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.colsum(g.contiguous()), None
+
+
+def broadcast_rows(vec, M):
+    """node_embedding[None, :].expand(N, -1) (models/net3d.py:61)."""
+    return _Broadcast.apply(vec, M)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return K.add(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _NTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, C, tau, norm, eps, row_offset, inv_B):
+        z1 = z1.contiguous()
+        z2 = z2.contiguous()
+        B, D = z1.shape
+        Bc = z2.shape[0] // C
+        n1 = K.row_norms(z1) if norm else None
+        n2 = K.row_norms(z2) if norm else None
+        P = torch.empty(B, Bc * C, dtype=torch.float32, device=z1.device)
+        K.gemm(K.NT, B, Bc * C, [{"A": z1, "B": z2, "K": D}], P)
+        rowstats, loss_rows = K.ntxent_rows_fwd(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset)
+        loss = K.sum_scaled(loss_rows, inv_B)
+        ctx.args = (B, Bc, C, D, tau, norm, eps, row_offset, inv_B)
+        ctx.save_for_backward(z1, z2, n1, n2, P, rowstats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        z1, z2, n1, n2, P, rowstats = ctx.saved_tensors
+        B, Bc, C, D, tau, norm, eps, row_offset, inv_B = ctx.args
+        gout = gout.contiguous().float()
+        G = P.clone() if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] else None
+        dn1, dn2 = K.ntxent_rows_bwd(G, B, Bc, C, n1, n2, norm, eps, tau, row_offset, rowstats, gout, inv_B)
+        dz1 = torch.empty_like(z1)
+        K.gemm(K.NN, B, D, [{"A": G, "B": z2, "K": Bc * C}], dz1)
+        dz2 = torch.empty_like(z2)
+        K.gemm(K.TN, Bc * C, D, [{"A": G, "B": z1, "K": B}], dz2)
+        if norm:
+            K.norm_bwd_accum(z1, n1, dn1, dz1)
+            K.norm_bwd_accum(z2, n2, dn2, dz2)
+        return dz1, dz2, None, None, None, None, None, None
+
+
+def ntxent(z1, z2, conformers, tau, norm, eps, row_offset=0, total_rows=None):
+    """-mean_i log(pos_i / neg_i) over exp(sim/tau) (commons/losses.py:143-155, 225-246).
+
+    z1 [B,D] are the local rows, z2 [Bc*C, D] the (possibly all-gathered) columns, molecule-major."""
+    B = z1.shape[0]
+    inv_B = 1.0 / float(total_rows if total_rows is not None else B)
+    return _NTXent.apply(z1, z2, int(conformers), float(tau), bool(norm), float(eps), int(row_offset), inv_B)

@@ -1,0 +1,159 @@
+"""``PNA`` — drop-in for the reference's ``model_type: 'PNA'`` (models/pna.py:90-252) on B200.
+
+Same constructor kwargs (unknown ones swallowed by ``**kwargs``, models/pna.py:115), same state-dict keys
+(SURVEY.md §8b), same input contract (a batched graph with int64 ``ndata['feat']`` [N,9] and
+``edata['feat']`` [E,3]) and the same visible side effect (``ndata['feat']`` ends as the final node states).
+
+Per layer (models/pna.py:199-213), in kernels:
+  pretrans   : ONE gather-fused GEMM over the virtual cat[h[src], h[dst], e] -> ReLU/BN -> GEMM -> BN
+               (edge rows are produced directly in CSR order, so each node's mailbox is contiguous);
+  aggregate  : ONE segmented reduction writing [mean|max|min|std]  (replaces DGL degree bucketing, ~25 launches
+               per distinct degree plus a host sync);
+  posttrans  : ONE GEMM over the virtual cat[h, agg, agg*ln(D+1), agg/ln(D+1)] (degree scalers applied to the
+               operand tile as it is staged, never materialised) -> BN -> + residual.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from .base_layers import MLP
+from .graph import graph_structure
+from .synthetic import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS
+
+_AGG_ORDER = ["mean", "max", "min", "std"]
+_SCALER_ORDER = ["identity", "amplification", "attenuation"]
+
+
+class _SummedEmbedding(nn.Module):
+    """Sum of per-column embeddings (commons/mol_encoder.py:10-73) evaluated by one gather-sum kernel."""
+
+    def __init__(self, dims, emb_dim, list_name):
+        super().__init__()
+        tables = nn.ModuleList()
+        for d in dims:
+            e = nn.Embedding(d, emb_dim)
+            nn.init.xavier_uniform_(e.weight.data)          # mol_encoder.py:27,62
+            tables.append(e)
+        setattr(self, list_name, tables)
+        self._list_name = list_name
+        offs, acc = [], 0
+        for d in dims:
+            offs.append(acc)
+            acc += d
+        self.register_buffer("_col_off", torch.tensor(offs, dtype=torch.int32), persistent=False)
+
+    def forward(self, idx, perm=None):
+        tables = getattr(self, self._list_name)
+        # pointer plumbing only: one contiguous table so the kernel takes a single base pointer; autograd's
+        # cat backward splits the table gradient back onto the per-column nn.Embedding weights
+        table = torch.cat([e.weight for e in tables], dim=0)
+        return ops.embed_sum(idx.contiguous(), self._col_off, perm, table)
+
+
+class AtomEncoder(_SummedEmbedding):
+    def __init__(self, emb_dim):
+        super().__init__(ATOM_FEATURE_DIMS, emb_dim, "atom_embedding_list")
+
+
+class BondEncoder(_SummedEmbedding):
+    def __init__(self, emb_dim):
+        super().__init__(BOND_FEATURE_DIMS, emb_dim, "bond_embedding_list")
+
+
+class PNALayer(nn.Module):
+    def __init__(self, in_dim, out_dim, in_dim_edges, aggregators, scalers, activation="relu",
+                 last_activation="none", dropout=0.0, residual=True, pairwise_distances=False, mid_batch_norm=False,
+                 last_batch_norm=False, batch_norm_momentum=0.1, avg_d=None, posttrans_layers=2, pretrans_layers=1):
+        super().__init__()
+        if list(aggregators) != _AGG_ORDER:
+            raise NotImplementedError("fused aggregation kernel implements aggregators %s (every shipped config); "
+                                      "got %s" % (_AGG_ORDER, list(aggregators)))
+        if list(scalers) != _SCALER_ORDER:
+            raise NotImplementedError("posttrans GEMM folds scalers %s (every shipped config); got %s"
+                                      % (_SCALER_ORDER, list(scalers)))
+        if pairwise_distances:
+            raise NotImplementedError("pairwise_distances=True is unused by the target configs")
+        if in_dim_edges != in_dim:
+            raise NotImplementedError("edge feature width must equal the node width (models/pna.py:150)")
+        self.residual = bool(residual) and in_dim == out_dim
+        self.pretrans = MLP(in_dim=2 * in_dim + in_dim_edges, hidden_size=in_dim, out_dim=in_dim,
+                            mid_batch_norm=mid_batch_norm, last_batch_norm=last_batch_norm, layers=pretrans_layers,
+                            mid_activation=activation, dropout=dropout, last_activation=last_activation,
+                            batch_norm_momentum=batch_norm_momentum)
+        self.posttrans = MLP(in_dim=(len(aggregators) * len(scalers) + 1) * in_dim, hidden_size=out_dim,
+                             out_dim=out_dim, layers=posttrans_layers, mid_activation=activation,
+                             last_activation=last_activation, dropout=dropout, mid_batch_norm=mid_batch_norm,
+                             last_batch_norm=last_batch_norm, batch_norm_momentum=batch_norm_momentum)
+
+    def forward(self, st, h, ef_csr):
+        # models/pna.py:203,237-252 — edge MLP over cat[h[src], h[dst], e], rows emitted in CSR order
+        msg = self.pretrans([ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
+                             ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr),
+                             ops.Seg(ef_csr)])
+        # models/pna.py:206,221-235
+        agg = ops.pna_aggregate(msg, st.rowptr)
+        # models/pna.py:207-211 — cat[h, agg, agg*amp, agg*att] -> posttrans -> + h
+        return self.posttrans([ops.Seg(h), ops.Seg(agg), ops.Seg(agg, scale=st.amp), ops.Seg(agg, scale=st.att)],
+                              residual=h if self.residual else None), msg
+
+
+class PNAGNN(nn.Module):
+    def __init__(self, hidden_dim, aggregators, scalers, residual=True, pairwise_distances=False, activation="relu",
+                 last_activation="none", mid_batch_norm=False, last_batch_norm=False, batch_norm_momentum=0.1,
+                 propagation_depth=5, dropout=0.0, posttrans_layers=1, pretrans_layers=1, **kwargs):
+        super().__init__()
+        self.mp_layers = nn.ModuleList([
+            PNALayer(in_dim=hidden_dim, out_dim=int(hidden_dim), in_dim_edges=hidden_dim, aggregators=aggregators,
+                     scalers=scalers, pairwise_distances=pairwise_distances, residual=residual, dropout=dropout,
+                     activation=activation, last_activation=last_activation, mid_batch_norm=mid_batch_norm,
+                     last_batch_norm=last_batch_norm, avg_d={"log": 1.0}, posttrans_layers=posttrans_layers,
+                     pretrans_layers=pretrans_layers, batch_norm_momentum=batch_norm_momentum)
+            for _ in range(propagation_depth)])
+        self.atom_encoder = AtomEncoder(emb_dim=hidden_dim)
+        self.bond_encoder = BondEncoder(emb_dim=hidden_dim)
+        self.keep_edge_side_effects = True
+
+    def forward(self, graph):
+        st = graph_structure(graph)
+        x_atom, e_attr = graph.ndata["feat"], graph.edata["feat"]
+        if x_atom.dtype != torch.int64 or e_attr.dtype != torch.int64:
+            raise TypeError("PNA expects int64 categorical features in ndata['feat'] / edata['feat'] "
+                            "(the graph is consumed by forward, as in the reference)")
+        h = self.atom_encoder(x_atom)                              # models/pna.py:162
+        ef_csr = self.bond_encoder(e_attr, perm=st.eid)            # models/pna.py:163, emitted in CSR order
+        graph.ndata["feat"] = h
+        if self.keep_edge_side_effects:
+            with torch.no_grad():
+                graph.edata["feat"] = self.bond_encoder(e_attr)    # edge-id order, as the reference leaves it
+        for layer in self.mp_layers:
+            h, _ = layer(st, h, ef_csr)
+            graph.ndata["feat"] = h                                # models/pna.py:213
+        return st, h
+
+
+class PNA(nn.Module):
+    """Message passing network over the 2-D molecular graph (no 3-D information)."""
+
+    def __init__(self, hidden_dim, target_dim, aggregators, scalers, readout_aggregators, readout_batchnorm=True,
+                 readout_hidden_dim=None, readout_layers=2, residual=True, pairwise_distances=False,
+                 activation="relu", last_activation="none", mid_batch_norm=False, last_batch_norm=False,
+                 propagation_depth=5, dropout=0.0, posttrans_layers=1, pretrans_layers=1, batch_norm_momentum=0.1,
+                 **kwargs):
+        super().__init__()
+        self.node_gnn = PNAGNN(hidden_dim=hidden_dim, aggregators=aggregators, scalers=scalers, residual=residual,
+                               pairwise_distances=pairwise_distances, activation=activation,
+                               last_activation=last_activation, mid_batch_norm=mid_batch_norm,
+                               last_batch_norm=last_batch_norm, propagation_depth=propagation_depth, dropout=dropout,
+                               posttrans_layers=posttrans_layers, pretrans_layers=pretrans_layers,
+                               batch_norm_momentum=batch_norm_momentum)
+        if readout_hidden_dim is None:
+            readout_hidden_dim = hidden_dim
+        self.readout_aggregators = list(readout_aggregators)
+        self.output = MLP(in_dim=hidden_dim * len(self.readout_aggregators), hidden_size=readout_hidden_dim,
+                          mid_batch_norm=readout_batchnorm, out_dim=target_dim, layers=readout_layers,
+                          batch_norm_momentum=batch_norm_momentum)
+
+    def forward(self, graph):
+        st, h = self.node_gnn(graph)
+        ro = ops.readout(h, st.graph_ptr, self.readout_aggregators)      # models/pna.py:133-134
+        return self.output(ro)                                           # models/pna.py:135

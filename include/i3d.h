@@ -1,0 +1,218 @@
+/*
+ * i3d.h — C ABI of lib3dinfomax_b200.so: the sm_100a kernels behind the 3DInfomax hot path
+ * (PNA 2-D encoder, Net3D 3-D encoder, NTXent losses, optimizer step).
+ *
+ * The reference (HannesStark/3DInfomax) is pure Python: every entry point below replaces a
+ * *library call site* of the reference (DGL message passing / PyTorch ATen ops), cited as
+ * file:line relative to the reference root.  The Python host layer (3dinfomax_b200/*.py) binds these
+ * with ctypes and mirrors the reference's model_type / model3d_type / loss_func plugin surface.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the comment says "host".
+ *     The library allocates nothing and keeps no mutable global state (error string: thread local).
+ *   - All matrices are row-major fp32 with an explicit leading dimension (elements).
+ *   - `stream` is a cudaStream_t passed as void*; every kernel is enqueued on it (CUDA-graph safe).
+ *   - Return value: 0 = ok, <0 = error (I3D_ERR_*); i3d_last_error_string() describes the last error
+ *     of the calling thread.  Nothing throws or aborts.
+ */
+#ifndef I3D_H_
+#define I3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I3D_OK 0
+#define I3D_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width ...) */
+#define I3D_ERR_UNSUPPORTED (-2) /* valid request the library has no kernel for */
+#define I3D_ERR_CUDA (-3)        /* a CUDA runtime call / launch failed */
+
+#define I3D_ACT_NONE 0
+#define I3D_ACT_RELU 1
+#define I3D_ACT_SILU 2
+
+#define I3D_GEMM_NT 0 /* C[m,n] = sum_k A[m,k]   * B[n,k]   (y = x W^T: nn.Linear forward) */
+#define I3D_GEMM_NN 1 /* C[m,n] = sum_k A[m,k]   * B[k,n]   (dx = dy W)                    */
+#define I3D_GEMM_TN 2 /* C[m,n] = sum_k A[k,m]   * B[k,n]   (dW = dy^T x)                  */
+
+#define I3D_RO_SUM 0
+#define I3D_RO_MEAN 1
+#define I3D_RO_MAX 2
+#define I3D_RO_MIN 3
+
+int i3d_version(void);
+const char* i3d_last_error_string(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
+int64_t i3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph structure.  Replaces DGL's per-call degree bucketing (host numpy sort + sync) behind
+ * g.update_all(message_func, reduce_func)  [models/pna.py:206]  and  fn.mean/fn.sum [models/net3d.py:94-96,109].
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stable counting sort of the E edges by `key` (dst for the in-CSR, src for the out-CSR).
+ *   rowptr[N+1], eid[E] (edge ids, ascending inside every row == argsort(key, stable) -- BIT EXACT),
+ *   col[E] = other[eid[k]], rowid[E] = key[eid[k]].  cursor_ws: N int32 scratch.                    */
+int i3d_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N, int32_t* rowptr,
+                  int32_t* col, int32_t* rowid, int32_t* eid, int32_t* cursor_ws, void* stream);
+/* same with int32 keys (used to sort the CSR-ordered edge list by source: the out-CSR position map) */
+int i3d_csr_build_i32(const int32_t* key, const int32_t* other, int64_t E, int64_t N, int32_t* rowptr,
+                      int32_t* col, int32_t* rowid, int32_t* eid, int32_t* cursor_ws, void* stream);
+
+/* ptr[0]=0, ptr[i+1]=ptr[i]+counts[i]  (graph_ptr from g.batch_num_nodes(), self_supervised_trainer.py:28) */
+int i3d_segment_ptr(const int64_t* counts, int64_t B, int32_t* ptr, void* stream);
+
+/* amp[v]=(float)ln(D+1), att[v]=(float)(1/ln(D+1)) with D=in-degree; both 0 for D=0.
+ * scale_amplification / scale_attenuation with avg_d["log"]=1.0  [models/pna.py:61-68,153]          */
+int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AtomEncoder / BondEncoder  [commons/mol_encoder.py:34-42,65-73; models/pna.py:162-163]
+ *   out[r,:] = sum_c table[col_off[c] + idx[perm ? perm[r] : r, c], :]
+ * `table` is the row-concatenation of the C embedding tables, col_off[c] the first row of table c.
+ * ---------------------------------------------------------------------------------------------- */
+int i3d_embed_sum_fwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
+                      const float* table, int F, float* out, void* stream);
+/* gtable (caller-zeroed) += scatter of gout; fp32 atomics */
+int i3d_embed_sum_bwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
+                      const float* gout, int F, float* gtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense stage.  Replaces cat + nn.Linear (cuBLAS SGEMM) at models/pna.py:249-252 (pretrans over
+ * cat[h_src,h_dst,e]), models/pna.py:207-209 (posttrans over cat[h, agg x scalers]),
+ * models/net3d.py:112-115,122-124 and the MLP heads [models/base_layers.py:100-101].
+ * The K dimension is a list of segments so that torch.cat / index_select / degree scalers never
+ * materialise:   C = sum_s  op(diag(scale_s) * gather(A_s, a_idx_s)) * op(gather(B_s, b_idx_s))
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A;       /* NT/NN: [*, K] rows indexed by m;  TN: [K, M] rows indexed by k           */
+  const float* B;       /* NT: [N, K] rows indexed by n;  NN/TN: [K, N] rows indexed by k            */
+  const int32_t* a_idx; /* optional row gather for A (NT/NN: per m; TN: per k)                        */
+  const int32_t* b_idx; /* optional row gather for B (TN only: per k)                                 */
+  const float* scale;   /* optional multiplier (NT/NN: per output row m; TN: per k)                   */
+  int32_t K;            /* depth of this segment                                                      */
+  int32_t lda, ldb;     /* leading dimensions (elements)                                              */
+} i3d_gemm_seg;
+
+/* segs: HOST array of n_seg (<=4) descriptors.  bias[N] optional (added once).  accumulate!=0: C += */
+int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+             const float* bias, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]
+ *   h = act(Y);  O = gamma*(h-mean)*rstd + beta (+ residual)
+ * ---------------------------------------------------------------------------------------------- */
+/* sums[0:F]=sum_rows act(Y), sums[F:2F]=sum_rows act(Y)^2 (fp64; zeroed inside) */
+int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double* sums, void* stream);
+/* training!=0: statistics from `sums` (biased var for normalisation), running stats updated with
+ * `momentum` (unbiased var), *num_batches_tracked += 1;  else running stats are used.
+ * save_mean_rstd[2F] receives the (mean, rstd) used.  residual (optional, ld = ldo) is added to O.   */
+int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const double* sums, float* running_mean,
+                 float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
+                 float momentum, float eps, int training, float* save_mean_rstd, const float* residual,
+                 float* O, int ldo, void* stream);
+/* sums2[0:F]=sum dO, sums2[F:2F]=sum dO*xhat (fp64; zeroed inside) */
+int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                      const float* save_mean_rstd, double* sums2, void* stream);
+/* dY = act'(Y) * gamma*rstd*(dO - mean(dO) - xhat*mean(dO*xhat))   (training)  |  act'(Y)*gamma*rstd*dO (eval)
+ * has_bn==0: dY = act'(Y)*dO.  dbias[F] (caller-zeroed) += sum_rows dY; dgamma/dbeta[F] written.      */
+int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
+                     int training, const float* save_mean_rstd, const float* gamma, const double* sums2,
+                     float* dY, int lddy, float* dbias, float* dgamma, float* dbeta, void* stream);
+/* y = act(x) elementwise (used where there is no BN, and for Net3D's second SiLU, models/net3d.py:81) */
+int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream);
+int i3d_act_bwd(const float* gy, const float* x, int64_t n, int act, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PNA aggregation  [models/pna.py:17-37 aggregators, :221-235 reduce_func, :206 update_all]
+ * msg[E,F] is in CSR (dst-sorted, edge-id-stable) order, so node v's mailbox is the contiguous row
+ * block [rowptr[v], rowptr[v+1]).  out[v, 0:4F] = [mean | max | min | std], std = sqrt(relu(E[x^2]-E[x]^2)+1e-5);
+ * zero in-degree -> zeros (DGL zero-fill).  The three degree scalers are NOT materialised: they are
+ * per-row scalars folded into the consuming GEMM (i3d_gemm scale segments).
+ * ---------------------------------------------------------------------------------------------- */
+int i3d_pna_aggregate_fwd(const float* msg, const int32_t* rowptr, int64_t N, int F, float* out, int ldo,
+                          void* stream);
+/* dmsg_k = g_mean/D + g_max*[k==first argmax] + g_min*[k==first argmin] + g_std*[var>0]*(x_k-mean)/(D*std) */
+int i3d_pna_aggregate_bwd(const float* g, int ldg, const float* msg, const float* out, int ldo,
+                          const int32_t* rowptr, int64_t N, int F, float* dmsg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segment ops over contiguous row blocks.
+ *   readout: dgl.readout_nodes(graph,'feat',op) for op in readout_aggregators  [models/pna.py:133; net3d.py:73]
+ *   segment_sum: builtin fn.sum / fn.mean reduce  [models/net3d.py:94-96,109]
+ * ---------------------------------------------------------------------------------------------- */
+/* out[b, i*F:(i+1)*F] = op_i over rows [ptr[b], ptr[b+1]); ops: n_ops (<=4) I3D_RO_* codes (host array) */
+int i3d_segment_readout_fwd(const float* x, int ldx, const int32_t* ptr, int64_t B, int F, int n_ops,
+                            const int32_t* ops, float* out, void* stream);
+/* max/min route the whole gradient to the FIRST row attaining the extremum (DGL segment_reduce arg) */
+int i3d_segment_readout_bwd(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
+                            int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, void* stream);
+/* out[v,:] = (mean ? 1/max(D,1) : 1) * sum_{k in [rowptr[v],rowptr[v+1])} x[idx ? idx[k] : k, :]  (+ addend[v,:])
+ * idx==NULL: rows of x are already in CSR order.  Also the backward of the h[src] / h[dst] gathers feeding the
+ * edge MLP (models/pna.py:249): in-CSR rowptr without idx, out-CSR rowptr with idx = position map.          */
+int i3d_segment_sum_fwd(const float* x, int ldx, const int32_t* rowptr, const int32_t* idx, int64_t N, int F,
+                        int mean, const float* addend, int lda, float* out, int ldo, void* stream);
+/* gx[k,:] = g[rowid[k],:] * (mean ? 1/D : 1) */
+int i3d_segment_sum_bwd(const float* g, const int32_t* rowptr, const int32_t* rowid, int64_t E, int F, int mean,
+                        float* gx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Net3D element-wise pieces  [commons/utils.py:103-110; models/net3d.py:61,112-118]
+ * ---------------------------------------------------------------------------------------------- */
+/* out[r,:] = [sin(d/2^0..2^(k-1)), cos(...), d] with d = dist[perm ? perm[r] : r] */
+int i3d_fourier_encode(const float* dist, const int32_t* perm, int64_t E, int k, float* out, void* stream);
+/* w = sigmoid(msg . ws + bs);  m = msg * w   (soft_edge_network, net3d.py:117-118) */
+int i3d_soft_gate_fwd(const float* msg, int64_t E, int H, const float* ws, const float* bs, float* m, float* w,
+                      void* stream);
+/* gmsg = gm*w + (sum_h gm*msg) w(1-w) ws ; gws[H], gbs[1] (caller-zeroed) accumulate */
+int i3d_soft_gate_bwd(const float* gm, const float* msg, const float* w, int64_t E, int H, const float* ws,
+                      float* gmsg, float* gws, float* gbs, void* stream);
+/* out[r,:] = vec[:]   /   out[c] = sum_rows x[r,c] */
+int i3d_broadcast_rows(const float* vec, int64_t M, int F, float* out, void* stream);
+int i3d_colsum(const float* x, int ldx, int64_t M, int F, float* out, void* stream);
+/* y = a + b (n elements) */
+int i3d_add(const float* a, const float* b, int64_t n, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NTXent / NTXentMultiplePositives  [commons/losses.py:143-155, 225-246]
+ *   dot[B, Bc*C] = z1 z2^T (i3d_gemm NT);  s = dot/(n1 n2 + eps) (norm) ; p = exp(s/tau);
+ *   Q_ij = sum_u p[i, j*C+u];  l_i = -log(Q_ii / (sum_j Q_ij - Q_ii));  loss = sum_i l_i / B_total.
+ * Rows are the local 2-D embeddings, columns the (all-gathered) 3-D embeddings; the positive of local row i
+ * is molecule (row_offset + i) in column space.  eps = 1e-8 for NTXent, 0 for MultiplePositives.
+ * ---------------------------------------------------------------------------------------------- */
+int i3d_row_norms(const float* z, int64_t R, int D, float* norms, void* stream);
+/* P[B, BcC] in: dot, out: p = exp(s/tau).  rowstats[B,2] = (pos, rowsum-pos).  loss_rows[B] = l_i   */
+int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1, const float* n2, int norm,
+                        float eps, float tau, int64_t row_offset, float* rowstats, float* loss_rows, void* stream);
+/* out[0] = scale * sum_i x[i]  (deterministic single-block reduction) */
+int i3d_sum_scaled(const float* x, int64_t n, float scale, float* out, void* stream);
+/* in: P (= p), dot recomputed as tau*log(p)*(n1n2+eps); out: P <- d loss / d dot; dn1[B], dn2[BcC] (caller-zeroed)
+ * gscale = d total / d loss_i  is read from the device scalar gout[0] times inv_B                           */
+int i3d_ntxent_rows_bwd(float* P, int64_t B, int64_t Bc, int C, const float* n1, const float* n2, int norm,
+                        float eps, float tau, int64_t row_offset, const float* rowstats, const float* gout,
+                        float inv_B, float* dn1, float* dn2, void* stream);
+/* dz[r,:] += dn[r] * z[r,:] / norms[r] */
+int i3d_norm_bwd_accum(const float* z, const float* norms, const float* dn, int64_t R, int D, float* dz,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer  [trainer/trainer.py:119-123 optim.step(); torch.optim.Adam semantics, L2 weight decay]
+ * ---------------------------------------------------------------------------------------------- */
+/* hyper_dev (optional, DEVICE double[6] = lr, beta1, beta2, eps, weight_decay, grad_scale) and step_dev
+ * (optional, DEVICE int64) override the by-value arguments so that a captured CUDA graph can be replayed
+ * while the schedule advances (WarmUpWrapper changes lr every step, trainer/lr_schedulers.py:30-52).     */
+int i3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, double grad_scale, int64_t step, const double* hyper_dev,
+                  const int64_t* step_dev, void* stream);
+int i3d_add_i64(int64_t* x, int64_t delta, void* stream);
+/* flat[off[t] : off[t]+len[t]] = src_t (to_flat!=0) or the reverse.  ptrs/off/len: DEVICE arrays of T entries */
+int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len, int T, float* flat, int to_flat,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I3D_H_ */
