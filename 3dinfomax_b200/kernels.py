@@ -181,6 +181,7 @@ def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=Tr
 
 
 def act_fwd(x, act):
+    _req(x, torch.float32, "x")
     x = x.contiguous()
     y = torch.empty_like(x)
     _lib.check(_L().i3d_act_fwd(_p(x), x.numel(), act, _p(y), _s()), "i3d_act_fwd")
@@ -188,6 +189,7 @@ def act_fwd(x, act):
 
 
 def act_bwd(gy, x, act):
+    _req(gy, torch.float32, "gy"), _req(x, torch.float32, "x")
     gy = gy.contiguous()
     gx = torch.empty_like(x)
     _lib.check(_L().i3d_act_bwd(_p(gy), _p(x), x.numel(), act, _p(gx), _s()), "i3d_act_bwd")
@@ -308,6 +310,7 @@ def colsum(x):
 
 
 def add(a, b):
+    _req(a, torch.float32, "a"), _req(b, torch.float32, "b")
     a, b = a.contiguous(), b.contiguous()
     y = torch.empty_like(a)
     _lib.check(_L().i3d_add(_p(a), _p(b), a.numel(), _p(y), _s()), "i3d_add")

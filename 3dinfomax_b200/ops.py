@@ -153,10 +153,28 @@ def embed_sum(idx, col_off, perm, table):
     return _EmbedSum.apply(idx, col_off, perm, table)
 
 
+# bench.py sets PROFILE = {"fwd": [], "bwd": []} to time every aggregation launch with CUDA events on the launch
+# stream; each entry is (start_event, end_event, algorithmic_bytes) with the byte model of SURVEY.md §8d.
+PROFILE = None
+
+
+def _timed(kind, nbytes, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    PROFILE[kind].append((e0, e1, nbytes))
+    return out
+
+
 class _PNAAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, msg, rowptr):
-        out = K.pna_aggregate_fwd(msg, rowptr)
+        E, F = msg.shape
+        N = rowptr.numel() - 1
+        out = _timed("fwd", 4 * F * E + 4 * E + 4 * (N + 1) + 16 * F * N, lambda: K.pna_aggregate_fwd(msg, rowptr))
         ctx.save_for_backward(msg, out, rowptr)
         return out
 
@@ -165,7 +183,10 @@ class _PNAAggregate(torch.autograd.Function):
         msg, out, rowptr = ctx.saved_tensors
         if g.stride(1) != 1:
             g = g.contiguous()
-        return K.pna_aggregate_bwd(g, msg, out, rowptr), None
+        E, F = msg.shape
+        N = rowptr.numel() - 1
+        return _timed("bwd", 32 * F * N + 8 * F * E + 4 * (N + 1),
+                      lambda: K.pna_aggregate_bwd(g, msg, out, rowptr)), None
 
 
 def pna_aggregate(msg, rowptr):
@@ -299,7 +320,10 @@ class _NTXent(torch.autograd.Function):
         z1, z2, n1, n2, P, rowstats = ctx.saved_tensors
         B, Bc, C, D, tau, norm, eps, row_offset, inv_B = ctx.args
         gout = gout.contiguous().float()
-        G = P.clone() if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] else None
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("NTXent backward overwrites its saved probabilities in place: call backward once")
+        ctx.consumed = True
+        G = P
         dn1, dn2 = K.ntxent_rows_bwd(G, B, Bc, C, n1, n2, norm, eps, tau, row_offset, rowstats, gout, inv_B)
         dz1 = torch.empty_like(z1)
         K.gemm(K.NN, B, D, [{"A": G, "B": z2, "K": Bc * C}], dz1)

@@ -364,9 +364,19 @@ def segment_readout(x, g, op):
     if op in ("sum", "mean"):
         out = torch.zeros(B, x.shape[1], dtype=x.dtype).index_add(0, g.seg, x)
         return out / g.bnn.to(x.dtype)[:, None] if op == "mean" else out
+    # DGL's segment_reduce max/min keeps the arg index (first row attaining the extremum, strict compare) and its
+    # backward sends the whole gradient there -- not an even split between ties
+    return x.gather(0, _first_extremum_rows(x.detach(), g.seg, B, op))
+
+
+def _first_extremum_rows(x, seg, B, op):
     red = {"max": "amax", "min": "amin"}[op]
-    idx = g.seg[:, None].expand_as(x)
-    return torch.zeros(B, x.shape[1], dtype=x.dtype).scatter_reduce(0, idx, x, red, include_self=False)
+    idx = seg[:, None].expand_as(x)
+    val = torch.zeros(B, x.shape[1], dtype=x.dtype).scatter_reduce(0, idx, x, red, include_self=False)
+    n = x.shape[0]
+    pos = torch.arange(n)[:, None].expand_as(x)
+    cand = torch.where(x == val[seg], pos, torch.full_like(pos, n))
+    return torch.zeros(B, x.shape[1], dtype=torch.long).scatter_reduce(0, idx, cand, "amin", include_self=False)
 
 
 def pna_forward(st, c, g, x_atom, e_attr, training=True, taps=None):

@@ -109,9 +109,16 @@ def _readout_nodes(g, feat, op="sum"):
         if op == "mean":
             out = out / g._bnn.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
         return out
+    # DGL segment_reduce max/min: value of the FIRST row attaining the extremum; backward routes the gradient there
     red = {"max": "amax", "min": "amin"}[op]
+    xd = x.detach()
     idx = seg.view(-1, *([1] * (x.dim() - 1))).expand_as(x)
-    return torch.zeros((B,) + x.shape[1:], dtype=x.dtype).scatter_reduce(0, idx, x, red, include_self=False)
+    val = torch.zeros((B,) + x.shape[1:], dtype=x.dtype).scatter_reduce(0, idx, xd, red, include_self=False)
+    n = x.shape[0]
+    pos = torch.arange(n).view(-1, *([1] * (x.dim() - 1))).expand_as(x)
+    cand = torch.where(xd == val[seg], pos, torch.full_like(pos, n))
+    first = torch.zeros((B,) + x.shape[1:], dtype=torch.long).scatter_reduce(0, idx, cand, "amin", include_self=False)
+    return x.gather(0, first)
 
 
 _LOADED = {}

@@ -1,0 +1,627 @@
+"""Kernel- and model-level parity cases: the CUDA path (through the C ABI) against the CPU oracle / plain fp32-fp64
+torch references on the same seeded inputs.  Each case returns [(label, error, tolerance)].
+
+Shared by tests/test_gpu_parity.py (pytest, -m gpu) and tests/gpu_diag.py (prints every number without stopping).
+Tolerances: integer / index work bit exact (tol 0); fp32 element-wise and reductions 1e-6..1e-5 relative to the
+tensor's magnitude; GEMM-containing results 2e-5 relative (fp32 accumulation order differs from MKL);
+end-to-end embeddings 1e-4 relative, parameter gradients 2e-4 of the global gradient scale.
+"""
+import importlib
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+i3d = importlib.import_module("3dinfomax_b200")
+K = importlib.import_module("3dinfomax_b200.kernels")
+ops = importlib.import_module("3dinfomax_b200.ops")
+syn = i3d.synthetic
+DEV = "cuda"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    if a.shape != b.shape:
+        return float("inf")
+    if a.numel() == 0:
+        return 0.0
+    if not torch.isfinite(a).all():
+        return float("inf")
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def exact(a, b):
+    a = torch.as_tensor(a).cpu()
+    b = torch.as_tensor(b).cpu()
+    return 0.0 if a.shape == b.shape and torch.equal(a.to(b.dtype), b) else 1.0
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def random_graph(seed, n, e, isolated=True):
+    g = gen(seed)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, n - (2 if isolated and n > 2 else 0), (e,), generator=g)   # last two nodes: in-degree 0
+    return src, dst
+
+
+# ------------------------------------------------------------------------------------------------ graph
+def case_csr():
+    out = []
+    for tag, (n, e) in {"small": (7, 19), "empty_edges": (5, 0), "bond_like": (3000, 6100),
+                        "high_degree": (64, 64 * 63)}.items():
+        src, dst = random_graph(1, n, e) if e else (torch.zeros(0, dtype=torch.long),) * 2
+        if tag == "high_degree":
+            s, d = syn.complete_graph_edges(64)
+            src, dst = torch.from_numpy(s), torch.from_numpy(d)
+        rowptr, col, eid = O.csr_reference(src.numpy(), dst.numpy(), n)
+        r, c, rid, ei = K.csr_build(dst.to(DEV), src.to(DEV), n)
+        out += [("csr/%s/rowptr" % tag, exact(r, rowptr), 0), ("csr/%s/col" % tag, exact(c, col), 0),
+                ("csr/%s/eid" % tag, exact(ei, eid), 0),
+                ("csr/%s/rowid" % tag, exact(rid, dst.numpy()[eid] if e else np.zeros(0)), 0)]
+        # int32 variant: sort the CSR-ordered edge list by source -> position map
+        if e:
+            r2, c2, _, pos = K.csr_build(c, rid, n)
+            rp2, col2, eid2 = O.csr_reference(rid.cpu().numpy(), c.cpu().numpy(), n)
+            out += [("csr/%s/out_rowptr" % tag, exact(r2, rp2), 0), ("csr/%s/out_pos" % tag, exact(pos, eid2), 0)]
+    counts = torch.tensor([3, 0, 5, 1, 29], dtype=torch.int64)
+    ptr = K.segment_ptr(counts.to(DEV))
+    out.append(("segment_ptr", exact(ptr, torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])), 0))
+    big = torch.randint(0, 40, (5000,), generator=gen(2))
+    out.append(("segment_ptr/5000", exact(K.segment_ptr(big.to(DEV)),
+                                           torch.cat([torch.zeros(1, dtype=torch.long), big.cumsum(0)])), 0))
+    rp = torch.tensor([0, 0, 1, 3, 6, 10, 10], dtype=torch.int32)
+    amp, att = K.degree_scalers(rp.to(DEV))
+    D = (rp[1:] - rp[:-1]).numpy()
+    with np.errstate(divide="ignore"):
+        ra = np.where(D > 0, np.log(D + 1.0), 0.0).astype(np.float32)
+        rt = np.where(D > 0, 1.0 / np.log(D + 1.0), 0.0).astype(np.float32)
+    out += [("degree_scalers/amp", exact(amp, ra), 0), ("degree_scalers/att", exact(att, rt), 0)]
+    return out
+
+
+# -------------------------------------------------------------------------------------------- embedding
+def case_embed():
+    g = gen(3)
+    dims = syn.ATOM_FEATURE_DIMS
+    out = []
+    for Fd in (200, 20, 6):
+        tables = [torch.randn(d, Fd, generator=g) for d in dims]
+        idx = torch.stack([torch.randint(0, d, (57,), generator=g) for d in dims], 1)
+        perm = torch.randperm(57, generator=g).int()
+        table = torch.cat(tables).requires_grad_(True)
+        off = torch.tensor(np.concatenate([[0], np.cumsum(dims)[:-1]]), dtype=torch.int32)
+        ref = sum(F.embedding(idx[perm.long(), c] + int(off[c]), table) for c in range(len(dims)))
+        gout = torch.randn(57, Fd, generator=g)
+        ref.backward(gout)
+        t_dev = table.detach().to(DEV).requires_grad_(True)
+        got = ops.embed_sum(idx.to(DEV), off.to(DEV), perm.to(DEV), t_dev)
+        got.backward(gout.to(DEV))
+        out += [("embed/F%d/fwd" % Fd, rel(got, ref), 1e-6), ("embed/F%d/bwd" % Fd, rel(t_dev.grad, table.grad), 1e-5)]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- gemm
+def _gemm_ref(mode, M, N, segs, bias, C0):
+    acc = torch.zeros(M, N, dtype=torch.float64) if C0 is None else C0.double().clone()
+    for s in segs:
+        A, B = s["A"].double(), s["B"].double()
+        if mode in (K.NT, K.NN):
+            a = A[s["a_idx"].long()] if s.get("a_idx") is not None else A[:M]
+            if s.get("scale") is not None:
+                a = a * s["scale"].double()[:, None]
+            acc += a @ (B.t() if mode == K.NT else B)
+        else:
+            a = A[s["a_idx"].long()] if s.get("a_idx") is not None else A
+            b = B[s["b_idx"].long()] if s.get("b_idx") is not None else B
+            if s.get("scale") is not None:
+                a = a * s["scale"].double()[:, None]
+            acc += a.t() @ b
+    if bias is not None:
+        acc += bias.double()[None, :]
+    return acc
+
+
+def _to_dev(segs):
+    return [{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in s.items()} for s in segs]
+
+
+def case_gemm():
+    g = gen(4)
+    out = []
+    rn = lambda *s: torch.randn(*s, generator=g)
+    # (tag, mode, M, N, Ks, gather, scale, bias, accumulate)
+    for tag, mode, M, N, Ks, gather, scale, bias, accum in [
+        ("nt_plain", K.NT, 300, 200, [600], False, False, True, False),
+        ("nt_tiny", K.NT, 1, 3, [5], False, False, True, False),
+        ("nt_k9", K.NT, 777, 20, [9], False, False, True, False),
+        ("nt_gather3", K.NT, 1000, 200, [200, 200, 200], True, False, True, False),
+        ("nt_scale4", K.NT, 513, 200, [200, 800, 800, 800], False, True, True, False),
+        ("nt_sim", K.NT, 96, 288, [256], False, False, False, False),
+        ("nn_plain", K.NN, 300, 600, [200], False, False, False, False),
+        ("nn_scale3_acc", K.NN, 257, 800, [200, 200, 200], False, True, False, True),
+        ("nn_small", K.NN, 50, 20, [20], False, False, False, False),
+        ("tn_plain", K.TN, 200, 600, [5000], False, False, False, False),
+        ("tn_gather", K.TN, 200, 200, [3001], True, False, False, False),
+        ("tn_scale", K.TN, 200, 800, [2000], False, True, False, False),
+        ("tn_acc", K.TN, 20, 60, [999], False, False, False, True),
+        ("tn_smallk", K.TN, 256, 20, [7], False, False, False, False),
+    ]:
+        segs = []
+        rows = 400
+        for Kd in Ks:
+            s = {"K": Kd}
+            if mode == K.NT:
+                s["A"] = rn(rows if gather else M, Kd)
+                s["B"] = rn(N, Kd)
+                if gather:
+                    s["a_idx"] = torch.randint(0, rows, (M,), generator=g).int()
+                if scale and len(segs) > 0:
+                    s["scale"] = rn(M)
+            elif mode == K.NN:
+                s["A"] = rn(M, Kd)
+                s["B"] = rn(Kd, N)
+                if scale and len(segs) > 0:
+                    s["scale"] = rn(M)
+            else:
+                s["A"] = rn(Kd, M)
+                s["B"] = rn(rows if gather else Kd, N)
+                if gather:
+                    s["b_idx"] = torch.randint(0, rows, (Kd,), generator=g).int()
+                if scale:
+                    s["scale"] = rn(Kd)
+            segs.append(s)
+        b = rn(N) if bias else None
+        C0 = rn(M, N) if accum else None
+        ref = _gemm_ref(mode, M, N, segs, b, C0)
+        C = C0.clone().to(DEV) if accum else torch.full((M, N), float("nan"), device=DEV)
+        K.gemm(mode, M, N, _to_dev(segs), C, None if b is None else b.to(DEV), accum)
+        out.append(("gemm/" + tag, rel(C, ref), 2e-5))
+    # strided views: weight column blocks and an output column block, as the FC operator uses them
+    W = rn(200, 2600)
+    X = rn(321, 800)
+    Cbig = torch.zeros(321, 1000, device=DEV)
+    K.gemm(K.NT, 321, 200, [{"A": X.to(DEV), "B": W.to(DEV)[:, 1000:1800], "K": 800}], Cbig[:, 400:600])
+    out.append(("gemm/strided_views", rel(Cbig[:, 400:600], X.double() @ W[:, 1000:1800].double().t()), 2e-5))
+    out.append(("gemm/strided_untouched", float(Cbig[:, :400].abs().max() + Cbig[:, 600:].abs().max()), 0))
+    return out
+
+
+# --------------------------------------------------------------------------------------- FC tail (BN)
+def case_bn():
+    g = gen(5)
+    out = []
+    for Fd, M in ((200, 1777), (20, 30001), (9, 101), (256, 64)):
+        for act_name in ("none", "relu", "silu"):
+            for training in (True, False):
+                act = K.ACT[act_name]
+                Y = (torch.randn(M, Fd, generator=g) * 0.7 + 0.3).requires_grad_(True)
+                gamma = (1 + 0.1 * torch.randn(Fd, generator=g)).requires_grad_(True)
+                beta = (0.1 * torch.randn(Fd, generator=g)).requires_grad_(True)
+                res = torch.randn(M, Fd, generator=g)
+                rm, rv = 0.1 * torch.randn(Fd, generator=g), 0.5 + torch.rand(Fd, generator=g)
+                rm_ref, rv_ref = rm.clone(), rv.clone()
+                h = {"none": lambda t: t, "relu": torch.relu, "silu": F.silu}[act_name](Y)
+                ref = F.batch_norm(h, rm_ref, rv_ref, gamma, beta, training, 0.93, 1e-5) + res
+                gout = torch.randn(M, Fd, generator=g)
+                ref.backward(gout)
+                Yd = Y.detach().to(DEV)
+                rm_d, rv_d = rm.to(DEV), rv.to(DEV)
+                nbt = torch.zeros((), dtype=torch.long, device=DEV)
+                sums = K.act_colstats(Yd, act) if training else None
+                Od, save = K.bn_apply(Yd, act, sums, rm_d, rv_d, nbt, gamma.detach().to(DEV), beta.detach().to(DEV),
+                                      0.93, 1e-5, training, res.to(DEV))
+                sums2 = K.bn_bwd_reduce(gout.to(DEV), Yd, act, save)
+                dY, db, dgam, dbet = K.bn_bwd_apply(gout.to(DEV), Yd, act, True, training, save,
+                                                    gamma.detach().to(DEV), sums2)
+                tag = "bn/F%d/%s/%s" % (Fd, act_name, "train" if training else "eval")
+                out += [(tag + "/fwd", rel(Od, ref), 3e-6), (tag + "/dY", rel(dY, Y.grad), 2e-5),
+                        (tag + "/dgamma", rel(dgam, gamma.grad), 2e-5), (tag + "/dbeta", rel(dbet, beta.grad), 2e-5),
+                        (tag + "/dbias", rel(db, Y.grad.sum(0)) if act_name != "none" or not training else
+                         float(db.abs().max().item() / (gout.abs().sum(0).max().item())), 2e-5)]
+                if training:
+                    out += [(tag + "/running_mean", rel(rm_d, rm_ref), 2e-6), (tag + "/running_var", rel(rv_d, rv_ref), 2e-6),
+                            (tag + "/nbt", exact(nbt, torch.tensor(1)), 0)]
+    # no-BN path + plain activations
+    Y = torch.randn(333, 20, generator=g)
+    gy = torch.randn(333, 20, generator=g)
+    for act_name in ("relu", "silu"):
+        Yr = Y.clone().requires_grad_(True)
+        r = {"relu": torch.relu, "silu": F.silu}[act_name](Yr)
+        r.backward(gy)
+        dY, db, _, _ = K.bn_bwd_apply(gy.to(DEV), Y.to(DEV), K.ACT[act_name], False, False, None, None, None)
+        out += [("act/%s/fwd" % act_name, rel(K.act_fwd(Y.to(DEV), K.ACT[act_name]), r), 2e-6),
+                ("act/%s/bwd" % act_name, rel(K.act_bwd(gy.to(DEV), Y.to(DEV), K.ACT[act_name]), Yr.grad), 2e-6),
+                ("act/%s/nobn_dY" % act_name, rel(dY, Yr.grad), 2e-6),
+                ("act/%s/nobn_db" % act_name, rel(db, Yr.grad.sum(0)), 1e-5)]
+    out.append(("colsum", rel(K.colsum(Y.to(DEV)), Y.sum(0)), 1e-5))
+    out.append(("add", rel(K.add(Y.to(DEV), gy.to(DEV)), Y + gy), 0))
+    v = torch.randn(20, generator=g)
+    out.append(("broadcast_rows", exact(K.broadcast_rows(v.to(DEV), 77), v[None].expand(77, 20)), 0))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ aggregation
+def _csr_order(src, dst, n):
+    rowptr, col, eid = O.csr_reference(src.numpy(), dst.numpy(), n)
+    return torch.from_numpy(rowptr), torch.from_numpy(eid).long()
+
+
+def case_aggregate():
+    out = []
+    for tag, (n, e, Fd) in {"bond": (500, 1100, 200), "narrow": (300, 700, 20), "odd": (50, 170, 6),
+                            "dense": (40, 1500, 200)}.items():
+        g = gen(6)
+        src, dst = random_graph(7, n, e)
+        og = O.OGraph(src, dst, torch.tensor([n]))
+        msg = torch.randn(e, Fd, generator=g)
+        msg[3] = msg[1]                       # exact ties -> first-index gradient routing must match torch.max/min
+        dst = dst.clone()
+        rowptr, eid = _csr_order(src, dst, n)
+        msg_ref = msg.clone().requires_grad_(True)
+        ref = O.pna_reduce(og, msg_ref, ["mean", "max", "min", "std"], ["identity"])          # [n, 4F], edge-id order in
+        gout = torch.randn(n, 4 * Fd, generator=g)
+        ref.backward(gout)
+        m_csr = msg[eid].to(DEV).requires_grad_(True)
+        got = ops.pna_aggregate(m_csr, rowptr.to(DEV))
+        got.backward(gout.to(DEV))
+        out += [("aggregate/%s/fwd" % tag, rel(got, ref), 1e-6),
+                ("aggregate/%s/bwd" % tag, rel(m_csr.grad, msg_ref.grad[eid]), 1e-5),
+                ("aggregate/%s/zero_degree_rows" % tag, float(got[n - 2:].abs().max()), 0)]
+    # duplicate messages inside one mailbox (symmetric hydrogens): tie routing + D=1 rows + var gate
+    src = torch.tensor([1, 2, 3, 0, 0, 0, 4])
+    dst = torch.tensor([0, 0, 0, 1, 2, 3, 1])
+    g = gen(8)
+    base = torch.randn(1, 200, generator=g)
+    msg = torch.cat([base, base, base, torch.randn(4, 200, generator=g)])
+    og = O.OGraph(src, dst, torch.tensor([5]))
+    rowptr, eid = _csr_order(src, dst, 5)
+    mr = msg.clone().requires_grad_(True)
+    ref = O.pna_reduce(og, mr, ["mean", "max", "min", "std"], ["identity"])
+    gout = torch.randn(5, 800, generator=g)
+    ref.backward(gout)
+    mc = msg[eid].to(DEV).requires_grad_(True)
+    got = ops.pna_aggregate(mc, rowptr.to(DEV))
+    got.backward(gout.to(DEV))
+    out += [("aggregate/ties/fwd", rel(got, ref), 1e-6), ("aggregate/ties/bwd", rel(mc.grad, mr.grad[eid]), 1e-5)]
+    return out
+
+
+def case_segment_ops():
+    g = gen(9)
+    out = []
+    nn_ = torch.tensor([3, 1, 7, 29, 2, 11])
+    og = O.OGraph(torch.zeros(0), torch.zeros(0), nn_)
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long), nn_.cumsum(0)]).int()
+    for Fd in (200, 20, 6):
+        for ops_ in (["min", "max", "mean"], ["min", "max", "mean", "sum"], ["sum"]):
+            x = torch.randn(int(nn_.sum()), Fd, generator=g)
+            x[4] = x[5]                                      # tie inside graph 2
+            xr = x.clone().requires_grad_(True)
+            ref = torch.cat([O.segment_readout(xr, og, o) for o in ops_], -1)
+            gout = torch.randn(ref.shape, generator=g)
+            ref.backward(gout)
+            xd = x.to(DEV).requires_grad_(True)
+            got = ops.readout(xd, ptr.to(DEV), ops_)
+            got.backward(gout.to(DEV))
+            tag = "readout/F%d/%s" % (Fd, "+".join(ops_))
+            out += [(tag + "/fwd", rel(got, ref), 1e-6), (tag + "/bwd", rel(xd.grad, xr.grad), 1e-6)]
+    # segment mean / sum over CSR rows (+ addend), and the indexed gather-sum used by the FC backward
+    n, e, H = 200, 900, 20
+    src, dst = random_graph(10, n, e)
+    rowptr, eid = _csr_order(src, dst, n)
+    rowid = dst[eid].int()
+    deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).float()
+    for mean in (True, False):
+        x = torch.randn(e, H, generator=g).requires_grad_(True)       # already CSR ordered
+        add = torch.randn(n, H, generator=g).requires_grad_(True)
+        ref = torch.zeros(n, H).index_add(0, rowid.long(), x)
+        ref = (ref / deg[:, None] if mean else ref) + add
+        gout = torch.randn(n, H, generator=g)
+        ref.backward(gout)
+        xd, ad = x.detach().to(DEV).requires_grad_(True), add.detach().to(DEV).requires_grad_(True)
+        got = ops.segment_reduce(xd, rowptr.to(DEV), rowid.to(DEV), mean, ad)
+        got.backward(gout.to(DEV))
+        tag = "segment_%s" % ("mean" if mean else "sum")
+        out += [(tag + "/fwd", rel(got, ref), 1e-6), (tag + "/bwd_x", rel(xd.grad, x.grad), 1e-6),
+                (tag + "/bwd_addend", rel(ad.grad, add.grad), 0)]
+    x = torch.randn(e, H, generator=g)
+    idx = torch.randperm(e, generator=g).int()
+    ref = torch.zeros(n, H).index_add(0, rowid.long(), x[idx.long()])
+    got = K.segment_sum_fwd(x.to(DEV), rowptr.to(DEV), idx.to(DEV))
+    out.append(("segment_sum/indexed", rel(got, ref), 1e-6))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ net3d
+def case_net3d_elementwise():
+    g = gen(11)
+    out = []
+    d = torch.rand(1234, generator=g) * 8 + 0.9
+    perm = torch.randperm(1234, generator=g).int()
+    ref = O.fourier_encode(d[perm.long()].reshape(-1, 1), 4)
+    out.append(("fourier/k4", rel(K.fourier_encode(d.to(DEV), perm.to(DEV), 4), ref), 1e-6))
+    out.append(("fourier/k0", exact(K.fourier_encode(d.to(DEV), None, 0), d.reshape(-1, 1)), 0))
+    for H in (20, 32, 7):
+        msg = torch.randn(999, H, generator=g).requires_grad_(True)
+        w = (torch.randn(1, H, generator=g) * 0.7).requires_grad_(True)
+        b = torch.randn(1, generator=g).requires_grad_(True)
+        ref = msg * torch.sigmoid(F.linear(msg, w, b))
+        gout = torch.randn(999, H, generator=g)
+        ref.backward(gout)
+        md, wd, bd = (t.detach().to(DEV).requires_grad_(True) for t in (msg, w, b))
+        got = ops.soft_gate(md, wd, bd)
+        got.backward(gout.to(DEV))
+        out += [("soft_gate/H%d/fwd" % H, rel(got, ref), 2e-6), ("soft_gate/H%d/dmsg" % H, rel(md.grad, msg.grad), 1e-5),
+                ("soft_gate/H%d/dw" % H, rel(wd.grad, w.grad), 1e-4), ("soft_gate/H%d/db" % H, rel(bd.grad, b.grad), 1e-4)]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- loss
+def case_ntxent():
+    g = gen(12)
+    out = []
+    for B, C, D in ((37, 1, 256), (24, 3, 256), (130, 1, 64)):
+        z1 = torch.randn(B, D, generator=g)
+        z2 = torch.randn(B * C, D, generator=g) * 0.5 + 0.2 * z1.repeat_interleave(C, 0)
+        for name, fn, eps in (("NTXent", O.ntxent, 1e-8), ("NTXentMultiplePositives", O.ntxent_multiple_positives, 0.0)):
+            if name == "NTXent" and C != 1:
+                continue
+            a, b = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+            ref = fn(a, b, tau=0.1)
+            (ref * 1.7).backward()
+            ad, bd = z1.to(DEV).requires_grad_(True), z2.to(DEV).requires_grad_(True)
+            mod = getattr(i3d, name)(tau=0.1)
+            got = mod(ad, bd)
+            (got * 1.7).backward()
+            tag = "%s/B%d_C%d" % (name, B, C)
+            out += [(tag + "/loss", abs(got.item() - ref.item()) / abs(ref.item()), 2e-6),
+                    (tag + "/dz1", rel(ad.grad, a.grad), 2e-5), (tag + "/dz2", rel(bd.grad, b.grad), 2e-5)]
+    # local rows against a gathered column set (data-parallel layout): rows 8..15 of a 24-molecule batch
+    B, C, D = 24, 3, 256
+    z1 = torch.randn(B, D, generator=g)
+    z2 = torch.randn(B * C, D, generator=g)
+    full = O.ntxent_multiple_positives(z1, z2, tau=0.1)
+    parts = [i3d.NTXentMultiplePositives(tau=0.1)(z1[r * 8:(r + 1) * 8].to(DEV), z2.to(DEV), row_offset=r * 8, total_rows=B)
+             for r in range(3)]
+    out.append(("NTXentMultiplePositives/row_offset_sum", abs(sum(p.item() for p in parts) - full.item()) / abs(full.item()),
+                2e-6))
+    return out
+
+
+# -------------------------------------------------------------------------------------------- optimizer
+def case_adam():
+    g = gen(13)
+    out = []
+    shapes = [(200, 600), (200,), (7, 3), (1,), (256, 200)]
+    params = [torch.randn(*s, generator=g) for s in shapes]
+    grads = [[torch.randn(*s, generator=g) * 0.01 for s in shapes] for _ in range(4)]
+    ref_p = [p.clone().requires_grad_(True) for p in params]
+    ref_opt = torch.optim.Adam([{"params": ref_p[:2], "weight_decay": 0}, {"params": ref_p[2:]}], lr=8e-5)
+    dev_p = [torch.nn.Parameter(p.clone().to(DEV)) for p in params]
+    for graph_safe in (False, True):
+        for p, q in zip(dev_p, params):
+            p.data = q.clone().to(DEV)
+        for p, q in zip(ref_p, params):
+            p.data.copy_(q)
+        ref_opt = torch.optim.Adam([{"params": ref_p[:2], "weight_decay": 0}, {"params": ref_p[2:]}], lr=8e-5)
+        opt = i3d.FusedAdam([{"params": dev_p[:2], "weight_decay": 0}, {"params": dev_p[2:]}], lr=8e-5,
+                            graph_safe=graph_safe)
+        for step in range(4):
+            lr = 8e-5 * (step + 1) / 4                       # WarmUpWrapper-style lr changes every step
+            for grp in ref_opt.param_groups + opt.param_groups:
+                grp["lr"] = lr
+            for p, q, gr in zip(ref_p, dev_p, grads[step]):
+                p.grad = gr.clone()
+                q.grad = gr.clone().to(DEV)
+            ref_opt.step()
+            opt.step()
+            opt.zero_grad()
+        err = max(rel(q, p) for p, q in zip(ref_p, dev_p))
+        upd = max(rel(q.detach().cpu() - p0, p.detach() - p0) for p, q, p0 in zip(ref_p, dev_p, params))
+        out += [("adam/graph_safe=%s/params" % graph_safe, err, 1e-6), ("adam/graph_safe=%s/update" % graph_safe, upd, 2e-3)]
+    sd = opt.state_dict()
+    out.append(("adam/state_dict_exp_avg", rel(sd["state"][0]["exp_avg"], ref_opt.state_dict()["state"][0]["exp_avg"]), 1e-5))
+    return out
+
+
+# -------------------------------------------------------------------------------------------- FC operator
+def case_fc():
+    """ops.fc over gathered / scaled K-segments against cat + Linear + act + BatchNorm in plain torch."""
+    g = gen(14)
+    out = []
+    n, e, Fd = 300, 700, 40
+    src, dst = random_graph(15, n, e, isolated=False)
+    st = i3d.GraphStructure(src.to(DEV), dst.to(DEV), torch.tensor([n]), n)
+    eid = st.eid.long().cpu()
+    src_c, dst_c = src[eid], dst[eid]
+    h = torch.randn(n, Fd, generator=g).requires_grad_(True)
+    ef = torch.randn(e, Fd, generator=g).requires_grad_(True)
+    W = (torch.randn(Fd, 3 * Fd, generator=g) * 0.1).requires_grad_(True)
+    b = (torch.randn(Fd, generator=g) * 0.1).requires_grad_(True)
+    gam = (1 + 0.1 * torch.randn(Fd, generator=g)).requires_grad_(True)
+    bet = (0.1 * torch.randn(Fd, generator=g)).requires_grad_(True)
+    rm, rv = torch.zeros(Fd), torch.ones(Fd)
+    ref = F.batch_norm(torch.relu(F.linear(torch.cat([h[src_c], h[dst_c], ef], -1), W, b)), rm.clone(), rv.clone(), gam, bet,
+                       True, 0.9, 1e-5)
+    gout = torch.randn(e, Fd, generator=g)
+    ref.backward(gout)
+    d = lambda t: t.detach().to(DEV).requires_grad_(True)
+    hd, efd, Wd, bd, gd, btd = d(h), d(ef), d(W), d(b), d(gam), d(bet)
+    bn = (gd, btd, rm.to(DEV), rv.to(DEV), torch.zeros((), dtype=torch.long, device=DEV), 0.9, 1e-5)
+    got = ops.fc([ops.Seg(hd, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
+                  ops.Seg(hd, idx=st.dst_csr, inv_rowptr=st.rowptr), ops.Seg(efd)], Wd, bd, K.ACT["relu"], bn, True)
+    got.backward(gout.to(DEV))
+    out += [("fc/gather/fwd", rel(got, ref), 2e-5), ("fc/gather/dh", rel(hd.grad, h.grad), 5e-5),
+            ("fc/gather/def", rel(efd.grad, ef.grad), 5e-5), ("fc/gather/dW", rel(Wd.grad, W.grad), 5e-5),
+            ("fc/gather/dgamma", rel(gd.grad, gam.grad), 5e-5), ("fc/gather/dbeta", rel(btd.grad, bet.grad), 5e-5),
+            ("fc/gather/db", rel(bd.grad, b.grad), 5e-5)]
+    # posttrans-style: cat[h, A, A*amp, A*att] with per-row scalers, no activation, BN, residual
+    A = torch.randn(n, 4 * Fd, generator=g).requires_grad_(True)
+    amp, att = st.amp.cpu(), st.att.cpu()
+    W2 = (torch.randn(Fd, 13 * Fd, generator=g) * 0.05).requires_grad_(True)
+    b2 = torch.zeros(Fd, requires_grad=True)
+    h2 = torch.randn(n, Fd, generator=g).requires_grad_(True)
+    x = torch.cat([h2, A, A * amp[:, None], A * att[:, None]], -1)
+    ref = F.batch_norm(F.linear(x, W2, b2), rm.clone(), rv.clone(), gam, bet, True, 0.9, 1e-5) + h2
+    gout = torch.randn(n, Fd, generator=g)
+    gam.grad = bet.grad = None
+    ref.backward(gout)
+    Ad, W2d, b2d, h2d, gd, btd = d(A), d(W2), d(b2), d(h2), d(gam), d(bet)
+    bn = (gd, btd, rm.to(DEV), rv.to(DEV), torch.zeros((), dtype=torch.long, device=DEV), 0.9, 1e-5)
+    got = ops.fc([ops.Seg(h2d), ops.Seg(Ad), ops.Seg(Ad, scale=st.amp), ops.Seg(Ad, scale=st.att)], W2d, b2d,
+                 K.ACT["none"], bn, True, residual=h2d)
+    got.backward(gout.to(DEV))
+    out += [("fc/scaled/fwd", rel(got, ref), 2e-5), ("fc/scaled/dA", rel(Ad.grad, A.grad), 5e-5),
+            ("fc/scaled/dh", rel(h2d.grad, h2.grad), 5e-5), ("fc/scaled/dW", rel(W2d.grad, W2.grad), 5e-5)]
+    return out
+
+
+# ------------------------------------------------------------------------------------------ whole models
+def _models(s2, s3, trained=True):
+    c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
+    st2, st3 = O.init_pna_state(c2, s2, trained), O.init_net3d_state(c3, s3, trained)
+    pna = i3d.PNA(avg_d=1, device=DEV, **O.PRETRAIN_QM9_PNA)
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **O.PRETRAIN_QM9_NET3D)
+    pna.load_state_dict(st2)
+    n3.load_state_dict(st3)
+    return c2, c3, st2, st3, pna.to(DEV), n3.to(DEV)
+
+
+def case_golden(name="qm9_b8"):
+    """CUDA path against the vectors emitted by the reference's own modules (tests/golden)."""
+    from oracle.make_golden import CASES, TAU, grad_fingerprint
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    bseed, B, shape, C, loss_name, (s2, s3) = CASES[name]
+    b = syn.make_batch(bseed, B, shape=shape, conformers=C)
+    out = []
+    for mode in ("eval", "train"):
+        c2, c3, st2, st3, pna, n3 = _models(s2, s3)
+        pna.train(mode == "train"), n3.train(mode == "train")
+        g2, g3 = i3d.batch_from_numpy(b, DEV)
+        z2, z3 = pna(g2), n3(g3)
+        loss = getattr(i3d, loss_name)(tau=TAU)(z2, z3)
+        tag = "golden/%s/%s" % (name, mode)
+        out += [(tag + "/z2d", rel(z2, gold["z2d_" + mode]), 1e-4), (tag + "/z3d", rel(z3, gold["z3d_" + mode]), 1e-4),
+                (tag + "/loss", abs(loss.item() - float(gold["loss_" + mode])), 1e-4)]
+        if mode == "train":
+            st = g2._i3d_struct
+            out += [(tag + "/csr_rowptr", exact(st.rowptr, gold["csr_rowptr"]), 0),
+                    (tag + "/csr_col", exact(st.src_csr, gold["csr_col"]), 0),
+                    (tag + "/csr_eid", exact(st.eid, gold["csr_eid"]), 0)]
+            loss.backward()
+            scale = float(gold["grad_scale"])
+            named = dict([("2d." + k, p) for k, p in pna.named_parameters()] + [("3d." + k, p) for k, p in n3.named_parameters()])
+            worst = 0.0
+            for k, fp in zip(gold["grad_keys"], gold["grad_fp"]):
+                mine = grad_fingerprint(named[str(k)].grad.cpu())
+                worst = max(worst, float(np.abs(mine[2:] - fp[2:]).max()) / scale)
+            out.append((tag + "/param_grads(all, sampled)", worst, 2e-4))
+            for k in gold.files:
+                if k.startswith("grad3d/"):
+                    out.append((tag + "/" + k, float(np.abs(named["3d." + k[7:]].grad.cpu().numpy() - gold[k]).max()) / scale, 2e-4))
+                if k.startswith("grad2d/"):
+                    out.append((tag + "/" + k, float(np.abs(named["2d." + k[7:]].grad.cpu().numpy() - gold[k]).max()) / scale, 2e-4))
+                if k.startswith("buf2d/"):
+                    out.append((tag + "/" + k, rel(pna.state_dict()[k[6:]], gold[k]), 1e-4))
+                if k.startswith("buf3d/"):
+                    out.append((tag + "/" + k, rel(n3.state_dict()[k[6:]], gold[k]), 1e-4))
+    return out
+
+
+def case_golden_qmugs():
+    return case_golden("qmugs_b6_c3")
+
+
+def case_train_steps(B=16, steps=3, captured=False, seed=21):
+    """Three optimisation steps (fwd, bwd, Adam) against the CPU oracle trainer on the same batches."""
+    c2, c3, st2, st3, pna, n3 = _models(31, 32)
+    otr = O.OracleTrainer(c2, c3, st2, st3, loss="NTXent", tau=0.1, lr=8e-5)
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), DEV, {"lr": 8e-5}, graph_safe=captured)
+    out = []
+    b = syn.make_batch(seed, B)
+    cap = None
+    if captured:
+        # CapturedStep runs ONE eager warm-up step on the example batch before capturing: mirror it in the oracle
+        otr.step(*O.graphs_from_batch(b))
+        g2, g3 = i3d.batch_from_numpy(b, DEV)
+        cap = i3d.CapturedStep(tr, g2, g3, warmup=1)
+    for s in range(steps):
+        if not captured:
+            b = syn.make_batch(seed + s, B)
+        ol, _, _ = otr.step(*O.graphs_from_batch(b))
+        g2, g3 = i3d.batch_from_numpy(b, DEV)
+        if captured:
+            cap.load(g2, g3)
+            l = cap.run()
+        else:
+            l, _, _ = tr.process_batch(([g2], [g3]))
+        out.append(("train%s/step%d/loss" % ("_captured" if captured else "", s), abs(l.item() - ol.item()), 1e-4))
+    named = dict([("2d." + k, p) for k, p in pna.named_parameters()] + [("3d." + k, p) for k, p in n3.named_parameters()])
+    # parameters whose gradient is mathematically zero (a bias that feeds a BatchNorm): Adam turns their rounding
+    # noise into +-lr steps, so they are compared for size only
+    zero_grad = ("pretrans.fully_connected.1.linear.bias", "posttrans.fully_connected.0.linear.bias",
+                 "pretrans.fully_connected.0.batch_norm.bias", "update_network.fully_connected.0.linear.bias")
+    n_steps = steps + (1 if captured else 0)
+    worst_p, bad, total = 0.0, 0, 0
+    for k, p in named.items():
+        ref = (otr.st2d if k.startswith("2d.") else otr.st3d)[k[3:]].detach()
+        worst_p = max(worst_p, rel(p, ref))
+        if any(z in k for z in zero_grad):
+            continue
+        err = (p.detach().cpu() - ref).abs() / (8e-5 * n_steps)          # error in units of the total Adam travel
+        bad += int((err > 0.05).sum())
+        total += err.numel()
+    tag = "train_captured" if captured else "train"
+    out += [(tag + "/params_after_%d_steps" % n_steps, worst_p, 1e-3),
+            (tag + "/fraction_of_weights_off_by_>5%%_of_update", bad / max(total, 1), 1e-3)]
+    return out
+
+
+def case_train_steps_captured():
+    return case_train_steps(captured=True)
+
+
+def case_full_size_properties():
+    """BASELINE config-2 size (B=512): properties that do not need the oracle to finish in seconds."""
+    out = []
+    b = syn.make_batch(5, 512)
+    c2, c3, st2, st3, pna, n3 = _models(41, 42)
+    pna.eval(), n3.eval()
+    with torch.no_grad():
+        g2, g3 = i3d.batch_from_numpy(b, DEV)
+        z2, z3 = pna(g2), n3(g3)
+        # molecules are independent in eval mode: the first 8 molecules alone give the same embeddings
+        nb = {k: v for k, v in b.items()}
+        n8, e8 = int(b["num_nodes"][:8].sum()), int(b["num_edges"][:8].sum())
+        n38, e38 = int(b["num_nodes3"][:8].sum()), int(b["num_edges3"][:8].sum())
+        nb.update(x_atom=b["x_atom"][:n8], e_attr=b["e_attr"][:e8], src=b["src"][:e8], dst=b["dst"][:e8],
+                  num_nodes=b["num_nodes"][:8], num_edges=b["num_edges"][:8], src3=b["src3"][:e38], dst3=b["dst3"][:e38],
+                  d3=b["d3"][:e38], num_nodes3=b["num_nodes3"][:8], num_edges3=b["num_edges3"][:8])
+        h2, h3 = i3d.batch_from_numpy(nb, DEV)
+        y2, y3 = pna(h2), n3(h3)
+        out += [("full/block_independence_2d", rel(y2, z2[:8]), 2e-5), ("full/block_independence_3d", rel(y3, z3[:8]), 2e-5)]
+        # oracle on the 8-molecule slice
+        og2, xa, ea, og3, d3 = O.graphs_from_batch(nb)
+        r2 = O.pna_forward(O.as_leaf_params(st2), c2, og2, xa, ea, False)
+        r3 = O.net3d_forward(O.as_leaf_params(st3), c3, og3, d3, False)
+        out += [("full/slice_vs_oracle_2d", rel(y2, r2), 1e-4), ("full/slice_vs_oracle_3d", rel(y3, r3), 1e-4)]
+        st = g2._i3d_struct
+        rowptr, col, eid = O.csr_reference(b["src"], b["dst"], len(b["x_atom"]))
+        out += [("full/csr_eid", exact(st.eid, eid), 0), ("full/csr_rowptr", exact(st.rowptr, rowptr), 0)]
+        loss = i3d.NTXent(tau=0.1)(z2, z3)
+        out.append(("full/loss_vs_oracle_loss_on_gpu_embeddings",
+                    abs(loss.item() - O.ntxent(z2.cpu(), z3.cpu(), 0.1).item()), 1e-4))
+    return out
+
+
+ALL_CASES = [case_csr, case_embed, case_gemm, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
+             case_ntxent, case_adam, case_fc, case_golden, case_golden_qmugs, case_train_steps,
+             case_train_steps_captured, case_full_size_properties]

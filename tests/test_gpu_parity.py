@@ -1,0 +1,44 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the CPU oracle / golden vectors (cases in gpu_cases.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    if not torch.cuda.is_available():
+        return []
+    import gpu_cases
+    return gpu_cases.ALL_CASES
+
+
+def _names():
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(__file__), "gpu_cases.py")).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "ALL_CASES":
+            return [e.id for e in node.value.elts]
+    return []
+
+
+@pytest.mark.parametrize("case_name", _names())
+def test_case(case_name):
+    import gpu_cases
+    results = getattr(gpu_cases, case_name)()
+    assert results, "case produced no checks"
+    failures = ["%s: err %.3e > tol %.1e" % (l, e, t) for l, e, t in results if not (e <= t)]
+    assert not failures, "\n".join(failures)
+
+
+def test_native_library_is_the_compute_path():
+    """the product must fail loudly without its extension and must have launched its own kernels"""
+    import importlib
+    lib = importlib.import_module("3dinfomax_b200.lib")
+    K = importlib.import_module("3dinfomax_b200.kernels")
+    n0 = lib.launch_count()
+    K.add(torch.ones(8, device="cuda"), torch.ones(8, device="cuda"))
+    assert lib.launch_count() == n0 + 1
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        K.add(torch.ones(8), torch.ones(8))

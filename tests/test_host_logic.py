@@ -1,0 +1,109 @@
+"""CPU: host-side logic of the product — plugin surface, state-dict contract, input generator, failure modes."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+i3d = importlib.import_module("3dinfomax_b200")
+syn = i3d.synthetic
+
+
+def test_plugin_names_and_kwargs():
+    pna = i3d.PNA(avg_d=1, device="cpu", some_unknown_kwarg=3, **O.PRETRAIN_QM9_PNA)       # train.py:208 call shape
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **O.PRETRAIN_QM9_NET3D)                # train.py:167-172
+    assert sum(p.numel() for p in pna.parameters()) == 4981856
+    assert sum(p.numel() for p in n3.parameters()) == 17617
+    assert isinstance(i3d.NTXent(tau=0.1), torch.nn.Module)
+    assert isinstance(i3d.NTXentMultiplePositives(tau=0.1), torch.nn.Module)
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
+    st2, st3 = O.init_pna_state(c2, 0), O.init_net3d_state(c3, 0)
+    pna = i3d.PNA(**O.PRETRAIN_QM9_PNA)
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, **O.PRETRAIN_QM9_NET3D)
+    assert set(pna.state_dict().keys()) == set(st2.keys())
+    assert set(n3.state_dict().keys()) == set(st3.keys())
+    pna.load_state_dict(st2, strict=True)
+    n3.load_state_dict(st3, strict=True)
+    for k, v in pna.state_dict().items():
+        assert v.shape == st2[k].shape, k
+    # optimizer grouping keys on the substring 'batch_norm' (trainer/self_supervised_trainer.py:79-82)
+    bn = [k for k, _ in pna.named_parameters() if "batch_norm" in k]
+    assert len(bn) == 2 * 22
+    assert "node_gnn.mp_layers.0.pretrans.fully_connected.0.linear.weight" in dict(pna.named_parameters())
+
+
+def test_fresh_init_follows_the_reference_initialisers():
+    torch.manual_seed(0)
+    pna = i3d.PNA(**O.PRETRAIN_QM9_PNA)
+    w = pna.node_gnn.mp_layers[0].pretrans.fully_connected[0].linear.weight
+    bound = (1 / 600) * np.sqrt(6 / (600 + 200))                      # xavier_uniform_(w, gain=1/in_dim)
+    assert w.abs().max().item() <= bound and w.abs().max().item() > 0.9 * bound
+    assert pna.node_gnn.mp_layers[0].pretrans.fully_connected[0].linear.bias.abs().max().item() == 0
+    e = pna.node_gnn.atom_encoder.atom_embedding_list[0].weight
+    assert e.shape == (119, 200) and e.abs().max().item() <= np.sqrt(6 / (119 + 200)) + 1e-6
+
+
+def test_unsupported_configs_fail_loudly():
+    bad = dict(O.PRETRAIN_QM9_PNA, aggregators=["mean", "sum"])
+    with pytest.raises(NotImplementedError):
+        i3d.PNA(**bad)
+    with pytest.raises(NotImplementedError):
+        i3d.PNA(**dict(O.PRETRAIN_QM9_PNA, dropout=0.1))
+    with pytest.raises(ValueError):
+        i3d.Net3D(node_dim=0, edge_dim=1, **dict(O.PRETRAIN_QM9_NET3D, reduce_func="max"))
+    with pytest.raises(AssertionError):
+        i3d.PNA(**dict(O.PRETRAIN_QM9_PNA, activation="not_an_activation"))
+    with pytest.raises(NotImplementedError):
+        i3d.NTXent(tau=0.1, variance_reg=1.0)
+
+
+def test_no_cpu_fallback():
+    pna = i3d.PNA(**O.PRETRAIN_QM9_PNA)
+    g2, _ = i3d.batch_from_numpy(syn.make_batch(0, 2), "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pna(g2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        i3d.NTXent(tau=0.1)(torch.randn(4, 8), torch.randn(4, 8))
+
+
+def test_synthetic_batch_contract():
+    b = syn.make_batch(7, 64)
+    N, E = len(b["x_atom"]), len(b["src"])
+    assert b["num_nodes"].sum() == N and b["num_edges"].sum() == E
+    # both directions stored, reverse pair adjacent (datasets/qm9_dataset.py:431-435)
+    assert np.array_equal(b["src"][0::2], b["dst"][1::2]) and np.array_equal(b["dst"][0::2], b["src"][1::2])
+    assert np.array_equal(b["e_attr"][0::2], b["e_attr"][1::2])
+    deg = np.bincount(b["dst"], minlength=N)
+    assert deg.min() >= 1 and deg.max() <= 4
+    for c, d in enumerate(syn.ATOM_FEATURE_DIMS):
+        assert b["x_atom"][:, c].min() >= 0 and b["x_atom"][:, c].max() < d
+    for c, d in enumerate(syn.BOND_FEATURE_DIMS):
+        assert b["e_attr"][:, c].max() < d
+    # block diagonal: no edge crosses a molecule boundary
+    ptr = np.concatenate([[0], np.cumsum(b["num_nodes"])])
+    mol_of = np.repeat(np.arange(64), b["num_nodes"])
+    assert np.array_equal(mol_of[b["src"]], mol_of[b["dst"]])
+    # complete graphs: n(n-1) edges, src = repeat_interleave(arange(n), n-1) (datasets/qm9_dataset.py:215-217)
+    assert np.array_equal(b["num_edges3"], b["num_nodes3"] * (b["num_nodes3"] - 1))
+    n0 = int(b["num_nodes3"][0])
+    assert np.array_equal(b["src3"][:n0 * (n0 - 1)], np.repeat(np.arange(n0), n0 - 1))
+    assert b["d3"].dtype == np.float32 and b["d3"].shape == (len(b["src3"]), 1) and b["d3"].min() > 0
+    assert ptr[-1] == N
+    again = syn.make_batch(7, 64)
+    assert all(np.array_equal(b[k], again[k]) for k in b if isinstance(b[k], np.ndarray))
+    c3 = syn.make_batch(1, 4, shape="qmugs", conformers=3)
+    assert len(c3["num_nodes3"]) == 12 and np.array_equal(c3["num_nodes3"][0::3], c3["num_nodes"])
+
+
+def test_graph_batch_mirrors_dgl_surface():
+    g2, g3 = i3d.batch_from_numpy(syn.make_batch(0, 3), "cpu")
+    assert g2.number_of_nodes() == int(g2.batch_num_nodes().sum()) and g2.batch_size == 3
+    s, d = g2.edges()
+    assert s.dtype == torch.int64 and len(s) == g2.number_of_edges() == int(g2.batch_num_edges().sum())
+    assert g2.ndata["feat"].shape[1] == 9 and g2.edata["feat"].shape[1] == 3 and g3.edata["d"].shape[1] == 1
+    assert g2.to("cpu").ndata["feat"].dtype == torch.int64
