@@ -39,7 +39,8 @@ class NTXentMultiplePositives(_NTXentBase):
 
     def forward(self, z1, z2, row_offset=0, total_rows=None, conformers=None, **kwargs):
         if conformers is None:
-            if z2.shape[0] % z1.shape[0] != 0:
-                raise ValueError("z2 rows must be a multiple of z1 rows")
-            conformers = z2.shape[0] // z1.shape[0]
+            rows = z1.shape[0] if total_rows is None else int(total_rows)   # z2 may be the all-gathered column set
+            if z2.shape[0] % rows != 0:
+                raise ValueError("z2 rows must be a multiple of the number of molecules")
+            conformers = z2.shape[0] // rows
         return ops.ntxent(z1, z2, conformers, self.tau, self.norm, 0.0, row_offset, total_rows)
