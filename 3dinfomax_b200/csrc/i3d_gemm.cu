@@ -270,7 +270,20 @@ __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int l
 
 }  // namespace i3d
 
+namespace i3d {
+bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+int gemm_tc_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+               int accumulate, cudaStream_t stream);
+static int g_gemm_backend = 0;   // 0: tensor cores (tcgen05) where eligible, fp32 SIMT otherwise; 1: SIMT only
+}  // namespace i3d
+
 using namespace i3d;
+
+extern "C" int i3d_gemm_backend(int backend) {
+  const int old = g_gemm_backend;
+  if (backend == 0 || backend == 1) g_gemm_backend = backend;
+  return old;
+}
 
 extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                         const float* bias, int accumulate, void* stream) {
@@ -279,6 +292,12 @@ extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_se
   if (M == 0 || N == 0) return I3D_OK;
   I3D_REQUIRE(C != nullptr, "C is null");
   I3D_REQUIRE(mode != I3D_GEMM_TN || n_seg == 1, "TN mode takes exactly one segment");
+  for (int s = 0; s < n_seg; ++s) {
+    I3D_REQUIRE(segs[s].K >= 0 && (segs[s].K == 0 || (segs[s].A && segs[s].B)), "segment operand is null");
+    I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
+  }
+  if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs))
+    return gemm_tc_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, as_stream(stream));
   GemmParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {

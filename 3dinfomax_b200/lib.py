@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "i3d.h")
 SO_PATH = os.path.join(_HERE, "lib3dinfomax_b200.so")
-SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_net3d.cu", "i3d_gemm.cu",
+SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_net3d.cu", "i3d_gemm.cu", "i3d_gemm_tc.cu",
            "i3d_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
@@ -45,6 +45,7 @@ SIGNATURES = {
     "i3d_degree_scalers": (_I, [_P, _L, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
+    "i3d_gemm_backend": (_I, [_I]),
     "i3d_gemm": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P]),
     "i3d_act_colstats": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "i3d_bn_apply": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),

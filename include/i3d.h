@@ -97,7 +97,10 @@ typedef struct {
   int32_t lda, ldb;     /* leading dimensions (elements)                                              */
 } i3d_gemm_seg;
 
-/* segs: HOST array of n_seg (<=4) descriptors.  bias[N] optional (added once).  accumulate!=0: C += */
+/* segs: HOST array of n_seg (<=4) descriptors.  bias[N] optional (added once).  accumulate!=0: C +=
+ * Backend: tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-level accuracy, accumulator in TMEM) for
+ * the shapes it covers, the fp32 SIMT kernel otherwise.  i3d_gemm_backend(1) forces SIMT; returns the old value. */
+int i3d_gemm_backend(int backend);
 int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
              const float* bias, int accumulate, void* stream);
 

@@ -196,6 +196,46 @@ def case_gemm():
     return out
 
 
+def case_gemm_tc():
+    """tcgen05 (3xTF32, TMEM accumulator) backend against fp64 and against the fp32 SIMT backend of the same ABI."""
+    g = gen(40)
+    out = []
+    rn = lambda *s: torch.randn(*s, generator=g)
+    L = i3d.lib.load()
+    for tag, M, N, Ks, gather, scale, bias, accum in [
+        ("fc1_gather3", 19000, 200, [200, 200, 200], True, False, True, False),
+        ("fc2_plain", 4111, 200, [200], False, False, True, False),
+        ("posttrans_scale4", 9226, 200, [200, 800, 800, 800], False, True, True, False),
+        ("k_tail_36", 1000, 200, [36], False, False, False, False),
+        ("n256_head", 512, 256, [200], False, False, True, True),
+        ("n512_two_tiles", 2048, 512, [256], False, False, False, False),
+        ("n32_net3d", 30000, 20, [20, 20, 20], True, False, True, False),
+        ("n64", 777, 64, [64], False, False, False, False),
+    ]:
+        segs, rows = [], 5000
+        for Kd in Ks:
+            s = {"K": Kd, "A": rn(rows if gather else M, Kd), "B": rn(N, Kd)}
+            if gather:
+                s["a_idx"] = torch.randint(0, rows, (M,), generator=g).int()
+            if scale and len(segs) > 0:
+                s["scale"] = rn(M)
+            segs.append(s)
+        b = rn(N) if bias else None
+        C0 = rn(M, N) if accum else None
+        ref = _gemm_ref(K.NT, M, N, segs, b, C0)
+        dsegs = _to_dev(segs)
+        res = {}
+        for backend in (0, 1):
+            L.i3d_gemm_backend(backend)
+            C = C0.clone().to(DEV) if accum else torch.full((M, N), float("nan"), device=DEV)
+            K.gemm(K.NT, M, N, dsegs, C, None if b is None else b.to(DEV), accum)
+            res[backend] = C
+        L.i3d_gemm_backend(0)
+        out += [("gemm_tc/%s/vs_fp64" % tag, rel(res[0], ref), 2e-5),
+                ("gemm_tc/%s/simt_vs_fp64" % tag, rel(res[1], ref), 2e-5)]
+    return out
+
+
 # --------------------------------------------------------------------------------------- FC tail (BN)
 def case_bn():
     g = gen(5)
@@ -641,6 +681,6 @@ def case_full_size_properties():
     return out
 
 
-ALL_CASES = [case_csr, case_embed, case_gemm, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
+ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_golden, case_golden_qmugs, case_train_steps,
              case_train_steps_captured, case_full_size_properties]
