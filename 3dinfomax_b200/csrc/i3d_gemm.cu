@@ -272,12 +272,43 @@ __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int l
 
 namespace i3d {
 bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
-int gemm_tc_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, cudaStream_t stream);
+int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+            int accumulate, cudaStream_t stream);
+
+// out[c, r] = in[r, c]  (32x32 shared-memory tiles, coalesced on both sides)
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in,
+                                 float* __restrict__ out, int ld_out) {
+  __shared__ float t[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = t[threadIdx.x][i];
+  }
+}
 static int g_gemm_backend = 0;   // 0: tensor cores (tcgen05) where eligible, fp32 SIMT otherwise; 1: SIMT only
 }  // namespace i3d
 
 using namespace i3d;
+
+extern "C" int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in, float* out, int ld_out, void* stream) {
+  I3D_REQUIRE(rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= rows && (rows * cols == 0 || (in && out)),
+              "invalid argument");
+  if (rows == 0 || cols == 0) return I3D_OK;
+  const int64_t gx = (rows + 31) / 32;
+  const int gy = (cols + 31) / 32;
+  I3D_REQUIRE(gx < (1ll << 31) && gy <= 65535, "matrix too large");
+  transpose_kernel<<<dim3((unsigned)gx, gy), dim3(32, 8), 0, as_stream(stream)>>>(in, rows, cols, ld_in, out, ld_out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
 
 extern "C" int i3d_gemm_backend(int backend) {
   const int old = g_gemm_backend;
@@ -297,7 +328,7 @@ extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_se
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
   if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs))
-    return gemm_tc_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, as_stream(stream));
+    return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, as_stream(stream));
   GemmParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {

@@ -129,6 +129,15 @@ def gemm(mode, M, N, segs, C, bias=None, accumulate=False):
     return C
 
 
+def transpose(x):
+    """[R, C] (unit inner stride) -> contiguous [C, R]"""
+    px, ldx = _mat(x, "x")
+    R, C = x.shape
+    out = torch.empty(C, R, dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_transpose(px, R, C, ldx, _p(out), R, _s()), "i3d_transpose")
+    return out
+
+
 # ------------------------------------------------------------------------------ FC tail (act+BN)
 def act_colstats(Y, act):
     py, ldy = _mat(Y, "Y")

@@ -46,6 +46,7 @@ SIGNATURES = {
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_gemm_backend": (_I, [_I]),
+    "i3d_transpose": (_I, [_P, _L, _I, _I, _P, _I, _P]),
     "i3d_gemm": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P]),
     "i3d_act_colstats": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "i3d_bn_apply": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),

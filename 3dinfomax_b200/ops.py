@@ -108,18 +108,24 @@ class _FC(torch.autograd.Function):
             if ctx.needs_input_grad[6 + i]:
                 groups.setdefault(x.data_ptr(), []).append((i, s, x, off))
             off += k
+        Wt = None
         for members in groups.values():
             x0 = members[0][2]
             R, k = x0.shape
             dx = torch.empty(R, k, dtype=torch.float32, device=W.device)
+            # dx = dy W is fed to the tensor-core NT kernel as dy (W^T)^T: one small transpose of the weight per
+            # backward instead of a second operand-staging variant
+            via_nt = R >= 256 and Fout % 4 == 0 and k % 4 == 0
+            if via_nt and Wt is None:
+                Wt = K.transpose(W)                                  # [in_features, out_features]
             nn = []
             for (_i, s, _x, o) in members:
                 if s.idx is None:
                     a = dY
                 else:
                     a = K.segment_sum_fwd(dY, s.inv_rowptr, s.inv_idx)
-                nn.append({"A": a, "B": W[:, o:o + k], "K": Fout, "scale": s.scale})
-            K.gemm(K.NN, R, k, nn, dx)
+                nn.append({"A": a, "B": Wt[o:o + k, :] if via_nt else W[:, o:o + k], "K": Fout, "scale": s.scale})
+            K.gemm(K.NT if via_nt else K.NN, R, k, nn, dx)
             dxs[members[0][0]] = dx
         dres = dO if (ctx.has_res and ctx.needs_input_grad[5]) else None
         return (None, dW, db, dgamma, dbeta, dres) + tuple(dxs)
@@ -326,7 +332,10 @@ class _NTXent(torch.autograd.Function):
         G = P
         dn1, dn2 = K.ntxent_rows_bwd(G, B, Bc, C, n1, n2, norm, eps, tau, row_offset, rowstats, gout, inv_B)
         dz1 = torch.empty_like(z1)
-        K.gemm(K.NN, B, D, [{"A": G, "B": z2, "K": Bc * C}], dz1)
+        if B >= 256 and (Bc * C) % 4 == 0:
+            K.gemm(K.NT, B, D, [{"A": G, "B": K.transpose(z2), "K": Bc * C}], dz1)     # tensor-core NT path
+        else:
+            K.gemm(K.NN, B, D, [{"A": G, "B": z2, "K": Bc * C}], dz1)
         dz2 = torch.empty_like(z2)
         K.gemm(K.TN, Bc * C, D, [{"A": G, "B": z1, "K": B}], dz2)
         if norm:

@@ -101,6 +101,8 @@ typedef struct {
  * Backend: tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-level accuracy, accumulator in TMEM) for
  * the shapes it covers, the fp32 SIMT kernel otherwise.  i3d_gemm_backend(1) forces SIMT; returns the old value. */
 int i3d_gemm_backend(int backend);
+/* out[c, r] = in[r, c]; used to hand W^T to the NT kernel so that dx = dy W runs on the same tensor-core path */
+int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in, float* out, int ld_out, void* stream);
 int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
              const float* bias, int accumulate, void* stream);
 

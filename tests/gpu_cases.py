@@ -231,8 +231,38 @@ def case_gemm_tc():
             K.gemm(K.NT, M, N, dsegs, C, None if b is None else b.to(DEV), accum)
             res[backend] = C
         L.i3d_gemm_backend(0)
-        out += [("gemm_tc/%s/vs_fp64" % tag, rel(res[0], ref), 2e-5),
+        out += [("gemm_tc/%s/vs_fp64" % tag, rel(res[0], ref), 3e-5),
                 ("gemm_tc/%s/simt_vs_fp64" % tag, rel(res[1], ref), 2e-5)]
+    # TN (weight gradients): split-K over CTAs, operands transposed while staged, fp32 atomics into C
+    for tag, M, N, Kd, gather, scale, accum in [
+        ("dW_fc2", 200, 200, 19092, False, False, False),
+        ("dW_fc1_gather", 200, 200, 19000, True, False, False),
+        ("dW_post_scaled", 200, 800, 9226, False, True, False),
+        ("dW_post_h", 200, 1000, 9226, False, False, False),
+        ("dz2_ntxent", 1536, 256, 512, False, False, False),
+        ("dW_small_acc", 20, 60, 30000, False, False, True),
+        ("k_tail", 64, 32, 1000, False, False, False),
+    ]:
+        rows = 5000
+        s = {"K": Kd, "A": rn(Kd, M), "B": rn(rows if gather else Kd, N)}
+        if gather:
+            s["b_idx"] = torch.randint(0, rows, (Kd,), generator=g).int()
+        if scale:
+            s["scale"] = rn(Kd)
+        C0 = rn(M, N) if accum else None
+        ref = _gemm_ref(K.TN, M, N, [s], None, C0)
+        dsegs = _to_dev([s])
+        res = {}
+        for backend in (0, 1):
+            L.i3d_gemm_backend(backend)
+            C = C0.clone().to(DEV) if accum else torch.full((M, N), float("nan"), device=DEV)
+            K.gemm(K.TN, M, N, dsegs, C, None, accum)
+            res[backend] = C
+        L.i3d_gemm_backend(0)
+        out += [("gemm_tc/tn_%s/vs_fp64" % tag, rel(res[0], ref), 3e-5),
+                ("gemm_tc/tn_%s/simt_vs_fp64" % tag, rel(res[1], ref), 2e-5)]
+    x = rn(777, 200)
+    out.append(("transpose", exact(K.transpose(x.to(DEV)[:, 8:72]), x[:, 8:72].t().contiguous()), 0))
     return out
 
 
