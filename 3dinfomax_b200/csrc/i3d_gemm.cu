@@ -273,7 +273,8 @@ __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int l
 namespace i3d {
 bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, cudaStream_t stream);
+            int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 
 // out[c, r] = in[r, c]  (32x32 shared-memory tiles, coalesced on both sides)
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in,
@@ -316,8 +317,18 @@ extern "C" int i3d_gemm_backend(int backend) {
   return old;
 }
 
+extern "C" size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
+  if (g_gemm_backend != 0 || !segs || n_seg < 1 || n_seg > 4 || mode < 0 || mode > 2) return 0;
+  return gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
+}
+
 extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                         const float* bias, int accumulate, void* stream) {
+  return i3d_gemm_ex(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                           const float* bias, int accumulate, void* ws, size_t ws_bytes, void* stream) {
   I3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be NT, NN or TN");
   I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N, "invalid shape");
   if (M == 0 || N == 0) return I3D_OK;
@@ -328,7 +339,7 @@ extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_se
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
   if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs))
-    return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, as_stream(stream));
+    return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, as_stream(stream));
   GemmParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {

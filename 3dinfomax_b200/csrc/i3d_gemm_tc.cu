@@ -3,13 +3,13 @@
 //   NT:  C[m, n] = bias[n] + sum_s sum_k  scale_s[m] * A_s[a_idx_s[m], k] * B_s[n, k]        (y = x W^T, dx = dy (W^T)^T)
 //   TN:  C[m, n] (+)= sum_k  scale[k] * A[a_idx[k], m] * B[b_idx[k], n]                      (dW = dy^T x, split over K)
 //
-// Why a hand-written kernel instead of cuBLAS: the operands are *virtual* — rows are gathered through the CSR
+// Why a hand-written kernel instead of cuBLAS: the A operand is *virtual* — rows are gathered through the CSR
 // edge lists (h[src], h[dst]) and scaled by the per-node degree scalers while they are staged, so neither
 // torch.cat nor index_select ever touches HBM (models/pna.py:207,232,249).  TMA cannot express that staging, so
-// operand tiles are produced by the CTA's own threads (LDG -> split -> STS in the canonical K-major SWIZZLE_128B
-// layout; TN transposes while staging), published to the async proxy with fence.proxy.async, and consumed by
-// tcgen05.mma issued by one thread.  The next k-block's global loads are issued before the barrier so that their
-// latency overlaps the MMA issue and the wait for the stage to drain.
+// A tiles are produced by the CTA's own threads (LDG -> hi/lo split -> STS in the canonical K-major SWIZZLE_128B
+// layout, two k-blocks of register prefetch), published to the async proxy with fence.proxy.async, and consumed by
+// tcgen05.mma issued by one thread.  The dense B operand (weights) is split into hi/lo ONCE per call by a small
+// kernel and then streamed by TMA (cp.async.bulk.tensor, SWIZZLE_128B) straight into shared memory.
 //
 // Precision: the reference computes in fp32 (SGEMM).  Each fp32 operand is split into hi = tf32(x) and lo = x - hi
 // and three MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM ("3xTF32").  Measured against fp64
@@ -17,12 +17,14 @@
 // truncates, so the error grows with the number of accumulated MMAs); the fp32 SIMT backend gives 3e-7 .. 2e-6.
 //
 // Tile: 128 (M) x BN (N, multiple of 16, <= 256) x 32 (K = one 128-byte swizzle atom of tf32), 2 smem stages,
-// 256 threads: all threads stage operands, thread 0 issues the MMAs, 8 warps drain TMEM (tcgen05.ld 32x32b).
-#include "i3d_common.cuh"
+// 256 threads: all threads stage A, thread 0 issues TMA + MMAs, 8 warps drain TMEM through shared memory.
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "i3d_tc.cuh"
 
 namespace i3d {
-
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 256;
 
 struct TcParams {
   i3d_gemm_seg seg[4];
@@ -37,118 +39,9 @@ struct TcParams {
   int splits;   // TN: gridDim.z
 };
 
-// ------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier when all MMAs issued so far by this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, sm_100):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 1024 B (8 rows x 128 B)
-//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=TF32 [7,10)=[10,13)=2, K-major both,
-// N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// float offset of 16-byte chunk j (0..7) of row r inside a [rows x 32 tf32] K-major SWIZZLE_128B tile
-__device__ __forceinline__ int sw128_off(int r, int j) { return (r >> 3) * 256 + (r & 7) * 32 + ((j ^ (r & 7)) << 2); }
-
-__device__ __forceinline__ void split_store4(float* hi_tile, float* lo_tile, int off, float4 v) {
-  float4 h, l;
-  h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-  l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
-}
-__device__ __forceinline__ void split_store1(float* hi_tile, float* lo_tile, int off, float v) {
-  const float h = to_tf32(v);
-  hi_tile[off] = h;
-  lo_tile[off] = v - h;
-}
-
-template <int BN>
-struct TcLayout {
-  static constexpr int A_TILE = TC_BM * TC_BK;                 // floats
-  static constexpr int B_TILE = BN * TC_BK;
-  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // a_hi, a_lo, b_hi, b_lo
-  static constexpr size_t BYTES = (size_t)TC_STAGES * STAGE * 4 + 1024 /*align slack*/ + 64 /*barriers*/;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int B_CHUNKS = (BN * 8 + TC_THREADS - 1) / TC_THREADS;     // float4 per thread per k-block
-};
-
+// =================================================================================================================
+// Generic kernel: both operands staged by threads.  NT without a workspace, and TN (transposes while staging).
+// =================================================================================================================
 template <int MODE, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using L = TcLayout<BN>;
@@ -333,16 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-#pragma unroll
-      for (int ks = 0; ks < TC_BK / 8; ++ks) {
-        const uint32_t koff = ks * 32;                            // 8 tf32 = 32 bytes along K inside the swizzle atom
-        const uint64_t dah = make_smem_desc(sa_hi + koff), dal = make_smem_desc(sa_lo + koff);
-        const uint64_t dbh = make_smem_desc(sb_hi + koff), dbl = make_smem_desc(sb_lo + koff);
-        umma_tf32(tmem, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-        umma_tf32(tmem, dal, dbh, idesc, 1u);
-        umma_tf32(tmem, dah, dbl, idesc, 1u);
-      }
+      issue_kblock(tmem, a_hi, a_lo, b_hi, b_lo, idesc, it == 0);
       umma_commit(&bars[st]);    // frees this stage when the MMAs above are done (implies fence::before_thread_sync)
     }
   }
@@ -351,45 +235,178 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     mbar_wait(&bars[TC_STAGES], 0);
     tc_fence_after();
   }
-
-  // ---- epilogue: TMEM -> registers -> global.  warp w owns lanes [32*(w&3), +32) and column half (w>>2) ----
   const bool atomic = (MODE == I3D_GEMM_TN) && p.splits > 1;
-  const bool add_bias = p.bias && !(atomic && blockIdx.z != 0);
-  const int q = warp & 3, half = warp >> 2;
-  const int64_t row = m0 + q * 32 + lane;
-  constexpr int HALF_COLS = BN / 2;
-  const int c_begin = half * HALF_COLS;
-  if (total > 0 || !atomic) {
-    for (int c = c_begin; c < c_begin + HALF_COLS; c += 16) {
-      float v[16];
-      if (total > 0) {
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);    // warp-collective: no divergence around it
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      const int lim = min(16, c_begin + HALF_COLS - c);
-      if (row < M) {
-        float* out = p.C + row * p.ldc + n0 + c;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + c + i;
-          if (i < lim && n < N) {
-            float o = v[i] + (add_bias ? __ldg(p.bias + n) : 0.f);
-            if (atomic) {
-              atomicAdd(out + i, o);
-            } else {
-              if (p.accumulate) o += out[i];
-              out[i] = o;
-            }
-          }
-        }
-      }
-    }
-  }
+  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc,
+                  (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
+// =================================================================================================================
+// NT kernel with the B operand (weights) pre-split into hi / lo [N, Kpad_total] buffers and streamed by TMA.
+// =================================================================================================================
+struct TcTmaParams {
+  CUtensorMap map_hi, map_lo;       // [N rows, Kpad_total cols] fp32, box = [BN rows x 32 cols], SWIZZLE_128B
+  const float* A[4];
+  const int32_t* a_idx[4];
+  const float* scale[4];
+  int32_t lda[4], K[4], kcol0[4];   // kcol0: first column of the segment inside the split buffers (multiple of 32)
+  int n_seg;
+  int64_t M;
+  int N;
+  float* C;
+  int ldc;
+  const float* bias;
+  int accumulate;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __grid_constant__ TcTmaParams p) {
+  using L = TcLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)TC_STAGES * L::STAGE);
+  uint64_t* mma_done = bars;                      // [STAGES] stage may be overwritten
+  uint64_t* b_full = bars + TC_STAGES;            // [STAGES] TMA bytes of the stage have landed
+  uint64_t* acc_done = bars + 2 * TC_STAGES;      // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t M = p.M;
+  const int N = p.N;
+
+  if (warp == 0) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  if (tid == 32) {
+    for (int s = 0; s < 2 * TC_STAGES + 1; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.map_hi);
+    tma_prefetch_desc(&p.map_lo);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+
+  int total = 0;
+  for (int s = 0; s < p.n_seg; ++s) total += (p.K[s] + TC_BK - 1) / TC_BK;
+
+  // A prefetch cursor (runs two k-blocks ahead of the consumer) and its per-segment row bookkeeping
+  int pf_seg = 0, pf_k0 = 0;
+  int64_t a_row[4];
+  float a_sc[4];
+  auto bind_segment = [&](int s) {
+    const int32_t* __restrict__ a_idx = p.a_idx[s];
+    const float* __restrict__ scale = p.scale[s];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t gm = m0 + i * 32 + (tid >> 3);
+      a_row[i] = -1;
+      a_sc[i] = 1.f;
+      if (gm < M) {
+        a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : gm;
+        if (scale) a_sc[i] = __ldg(scale + gm);
+      }
+    }
+  };
+  bind_segment(0);
+  auto prefetch = [&](float4 (&va)[4]) {
+    const float* __restrict__ A = p.A[pf_seg];
+    const int lda = p.lda[pf_seg], K = p.K[pf_seg];
+    const int kc = pf_k0 + (tid & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_row[i] >= 0 && kc < K) {
+        v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
+        const float sc = a_sc[i];
+        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+      }
+      va[i] = v;
+    }
+    pf_k0 += TC_BK;
+    if (pf_k0 >= K && pf_seg + 1 < p.n_seg) {
+      pf_seg += 1;
+      pf_k0 = 0;
+      bind_segment(pf_seg);
+    }
+  };
+
+  // consumer cursor: column of the current k-block inside the split B buffers
+  int cs_seg = 0, cs_k0 = 0;
+
+  auto body = [&](int it, float4 (&va)[4]) {
+    const int st = it % TC_STAGES;
+    const int use = it / TC_STAGES;
+    float* a_hi = tiles + (size_t)st * L::STAGE;
+    float* a_lo = a_hi + L::A_TILE;
+    float* b_hi = a_lo + L::A_TILE;
+    float* b_lo = b_hi + L::B_TILE;
+    if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+    tc_fence_after();
+    if (tid == 0) {                         // B tiles of this k-block: two TMA boxes, one transaction barrier
+      const int kcol = p.kcol0[cs_seg] + cs_k0;
+      mbar_expect_tx(&b_full[st], 2u * BN * TC_BK * 4u);
+      tma_load_2d(b_hi, &p.map_hi, kcol, n0, &b_full[st]);
+      tma_load_2d(b_lo, &p.map_lo, kcol, n0, &b_full[st]);
+    }
+    cs_k0 += TC_BK;
+    if (cs_k0 >= p.K[cs_seg] && cs_seg + 1 < p.n_seg) {
+      cs_seg += 1;
+      cs_k0 = 0;
+    }
+    const int j = tid & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), va[i]);
+    fence_proxy_async();
+    if (it + 2 < total) prefetch(va);       // refill this register set with the k-block two iterations ahead
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(&b_full[st], (uint32_t)(use & 1));
+      tc_fence_after();
+      issue_kblock(tmem, a_hi, a_lo, b_hi, b_lo, idesc, it == 0);
+      umma_commit(&mma_done[st]);
+    }
+  };
+
+  float4 va0[4], va1[4];
+  if (total > 0) prefetch(va0);
+  if (total > 1) prefetch(va1);
+  for (int it = 0; it < total; it += 2) {
+    body(it, va0);
+    if (it + 1 < total) body(it + 1, va1);
+  }
+  if (total > 0) {
+    if (tid == 0) umma_commit(acc_done);
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+  }
+  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
+// hi[n, col0 + c] = tf32(B[n, c]),  lo = B - hi  for c < K;  zeros for K <= c < Kpad
+__global__ void split_tf32_kernel(const float* __restrict__ B, int N, int K, int ldb, float* __restrict__ hi,
+                                  float* __restrict__ lo, int ldo, int col0, int Kpad) {
+  const int quads = Kpad >> 2;
+  const int64_t total = (int64_t)N * quads;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(t / quads);
+    const int c = (int)(t - (int64_t)n * quads) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < K) v = __ldg(reinterpret_cast<const float4*>(B + (int64_t)n * ldb + c));
+    float4 h, l;
+    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + (int64_t)n * ldo + col0 + c) = h;
+    *reinterpret_cast<float4*>(lo + (int64_t)n * ldo + col0 + c) = l;
+  }
 }
 
 __global__ void tc_zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
@@ -400,19 +417,64 @@ __global__ void tc_zero_block_kernel(float* __restrict__ C, int64_t M, int N, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static bool make_b_map(CUtensorMap* map, float* base, int N, int ktot, int bn) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t bytes, bool* configured) {
+  if (*configured) return I3D_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("i3d_gemm(tc): cudaFuncSetAttribute -> %s", cudaGetErrorString(e));
+    return I3D_ERR_CUDA;
+  }
+  *configured = true;
+  return I3D_OK;
+}
+
+static int launched(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("i3d_gemm(tc): %s launch failed -> %s", what, cudaGetErrorString(e));
+    return I3D_ERR_CUDA;
+  }
+  count_launch();
+  return I3D_OK;
+}
+
 template <int MODE, int BN>
-static int launch_tc(TcParams& p, cudaStream_t s) {
+static int launch_generic(TcParams& p, cudaStream_t s) {
   using L = TcLayout<BN>;
   static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
-    if (e != cudaSuccess) {
-      set_error("i3d_gemm(tc): cudaFuncSetAttribute -> %s", cudaGetErrorString(e));
-      return I3D_ERR_CUDA;
-    }
-    configured = true;
-  }
+  if (int rc = set_smem(gemm_tc_kernel<MODE, BN>, L::BYTES, &configured)) return rc;
   const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
   const int gy = (p.N + BN - 1) / BN;
   int gz = 1;
@@ -429,17 +491,26 @@ static int launch_tc(TcParams& p, cudaStream_t s) {
     gz = p.splits;
     if (p.splits > 1 && !p.accumulate) {
       tc_zero_block_kernel<<<grid_for(p.M * p.N, 256), 256, 0, s>>>(p.C, p.M, p.N, p.ldc);
-      count_launch();
+      if (int rc = launched("zero")) return rc;
     }
   }
   gemm_tc_kernel<MODE, BN><<<dim3((unsigned)gx, gy, gz), TC_THREADS, L::BYTES, s>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("i3d_gemm(tc): launch failed -> %s", cudaGetErrorString(e));
+  return launched("gemm");
+}
+
+template <int BN>
+static int launch_tma(TcTmaParams& p, float* hi, float* lo, int ktot, cudaStream_t s) {
+  using L = TcLayout<BN>;
+  static bool configured = false;
+  if (int rc = set_smem(gemm_tc_nt_tma_kernel<BN>, L::BYTES, &configured)) return rc;
+  if (!make_b_map(&p.map_hi, hi, p.N, ktot, BN) || !make_b_map(&p.map_lo, lo, p.N, ktot, BN)) {
+    set_error("i3d_gemm(tc): cuTensorMapEncodeTiled failed");
     return I3D_ERR_CUDA;
   }
-  count_launch();
-  return I3D_OK;
+  const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
+  const int gy = (p.N + BN - 1) / BN;
+  gemm_tc_nt_tma_kernel<BN><<<dim3((unsigned)gx, gy, 1), TC_THREADS, L::BYTES, s>>>(p);
+  return launched("gemm(tma)");
 }
 
 static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
@@ -462,37 +533,62 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
   return false;
 }
 
-template <int MODE>
-static int dispatch_bn(TcParams& p, cudaStream_t stream) {
-  const int N = p.N;
-  const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
-  if (N <= 32) return launch_tc<MODE, 32>(p, stream);
-  if (N <= 64) return launch_tc<MODE, 64>(p, stream);
-  if (N <= 112) return launch_tc<MODE, 112>(p, stream);
-  if (N <= 128) return launch_tc<MODE, 128>(p, stream);
+static inline int kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
+
+// bytes of scratch that let the NT kernel stream the B operand by TMA (hi + lo copies, K padded per segment)
+size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
+  if (mode != I3D_GEMM_NT || !gemm_tc_eligible(mode, M, N, n_seg, segs)) return 0;
+  int64_t ktot = 0;
+  for (int s = 0; s < n_seg; ++s) ktot += kpad(segs[s].K);
+  return (size_t)2 * (size_t)N * (size_t)ktot * sizeof(float) + 256;
+}
+
+// pick the N tile: 208 covers the F=200 outputs of the PNA layers with one accumulator
+template <typename F>
+static int with_bn(int mode, int64_t M, int N, F&& f) {
+  const int64_t gx = (M + TC_BM - 1) / TC_BM;
+  if (N <= 32) return f(std::integral_constant<int, 32>());
+  if (N <= 64) return f(std::integral_constant<int, 64>());
+  if (N <= 112) return f(std::integral_constant<int, 112>());
+  if (N <= 128) return f(std::integral_constant<int, 128>());
   // few row tiles (node-level GEMMs at batch 512: 72 tiles on 148 SMs): split N over two CTAs to fill the machine
-  if (MODE == I3D_GEMM_NT && N <= 208 && gx * 2 <= sm_count()) return launch_tc<MODE, 112>(p, stream);
-  if (N <= 208) return launch_tc<MODE, 208>(p, stream);
-  if ((N + 207) / 208 <= (N + 255) / 256) return launch_tc<MODE, 208>(p, stream);   // same tile count, less padding
-  return launch_tc<MODE, 256>(p, stream);
+  if (mode == I3D_GEMM_NT && N <= 208 && gx * 2 <= sm_count()) return f(std::integral_constant<int, 112>());
+  if (N <= 208) return f(std::integral_constant<int, 208>());
+  if ((N + 207) / 208 <= (N + 255) / 256) return f(std::integral_constant<int, 208>());   // same tiles, less padding
+  return f(std::integral_constant<int, 256>());
 }
 
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, cudaStream_t stream) {
+            int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const size_t need = gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
+  if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && encode_tiled()) {
+    TcTmaParams p;
+    memset(&p, 0, sizeof(p));
+    int ktot = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;
+      p.lda[s] = segs[s].lda, p.K[s] = segs[s].K, p.kcol0[s] = ktot;
+      ktot += kpad(segs[s].K);
+    }
+    p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
+    float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
+    float* lo = hi + (size_t)N * ktot;
+    for (int s = 0; s < n_seg; ++s) {
+      const int kp = kpad(segs[s].K);
+      split_tf32_kernel<<<grid_for((int64_t)N * (kp / 4), 256), 256, 0, stream>>>(segs[s].B, N, segs[s].K, segs[s].ldb, hi,
+                                                                                   lo, ktot, p.kcol0[s], kp);
+      if (int rc = launched("split")) return rc;
+    }
+    return with_bn(mode, M, N, [&](auto bn) { return launch_tma<decltype(bn)::value>(p, hi, lo, ktot, stream); });
+  }
   TcParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];
-  p.n_seg = n_seg;
-  p.M = M;
-  p.N = N;
-  p.C = C;
-  p.ldc = ldc;
-  p.bias = bias;
-  p.accumulate = accumulate;
-  p.kchunk = 0;
-  p.splits = 1;
-  if (mode == I3D_GEMM_NT) return dispatch_bn<I3D_GEMM_NT>(p, stream);
-  return dispatch_bn<I3D_GEMM_TN>(p, stream);
+  p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
+  p.kchunk = 0, p.splits = 1;
+  if (mode == I3D_GEMM_NT)
+    return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_NT, decltype(bn)::value>(p, stream); });
+  return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_TN, decltype(bn)::value>(p, stream); });
 }
 
 }  // namespace i3d

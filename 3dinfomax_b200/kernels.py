@@ -124,8 +124,11 @@ def gemm(mode, M, N, segs, C, bias=None, accumulate=False):
         arr[i].K, arr[i].lda, arr[i].ldb = int(s["K"]), int(lda), int(ldb)
         keep.append(s)
     pc, ldc = _mat(C, "C")
-    _lib.check(_L().i3d_gemm(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                             1 if accumulate else 0, _s()), "i3d_gemm")
+    L = _L()
+    nws = int(L.i3d_gemm_ws_bytes(mode, M, N, len(segs), arr))
+    ws = torch.empty(nws, dtype=torch.uint8, device=C.device) if nws else None      # tf32 hi/lo copies of B for TMA
+    _lib.check(L.i3d_gemm_ex(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                             1 if accumulate else 0, _p(ws), nws, _s()), "i3d_gemm")
     return C
 
 

@@ -270,7 +270,8 @@ def run_b200(args):
 
         def summarise(rows):
             rows = rows[len(rows) // 3:]                     # drop the first instrumented step
-            t = sum(a.elapsed_time(b) for a, b, _ in rows) / len(rows)
+            ts = sorted(a.elapsed_time(b) for a, b, _ in rows)
+            t = ts[len(ts) // 2]                             # median: a cudaMalloc inside one launch must not count
             byts = sum(x for _, _, x in rows) / len(rows)
             return t, byts
         t_f, b_f = summarise(prof["fwd"])

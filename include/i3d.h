@@ -105,6 +105,12 @@ int i3d_gemm_backend(int backend);
 int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in, float* out, int ld_out, void* stream);
 int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
              const float* bias, int accumulate, void* stream);
+/* Same, with caller-owned device scratch: when ws_bytes >= i3d_gemm_ws_bytes(...) the NT kernel splits the dense B
+ * operand (weights) into tf32 hi/lo copies once and streams them by TMA instead of staging them through threads.
+ * i3d_gemm_ws_bytes returns 0 for problems that do not use scratch. */
+size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                const float* bias, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]
