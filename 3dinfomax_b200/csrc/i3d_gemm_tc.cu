@@ -100,7 +100,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   bind_segment(0);
 
   float4 va[4];
+  float va_sc[4];              // scale of each staged A chunk, applied at store time (keeps the loads a prefetch)
   float4 vb[L::B_CHUNKS];
+
+  // TN: the one k-row this thread stages in the k-block starting at k0 (indices resolved one block ahead)
+  int64_t tn_arow = -1, tn_brow = 0;
+  float tn_sc = 1.f;
+  auto tn_bind = [&](int k0) {
+    if (MODE != I3D_GEMM_TN) return;
+    const int k = k0 + (warp & 3) * 8 + (lane >> 2);
+    tn_arow = -1;
+    tn_sc = 1.f;
+    if (k < kend) {
+      tn_arow = p.seg[0].a_idx ? (int64_t)__ldg(p.seg[0].a_idx + k) : (int64_t)k;
+      tn_brow = p.seg[0].b_idx ? (int64_t)__ldg(p.seg[0].b_idx + k) : (int64_t)k;
+      if (p.seg[0].scale) tn_sc = __ldg(p.seg[0].scale + k);
+    }
+  };
+  tn_bind(cur_k0);
 
   // issue the global loads of the k-block under the cursor into registers (zero-filled outside the matrices)
   auto prefetch = [&]() {
@@ -112,12 +129,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a_row[i] >= 0 && kc < K) {
-          v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
-          const float sc = a_sc[i];
-          v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-        }
+        if (a_row[i] >= 0 && kc < K) v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
         va[i] = v;
+        va_sc[i] = a_sc[i];
       }
 #pragma unroll
       for (int i = 0; i < L::B_CHUNKS; ++i) {
@@ -133,43 +147,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         bind_segment(cur_seg);
       }
     } else {
-      // TN: tiles are transposed while staging.  One warp pass = 8 k-rows x 16 columns (float4 per lane).
+      // TN: tiles are transposed while staging.  One warp pass = 8 k-rows x 16 columns (float4 per lane); every
+      // pass of a thread reads the SAME k-row (k = k0 + (warp&3)*8 + lane>>2), whose gather indices / scale were
+      // loaded one k-block earlier (tn_arow / tn_brow / tn_sc) so that no data load waits on an index load.
       const float* __restrict__ A = p.seg[0].A;
       const float* __restrict__ B = p.seg[0].B;
-      const int32_t* __restrict__ a_idx = p.seg[0].a_idx;
-      const int32_t* __restrict__ b_idx = p.seg[0].b_idx;
-      const float* __restrict__ scale = p.seg[0].scale;
       const int lda = p.seg[0].lda, ldb = p.seg[0].ldb;
-      const int kl = lane >> 2, cg = (lane & 3) * 4;
+      const int cg = (lane & 3) * 4;
+      const bool kvalid = tn_arow >= 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int pid = warp + 8 * i;                    // 32 passes: 8 column blocks x 4 k blocks
-        const int k = cur_k0 + (pid & 3) * 8 + kl;
-        const int64_t m = m0 + (pid >> 2) * 16 + cg;
+        const int64_t m = m0 + ((warp + 8 * i) >> 2) * 16 + cg;       // 8 column blocks of 16
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < kend && m < M) {
-          const int64_t row = a_idx ? (int64_t)__ldg(a_idx + k) : (int64_t)k;
-          v = __ldg(reinterpret_cast<const float4*>(A + row * lda + m));
-          if (scale) {
-            const float sc = __ldg(scale + k);
-            v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-          }
-        }
+        if (kvalid && m < M) v = __ldg(reinterpret_cast<const float4*>(A + tn_arow * lda + m));
         va[i] = v;
+        va_sc[i] = tn_sc;
       }
 #pragma unroll
       for (int i = 0; i < L::B_CHUNKS; ++i) {
-        const int pid = warp + 8 * i;                    // BN/16 column blocks x 4 k blocks
-        const int k = cur_k0 + (pid & 3) * 8 + kl;
-        const int c = (pid >> 2) * 16 + cg;
+        const int c = ((warp + 8 * i) >> 2) * 16 + cg;                // BN/16 column blocks
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < BN && k < kend && n0 + c < N) {
-          const int64_t row = b_idx ? (int64_t)__ldg(b_idx + k) : (int64_t)k;
-          v = __ldg(reinterpret_cast<const float4*>(B + row * ldb + n0 + c));
-        }
+        if (kvalid && c < BN && n0 + c < N) v = __ldg(reinterpret_cast<const float4*>(B + tn_brow * ldb + n0 + c));
         vb[i] = v;
       }
       cur_k0 += TC_BK;
+      tn_bind(cur_k0);
     }
   };
 
@@ -177,7 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (MODE == I3D_GEMM_NT) {
       const int j = tid & 7;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), va[i]);
+      for (int i = 0; i < 4; ++i) {
+        float4 v = va[i];
+        const float sc = va_sc[i];
+        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+        split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), v);
+      }
 #pragma unroll
       for (int i = 0; i < L::B_CHUNKS; ++i) {
         const int r = (tid + i * TC_THREADS) >> 3;
@@ -190,7 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int pid = warp + 8 * i;
         const int kk = (pid & 3) * 8 + kl;               // k position inside the tile (0..31)
         const int r = (pid >> 2) * 16 + cg;              // tile row (= output row m)
-        const float e[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+        const float sc = va_sc[i];
+        const float e[4] = {va[i].x * sc, va[i].y * sc, va[i].z * sc, va[i].w * sc};
 #pragma unroll
         for (int q = 0; q < 4; ++q) split_store1(a_hi, a_lo, sw128_off(r + q, kk >> 2) + (kk & 3), e[q]);
       }
@@ -313,19 +321,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __g
     }
   };
   bind_segment(0);
-  auto prefetch = [&](float4 (&va)[4]) {
+  // NOTE: nothing in here may consume the loaded values (the scale is applied at store time), otherwise the
+  // loads stop being a prefetch
+  auto prefetch = [&](float4 (&va)[4], float (&vs)[4]) {
     const float* __restrict__ A = p.A[pf_seg];
     const int lda = p.lda[pf_seg], K = p.K[pf_seg];
     const int kc = pf_k0 + (tid & 7) * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_row[i] >= 0 && kc < K) {
-        v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
-        const float sc = a_sc[i];
-        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-      }
+      if (a_row[i] >= 0 && kc < K) v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
       va[i] = v;
+      vs[i] = a_sc[i];
     }
     pf_k0 += TC_BK;
     if (pf_k0 >= K && pf_seg + 1 < p.n_seg) {
@@ -338,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __g
   // consumer cursor: column of the current k-block inside the split B buffers
   int cs_seg = 0, cs_k0 = 0;
 
-  auto body = [&](int it, float4 (&va)[4]) {
+  auto body = [&](int it, float4 (&va)[4], float (&vs)[4]) {
     const int st = it % TC_STAGES;
     const int use = it / TC_STAGES;
     float* a_hi = tiles + (size_t)st * L::STAGE;
@@ -360,9 +367,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __g
     }
     const int j = tid & 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), va[i]);
+    for (int i = 0; i < 4; ++i) {
+      float4 v = va[i];
+      const float sc = vs[i];
+      v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+      split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), v);
+    }
     fence_proxy_async();
-    if (it + 2 < total) prefetch(va);       // refill this register set with the k-block two iterations ahead
+    if (it + 2 < total) prefetch(va, vs);   // refill this register set with the k-block two iterations ahead
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -374,11 +386,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __g
   };
 
   float4 va0[4], va1[4];
-  if (total > 0) prefetch(va0);
-  if (total > 1) prefetch(va1);
+  float vs0[4], vs1[4];
+  if (total > 0) prefetch(va0, vs0);
+  if (total > 1) prefetch(va1, vs1);
   for (int it = 0; it < total; it += 2) {
-    body(it, va0);
-    if (it + 1 < total) body(it + 1, va1);
+    body(it, va0, vs0);
+    if (it + 1 < total) body(it + 1, va1, vs1);
   }
   if (total > 0) {
     if (tid == 0) umma_commit(acc_done);
@@ -533,14 +546,15 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
   return false;
 }
 
-static inline int kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
+bool gemm_ws_available();
+size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
+int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+               int accumulate, void* ws, cudaStream_t stream);
 
 // bytes of scratch that let the NT kernel stream the B operand by TMA (hi + lo copies, K padded per segment)
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
   if (mode != I3D_GEMM_NT || !gemm_tc_eligible(mode, M, N, n_seg, segs)) return 0;
-  int64_t ktot = 0;
-  for (int s = 0; s < n_seg; ++s) ktot += kpad(segs[s].K);
-  return (size_t)2 * (size_t)N * (size_t)ktot * sizeof(float) + 256;
+  return gemm_ws_bytes(N, n_seg, segs);
 }
 
 // pick the N tile: 208 covers the F=200 outputs of the PNA layers with one accumulator
@@ -561,26 +575,8 @@ static int with_bn(int mode, int64_t M, int N, F&& f) {
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
             int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const size_t need = gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
-  if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && encode_tiled()) {
-    TcTmaParams p;
-    memset(&p, 0, sizeof(p));
-    int ktot = 0;
-    for (int s = 0; s < n_seg; ++s) {
-      p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;
-      p.lda[s] = segs[s].lda, p.K[s] = segs[s].K, p.kcol0[s] = ktot;
-      ktot += kpad(segs[s].K);
-    }
-    p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
-    float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
-    float* lo = hi + (size_t)N * ktot;
-    for (int s = 0; s < n_seg; ++s) {
-      const int kp = kpad(segs[s].K);
-      split_tf32_kernel<<<grid_for((int64_t)N * (kp / 4), 256), 256, 0, stream>>>(segs[s].B, N, segs[s].K, segs[s].ldb, hi,
-                                                                                   lo, ktot, p.kcol0[s], kp);
-      if (int rc = launched("split")) return rc;
-    }
-    return with_bn(mode, M, N, [&](auto bn) { return launch_tma<decltype(bn)::value>(p, hi, lo, ktot, stream); });
-  }
+  if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && gemm_ws_available())
+    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stream);
   TcParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];

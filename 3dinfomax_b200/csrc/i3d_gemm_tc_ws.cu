@@ -1,0 +1,377 @@
+// Warp-specialised NT tensor-core GEMM (the forward y = x W^T and, through W^T, dx = dy W).
+//
+//   C[m, n] = bias[n] + sum_s sum_k  scale_s[m] * A_s[a_idx_s[m], k] * B_s[n, k]
+//
+// Roles inside one 320-thread CTA (one CTA per SM, one 128 x BN output tile each):
+//   warps 0-7  A stagers   : LDG (row-gathered, degree-scaled) -> tf32 hi/lo split -> STS into a K-major
+//                            SWIZZLE_64B stage -> fence.proxy.async -> mbarrier arrive (a_full).  Two k-blocks of
+//                            register prefetch; no CTA-wide barrier in the main loop.
+//   warp  8    B producer  : one lane streams the pre-split weight tiles (hi, lo) with TMA
+//                            (cp.async.bulk.tensor.2d, SWIZZLE_64B) up to STAGES k-blocks ahead (b_full, expect_tx).
+//   warp  9    MMA issuer  : one lane waits a_full/b_full, issues 3xTF32 tcgen05.mma into the TMEM accumulator and
+//                            tcgen05.commit's the stage back to the producers (mma_done).
+//   epilogue   warps 0-7   : TMEM -> registers -> shared tile -> coalesced float4 stores.
+//
+// K is tiled in 16-float blocks (one 64-byte swizzle atom) so that 5 stages fit in shared memory: the B tiles of a
+// k-block arrive ~2000 cycles after they are requested, a k-block of MMAs takes ~620 cycles, so the ring has to be
+// at least 4 deep to keep the tensor pipe busy (ncu: 39 % tensor-active with the 2-stage kernel this one replaces).
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "i3d_tc.cuh"
+
+namespace i3d {
+
+constexpr int WS_BK = 16;                 // floats per k-block = one SWIZZLE_64B row
+constexpr int WS_STAGER_THREADS = 256;    // warps 0-7
+constexpr int WS_THREADS = 320;           // + TMA warp + MMA warp
+
+struct WsParams {
+  CUtensorMap map_hi, map_lo;       // [N rows, Kpad_total cols] fp32, box = [BN rows x 16 cols], SWIZZLE_64B
+  const float* A[4];
+  const int32_t* a_idx[4];
+  const float* scale[4];
+  int32_t lda[4], K[4], kcol0[4];   // kcol0: first column of the segment inside the split buffers
+  int n_seg;
+  int64_t M;
+  int N;
+  float* C;
+  int ldc;
+  const float* bias;
+  int accumulate;
+};
+
+template <int BN>
+struct WsLayout {
+  static constexpr int A_TILE = TC_BM * WS_BK;                 // floats (hi or lo)
+  static constexpr int B_TILE = BN * WS_BK;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // a_hi, a_lo, b_hi, b_lo
+  static constexpr int STAGE_BYTES = STAGE * 4;
+  static constexpr int MAX_BYTES = 220 * 1024;
+  static constexpr int STAGES = (MAX_BYTES / STAGE_BYTES) < 6 ? (MAX_BYTES / STAGE_BYTES) : 6;
+  static constexpr int CTILE_BYTES = TC_BM * (BN + 4) * 4;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES > CTILE_BYTES ? STAGES * STAGE_BYTES : CTILE_BYTES;
+  static constexpr size_t BYTES = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// float offset of 16-byte chunk j (0..3) of row r inside a [rows x 16 tf32] K-major SWIZZLE_64B tile
+// (Swizzle<2,4,3>: byte-address bits [4,6) ^= bits [7,9); identical to CU_TENSOR_MAP_SWIZZLE_64B with a 64-byte box)
+__device__ __forceinline__ int sw64_off(int r, int j) { return (r >> 3) * 128 + (r & 7) * 16 + ((j ^ ((r >> 1) & 3)) << 2); }
+
+// K-major SWIZZLE_64B smem descriptor: SBO = 512 B (8 rows x 64 B), layout type 4
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_nt_ws_kernel(const __grid_constant__ WsParams p) {
+  using L = WsLayout<BN>;
+  constexpr int S = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tiles) + L::RING_BYTES);
+  uint64_t* mma_done = bars;            // [S] stage drained by the tensor core (count 1, tcgen05.commit)
+  uint64_t* a_full = bars + S;          // [S] A tile staged (count 8: one arrival per stager warp)
+  uint64_t* b_full = bars + 2 * S;      // [S] B tiles landed (count 1 + TMA transaction bytes)
+  uint64_t* acc_done = bars + 3 * S;    // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t M = p.M;
+  const int N = p.N;
+
+  if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  if (tid == 256) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&mma_done[s], 1);
+      mbar_init(&a_full[s], 8);
+      mbar_init(&b_full[s], 1);
+    }
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.map_hi);
+    tma_prefetch_desc(&p.map_lo);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  int total = 0;
+  for (int s = 0; s < p.n_seg; ++s) total += (p.K[s] + WS_BK - 1) / WS_BK;
+
+  if (warp < 8) {
+    // ======================================= A stagers =======================================================
+    // chunk c = tid + i*256 (i < 2): row = c >> 2 = (tid >> 2) + 64 i, 16-byte chunk j = tid & 3
+    int pf_seg = 0, pf_k0 = 0;
+    int64_t a_row[2];
+    float a_sc[2];
+    auto bind_segment = [&](int s) {
+      const int32_t* __restrict__ a_idx = p.a_idx[s];
+      const float* __restrict__ scale = p.scale[s];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t gm = m0 + (tid >> 2) + 64 * i;
+        a_row[i] = -1;
+        a_sc[i] = 1.f;
+        if (gm < M) {
+          a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : gm;
+          if (scale) a_sc[i] = __ldg(scale + gm);
+        }
+      }
+    };
+    bind_segment(0);
+    // nothing in here may consume the loaded values (the scale is applied at store time): it is a prefetch
+    auto prefetch = [&](float4 (&va)[2], float (&vs)[2]) {
+      const float* __restrict__ A = p.A[pf_seg];
+      const int lda = p.lda[pf_seg], K = p.K[pf_seg];
+      const int kc = pf_k0 + (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_row[i] >= 0 && kc < K) v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
+        va[i] = v;
+        vs[i] = a_sc[i];
+      }
+      pf_k0 += WS_BK;
+      if (pf_k0 >= K && pf_seg + 1 < p.n_seg) {
+        pf_seg += 1;
+        pf_k0 = 0;
+        bind_segment(pf_seg);
+      }
+    };
+    auto body = [&](int it, float4 (&va)[2], float (&vs)[2]) {
+      const int st = it % S;
+      const int use = it / S;
+      float* a_hi = tiles + (size_t)st * L::STAGE;
+      float* a_lo = a_hi + L::A_TILE;
+      if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+      const int j = tid & 3;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 v = va[i];
+        const float sc = vs[i];
+        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+        split_store4(a_hi, a_lo, sw64_off((tid >> 2) + 64 * i, j), v);
+      }
+      fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
+      if (it + 2 < total) prefetch(va, vs);      // refill with the k-block two iterations ahead
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[st]);
+    };
+    float4 va0[2], va1[2];
+    float vs0[2], vs1[2];
+    if (total > 0) prefetch(va0, vs0);
+    if (total > 1) prefetch(va1, vs1);
+    for (int it = 0; it < total; it += 2) {
+      body(it, va0, vs0);
+      if (it + 1 < total) body(it + 1, va1, vs1);
+    }
+  } else if (warp == 8) {
+    // ======================================= B producer (TMA) ================================================
+    if (lane == 0) {
+      int seg = 0, k0 = 0;
+      for (int it = 0; it < total; ++it) {
+        const int st = it % S;
+        const int use = it / S;
+        float* b_hi = tiles + (size_t)st * L::STAGE + 2 * L::A_TILE;
+        float* b_lo = b_hi + L::B_TILE;
+        if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+        const int kcol = p.kcol0[seg] + k0;
+        mbar_expect_tx(&b_full[st], 2u * BN * WS_BK * 4u);
+        tma_load_2d(b_hi, &p.map_hi, kcol, n0, &b_full[st]);
+        tma_load_2d(b_lo, &p.map_lo, kcol, n0, &b_full[st]);
+        k0 += WS_BK;
+        if (k0 >= p.K[seg] && seg + 1 < p.n_seg) {
+          seg += 1;
+          k0 = 0;
+        }
+      }
+    }
+  } else {
+    // ======================================= MMA issuer ======================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      for (int it = 0; it < total; ++it) {
+        const int st = it % S;
+        const uint32_t par = (uint32_t)((it / S) & 1);
+        float* a_hi = tiles + (size_t)st * L::STAGE;
+        float* a_lo = a_hi + L::A_TILE;
+        float* b_hi = a_lo + L::A_TILE;
+        float* b_lo = b_hi + L::B_TILE;
+        mbar_wait(&a_full[st], par);
+        mbar_wait(&b_full[st], par);
+        tc_fence_after();
+        const uint64_t dah = make_smem_desc_sw64(smem_u32(a_hi)), dal = make_smem_desc_sw64(smem_u32(a_lo));
+        const uint64_t dbh = make_smem_desc_sw64(smem_u32(b_hi)), dbl = make_smem_desc_sw64(smem_u32(b_lo));
+#pragma unroll
+        for (int ks = 0; ks < WS_BK / 8; ++ks) {
+          const uint64_t koff = (uint64_t)(ks * 32 >> 4);      // 8 tf32 = 32 bytes along K inside the 64-byte row
+          umma_tf32(tmem, dah + koff, dbh + koff, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem, dal + koff, dbh + koff, idesc, 1u);
+          umma_tf32(tmem, dah + koff, dbl + koff, idesc, 1u);
+        }
+        umma_commit(&mma_done[st]);
+      }
+      if (total > 0) umma_commit(acc_done);
+    }
+  }
+
+  // ---- epilogue (warps 0-7 move the tile; all warps take part in the CTA barriers) ----
+  if (total > 0) {
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+  }
+  __syncthreads();      // every role has left the operand ring before it is reused as the output tile
+  tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
+// hi[n, col0 + c] = tf32(B[n, c]),  lo = B - hi  for c < K;  zeros for K <= c < Kpad
+__global__ void ws_split_tf32_kernel(const float* __restrict__ B, int N, int K, int ldb, float* __restrict__ hi,
+                                     float* __restrict__ lo, int ldo, int col0, int Kpad) {
+  const int quads = Kpad >> 2;
+  const int64_t total = (int64_t)N * quads;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(t / quads);
+    const int c = (int)(t - (int64_t)n * quads) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < K) v = __ldg(reinterpret_cast<const float4*>(B + (int64_t)n * ldb + c));
+    float4 h, l;
+    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + (int64_t)n * ldo + col0 + c) = h;
+    *reinterpret_cast<float4*>(lo + (int64_t)n * ldo + col0 + c) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static WsEncodeTiledFn ws_encode_tiled() {
+  static WsEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WsEncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool gemm_ws_available() { return ws_encode_tiled() != nullptr; }
+
+static bool ws_make_b_map(CUtensorMap* map, float* base, int N, int ktot, int bn) {
+  WsEncodeTiledFn enc = ws_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)WS_BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline int ws_kpad(int K) { return (K + 31) / 32 * 32; }   // segment columns padded to 32 (zeros)
+
+size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs) {
+  int64_t ktot = 0;
+  for (int s = 0; s < n_seg; ++s) ktot += ws_kpad(segs[s].K);
+  return (size_t)2 * (size_t)N * (size_t)ktot * sizeof(float) + 256;
+}
+
+template <int BN>
+static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s) {
+  using L = WsLayout<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_tc_nt_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+    if (e != cudaSuccess) {
+      set_error("i3d_gemm(ws): cudaFuncSetAttribute -> %s", cudaGetErrorString(e));
+      return I3D_ERR_CUDA;
+    }
+    configured = true;
+  }
+  if (!ws_make_b_map(&p.map_hi, hi, p.N, ktot, BN) || !ws_make_b_map(&p.map_lo, lo, p.N, ktot, BN)) {
+    set_error("i3d_gemm(ws): cuTensorMapEncodeTiled failed");
+    return I3D_ERR_CUDA;
+  }
+  const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
+  const int gy = (p.N + BN - 1) / BN;
+  gemm_tc_nt_ws_kernel<BN><<<dim3((unsigned)gx, gy, 1), WS_THREADS, L::BYTES, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("i3d_gemm(ws): launch failed -> %s", cudaGetErrorString(e));
+    return I3D_ERR_CUDA;
+  }
+  count_launch();
+  return I3D_OK;
+}
+
+// NT GEMM through the warp-specialised kernel.  ws: device scratch of gemm_ws_bytes(...) for the hi/lo weight copies.
+int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+               int accumulate, void* ws, cudaStream_t stream) {
+  WsParams p;
+  memset(&p, 0, sizeof(p));
+  int ktot = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;
+    p.lda[s] = segs[s].lda, p.K[s] = segs[s].K, p.kcol0[s] = ktot;
+    ktot += ws_kpad(segs[s].K);
+  }
+  p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
+  float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
+  float* lo = hi + (size_t)N * ktot;
+  for (int s = 0; s < n_seg; ++s) {
+    const int kp = ws_kpad(segs[s].K);
+    ws_split_tf32_kernel<<<grid_for((int64_t)N * (kp / 4), 256), 256, 0, stream>>>(segs[s].B, N, segs[s].K, segs[s].ldb,
+                                                                                    hi, lo, ktot, p.kcol0[s], kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("i3d_gemm(ws): split launch failed -> %s", cudaGetErrorString(e));
+      return I3D_ERR_CUDA;
+    }
+    count_launch();
+  }
+  const int64_t gx = (M + TC_BM - 1) / TC_BM;
+  const int sms = sm_count();
+  if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
+  if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
+  if (N <= 112) return launch_ws<112>(p, hi, lo, ktot, stream);
+  if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
+  if (N <= 208) {
+    // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when that fills the machine
+    // better: node-level GEMMs (72 row tiles at batch 512) and row-tile counts just above a multiple of the SM count.
+    const int64_t rounds_full = (gx + sms - 1) / sms;
+    const int64_t rounds_half = (2 * gx + sms - 1) / sms;
+    if (rounds_half < 2 * rounds_full) return launch_ws<112>(p, hi, lo, ktot, stream);
+    return launch_ws<208>(p, hi, lo, ktot, stream);
+  }
+  if ((N + 207) / 208 <= (N + 255) / 256) return launch_ws<208>(p, hi, lo, ktot, stream);   // same tiles, less padding
+  return launch_ws<256>(p, hi, lo, ktot, stream);
+}
+
+}  // namespace i3d

@@ -149,7 +149,7 @@ struct TcLayout {
 // ---- epilogue shared by all tensor-core kernels -----------------------------------------------------------------
 // TMEM -> registers (tcgen05.ld 32x32b: warp w owns lanes [32*(w&3), +32) and column half w>>2) -> row-major tile in
 // shared memory (the operand stages are dead by now) -> coalesced float4 stores / vector atomics to global.
-template <int BN>
+template <int BN, int NTHR = TC_THREADS>
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N, int64_t m0,
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
                                             int accumulate, bool atomic) {
@@ -159,7 +159,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
   constexpr int HALF_COLS = BN / 2;
   const int c_begin = half * HALF_COLS;
   float* trow = ctile + (q * 32 + lane) * LDT;
-  for (int c = c_begin; c < c_begin + HALF_COLS; c += 16) {
+  for (int c = c_begin; tid < NTHR && c < c_begin + HALF_COLS; c += 16) {   // warp-uniform: NTHR is a multiple of 32
     float v[16];
     if (has_acc) {
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);    // warp-collective: no divergence around it
@@ -175,7 +175,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
   __syncthreads();
   const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);
   constexpr int QUADS = BN / 4;
-  for (int idx = tid; idx < TC_BM * QUADS; idx += TC_THREADS) {
+  for (int idx = tid; tid < NTHR && idx < TC_BM * QUADS; idx += NTHR) {
     const int r = idx / QUADS, c = (idx - r * QUADS) * 4;
     const int64_t gm = m0 + r;
     const int gn = n0 + c;
