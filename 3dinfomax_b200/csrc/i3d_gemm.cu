@@ -273,7 +273,7 @@ __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int l
 namespace i3d {
 bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream);
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 
 // out[c, r] = in[r, c]  (32x32 shared-memory tiles, coalesced on both sides)
@@ -324,12 +324,14 @@ extern "C" size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const
 
 extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                         const float* bias, int accumulate, void* stream) {
-  return i3d_gemm_ex(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, nullptr, 0, stream);
+  return i3d_gemm_ex(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, nullptr, 0, nullptr, 0, stream);
 }
 
 extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
-                           const float* bias, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+                           const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats,
+                           int stats_act, void* stream) {
   I3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be NT, NN or TN");
+  I3D_REQUIRE(!col_stats || (mode == I3D_GEMM_NT && !accumulate), "col_stats needs NT mode without accumulate");
   I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N, "invalid shape");
   if (M == 0 || N == 0) return I3D_OK;
   I3D_REQUIRE(C != nullptr, "C is null");
@@ -338,8 +340,11 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     I3D_REQUIRE(segs[s].K >= 0 && (segs[s].K == 0 || (segs[s].A && segs[s].B)), "segment operand is null");
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
-  if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs))
-    return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, as_stream(stream));
+  if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
+    if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+    return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act,
+                   as_stream(stream));
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {
@@ -379,6 +384,10 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     gemm_kernel<I3D_GEMM_TN><<<dim3((unsigned)gx, gy, p.splits), GEMM_THREADS, 0, s>>>(p);
   } else if (mode == I3D_GEMM_NT) {
     gemm_kernel<I3D_GEMM_NT><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
+    if (col_stats) {
+      I3D_LAUNCHED();
+      return i3d_act_colstats(C, M, N, ldc, stats_act, col_stats, stream);
+    }
   } else {
     gemm_kernel<I3D_GEMM_NN><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
   }

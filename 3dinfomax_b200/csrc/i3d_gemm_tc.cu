@@ -37,6 +37,8 @@ struct TcParams {
   int accumulate;
   int kchunk;   // TN: K range per CTA (multiple of TC_BK)
   int splits;   // TN: gridDim.z
+  double* stats;    // optional fused BatchNorm statistics [2N] (NT only)
+  int stats_act;
 };
 
 // =================================================================================================================
@@ -245,7 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
   const bool atomic = (MODE == I3D_GEMM_TN) && p.splits > 1;
   tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc,
-                  (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic);
+                  (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic,
+                  MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -549,7 +552,7 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
 bool gemm_ws_available();
 size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, cudaStream_t stream);
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream);
 
 // bytes of scratch that let the NT kernel stream the B operand by TMA (hi + lo copies, K padded per segment)
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
@@ -573,15 +576,15 @@ static int with_bn(int mode, int64_t M, int N, F&& f) {
 }
 
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream) {
   const size_t need = gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
   if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && gemm_ws_available())
-    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stream);
+    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stats, stats_act, stream);
   TcParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];
   p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
-  p.kchunk = 0, p.splits = 1;
+  p.kchunk = 0, p.splits = 1, p.stats = stats, p.stats_act = stats_act;
   if (mode == I3D_GEMM_NT)
     return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_NT, decltype(bn)::value>(p, stream); });
   return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_TN, decltype(bn)::value>(p, stream); });

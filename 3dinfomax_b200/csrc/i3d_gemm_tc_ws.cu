@@ -40,6 +40,11 @@ struct WsParams {
   int ldc;
   const float* bias;
   int accumulate;
+  double* stats;                    // optional fused BatchNorm statistics [2N] (fp64), see tc_epilogue
+  int stats_act;
+  // B split (one launch for all segments)
+  const float* Bsrc[4];
+  int32_t ldb[4];
 };
 
 template <int BN>
@@ -237,17 +242,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_nt_ws_kernel(const __gr
     tc_fence_after();
   }
   __syncthreads();      // every role has left the operand ring before it is reused as the output tile
-  tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false);
+  tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false,
+                                     p.stats, p.stats_act);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-// hi[n, col0 + c] = tf32(B[n, c]),  lo = B - hi  for c < K;  zeros for K <= c < Kpad
-__global__ void ws_split_tf32_kernel(const float* __restrict__ B, int N, int K, int ldb, float* __restrict__ hi,
-                                     float* __restrict__ lo, int ldo, int col0, int Kpad) {
-  const int quads = Kpad >> 2;
-  const int64_t total = (int64_t)N * quads;
+// hi[n, kcol0_s + c] = tf32(B_s[n, c]),  lo = B_s - hi  for c < K_s;  zeros for K_s <= c < Kpad_s  (blockIdx.y = s)
+struct WsSplitArgs {
+  const float* B[4];
+  int32_t ldb[4], K[4], kcol0[4], kpad[4];
+  int N, ldo;
+};
+__global__ void ws_split_tf32_kernel(const WsSplitArgs a, float* __restrict__ hi, float* __restrict__ lo) {
+  const int sg = blockIdx.y;
+  const float* __restrict__ B = a.B[sg];
+  const int K = a.K[sg], ldb = a.ldb[sg], col0 = a.kcol0[sg];
+  const int quads = a.kpad[sg] >> 2;
+  const int64_t total = (int64_t)a.N * quads;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(t / quads);
     const int c = (int)(t - (int64_t)n * quads) * 4;
@@ -256,8 +269,8 @@ __global__ void ws_split_tf32_kernel(const float* __restrict__ B, int N, int K, 
     float4 h, l;
     h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
     l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi + (int64_t)n * ldo + col0 + c) = h;
-    *reinterpret_cast<float4*>(lo + (int64_t)n * ldo + col0 + c) = l;
+    *reinterpret_cast<float4*>(hi + (int64_t)n * a.ldo + col0 + c) = h;
+    *reinterpret_cast<float4*>(lo + (int64_t)n * a.ldo + col0 + c) = l;
   }
 }
 
@@ -333,7 +346,7 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
 
 // NT GEMM through the warp-specialised kernel.  ws: device scratch of gemm_ws_bytes(...) for the hi/lo weight copies.
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, cudaStream_t stream) {
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream) {
   WsParams p;
   memset(&p, 0, sizeof(p));
   int ktot = 0;
@@ -343,12 +356,20 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
     ktot += ws_kpad(segs[s].K);
   }
   p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
+  p.stats = stats, p.stats_act = stats_act;
   float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
   float* lo = hi + (size_t)N * ktot;
-  for (int s = 0; s < n_seg; ++s) {
-    const int kp = ws_kpad(segs[s].K);
-    ws_split_tf32_kernel<<<grid_for((int64_t)N * (kp / 4), 256), 256, 0, stream>>>(segs[s].B, N, segs[s].K, segs[s].ldb,
-                                                                                    hi, lo, ktot, p.kcol0[s], kp);
+  {
+    WsSplitArgs a;
+    memset(&a, 0, sizeof(a));
+    int kmax = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      a.B[s] = segs[s].B, a.ldb[s] = segs[s].ldb, a.K[s] = segs[s].K, a.kcol0[s] = p.kcol0[s];
+      a.kpad[s] = ws_kpad(segs[s].K);
+      kmax = a.kpad[s] > kmax ? a.kpad[s] : kmax;
+    }
+    a.N = N, a.ldo = ktot;
+    ws_split_tf32_kernel<<<dim3(grid_for((int64_t)N * (kmax / 4), 256), n_seg), 256, 0, stream>>>(a, hi, lo);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("i3d_gemm(ws): split launch failed -> %s", cudaGetErrorString(e));
@@ -363,11 +384,9 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
   if (N <= 112) return launch_ws<112>(p, hi, lo, ktot, stream);
   if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
   if (N <= 208) {
-    // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when that fills the machine
-    // better: node-level GEMMs (72 row tiles at batch 512) and row-tile counts just above a multiple of the SM count.
-    const int64_t rounds_full = (gx + sms - 1) / sms;
-    const int64_t rounds_half = (2 * gx + sms - 1) / sms;
-    if (rounds_half < 2 * rounds_full) return launch_ws<112>(p, hi, lo, ktot, stream);
+    // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when the row tiles alone leave
+    // half the SMs idle (node-level GEMMs: 72 row tiles at batch 512).
+    if (2 * gx <= sms) return launch_ws<112>(p, hi, lo, ktot, stream);
     return launch_ws<208>(p, hi, lo, ktot, stream);
   }
   if ((N + 207) / 208 <= (N + 255) / 256) return launch_ws<208>(p, hi, lo, ktot, stream);   // same tiles, less padding

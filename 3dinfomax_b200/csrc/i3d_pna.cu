@@ -57,6 +57,47 @@ __global__ void embed_sum_bwd_kernel(const int64_t* __restrict__ idx, int64_t R,
   }
 }
 
+// Same gradient with a per-CTA shared-memory copy of ONE column's table slice: a CTA takes a chunk of rows and one
+// categorical column c, accumulates gout rows into acc[value][F] with shared-memory atomics (a column has <= 119
+// values, half the atoms are hydrogens: global atomics on those rows serialise), then flushes only the touched rows.
+template <int V>
+__global__ void __launch_bounds__(256)
+    embed_sum_bwd_smem_kernel(const int64_t* __restrict__ idx, int64_t R, int C, const int32_t* __restrict__ col_off,
+                              const int32_t* __restrict__ perm, const float* __restrict__ gout, int F,
+                              float* __restrict__ gtable, int table_rows, int rows_per_cta) {
+  extern __shared__ float acc[];          // [dim][F]
+  __shared__ unsigned touched[8];
+  const int c = blockIdx.y;
+  const int base = col_off[c];
+  const int dim = min((c + 1 < C ? col_off[c + 1] : table_rows) - base, 256);
+  for (int t = threadIdx.x; t < dim * F; t += blockDim.x) acc[t] = 0.f;
+  if (threadIdx.x < 8) touched[threadIdx.x] = 0u;
+  __syncthreads();
+  const int FV = F / V;
+  const int RP = blockDim.x / FV;
+  const int cgp = threadIdx.x % FV, rg = threadIdx.x / FV;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(R, r0 + rows_per_cta);
+  if (rg < RP) {
+    for (int64_t r = r0 + rg; r < r1; r += RP) {
+      const int64_t rr = perm ? (int64_t)perm[r] : r;
+      const int v = (int)idx[rr * C + c];
+      if (v < 0 || v >= dim) continue;
+      Vec<V> g;
+      g.load(gout + r * F + cgp * V);
+      float* dst = acc + v * F + cgp * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(dst + i, g.v[i]);
+      if (cgp == 0) atomicOr(&touched[v >> 5], 1u << (v & 31));
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < dim * F; t += blockDim.x) {
+    const int v = t / F;
+    if (touched[v >> 5] & (1u << (v & 31))) atomicAdd(gtable + (int64_t)(base + v) * F + (t - v * F), acc[t]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // PNA aggregation forward (models/pna.py:17-37,221-235).  One thread = one node x one column group.
 // Arithmetic is written with explicit round-to-nearest intrinsics so that nvcc does not contract
@@ -367,10 +408,32 @@ int i3d_embed_sum_fwd(const int64_t* idx, int64_t R, int C, const int32_t* col_o
 }
 
 int i3d_embed_sum_bwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
-                      const float* gout, int F, float* gtable, void* stream) {
+                      const float* gout, int F, float* gtable, int table_rows, int max_dim, void* stream) {
   I3D_REQUIRE(R >= 0 && C > 0 && F > 0 && col_off && gtable && (R == 0 || (idx && gout)), "invalid argument");
   if (R == 0) return I3D_OK;
   const bool v4 = can_vec4({gout}, {F});
+  const size_t smem = (size_t)max_dim * F * sizeof(float);
+  if (table_rows > 0 && max_dim > 0 && max_dim <= 256 && smem <= 200 * 1024 && F / (v4 ? 4 : 1) <= 256) {
+    static bool configured = false;
+    if (!configured) {
+      I3D_CUDA(cudaFuncSetAttribute(embed_sum_bwd_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      I3D_CUDA(cudaFuncSetAttribute(embed_sum_bwd_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    int64_t chunks = (2 * (int64_t)sm_count() + C - 1) / C;
+    int rows_per_cta = (int)((R + chunks - 1) / chunks);
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    chunks = (R + rows_per_cta - 1) / rows_per_cta;
+    const dim3 grid((unsigned)chunks, C);
+    if (v4)
+      embed_sum_bwd_smem_kernel<4><<<grid, 256, smem, as_stream(stream)>>>(idx, R, C, col_off, perm, gout, F, gtable,
+                                                                            table_rows, rows_per_cta);
+    else
+      embed_sum_bwd_smem_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(idx, R, C, col_off, perm, gout, F, gtable,
+                                                                            table_rows, rows_per_cta);
+    I3D_LAUNCHED();
+    return I3D_OK;
+  }
   const int64_t work = R * (F / (v4 ? 4 : 1));
   I3D_DISPATCH_VEC(v4, embed_sum_bwd_kernel, grid_for(work, 256), 256, as_stream(stream), idx, R, C, col_off, perm,
                    gout, F, gtable);

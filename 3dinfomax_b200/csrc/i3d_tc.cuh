@@ -152,7 +152,8 @@ struct TcLayout {
 template <int BN, int NTHR = TC_THREADS>
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N, int64_t m0,
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
-                                            int accumulate, bool atomic) {
+                                            int accumulate, bool atomic, double* __restrict__ stats = nullptr,
+                                            int stats_act = 0) {
   constexpr int LDT = BN + 4;               // row stride (floats): 16-byte aligned, conflict-free for per-row STS.128
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
@@ -173,6 +174,23 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       if (i < lim) *reinterpret_cast<float4*>(trow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
   __syncthreads();
+  if (stats) {
+    // fused FCLayer statistics (models/base_layers.py:102-110): column sums of act(y) and act(y)^2 over the valid rows
+    // of this tile, accumulated in fp64 (BatchNorm inputs with mean^2 >> var), one atomic pair per column and CTA
+    const int rows = (int)(M - m0 < TC_BM ? M - m0 : TC_BM);
+    for (int c = tid; tid < NTHR && c < BN; c += NTHR) {
+      if (n0 + c >= N) continue;
+      const float b = bias ? __ldg(bias + n0 + c) : 0.f;
+      double s1 = 0.0, s2 = 0.0;
+      for (int r = 0; r < rows; ++r) {
+        const double h = (double)act_apply(ctile[r * LDT + c] + b, stats_act);
+        s1 += h;
+        s2 += h * h;
+      }
+      atomicAdd(stats + n0 + c, s1);
+      atomicAdd(stats + N + n0 + c, s2);
+    }
+  }
   const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);
   constexpr int QUADS = BN / 4;
   for (int idx = tid; tid < NTHR && idx < TC_BM * QUADS; idx += NTHR) {

@@ -99,19 +99,21 @@ def embed_sum_fwd(idx, col_off, perm, table):
     return out
 
 
-def embed_sum_bwd(idx, col_off, perm, gout, n_table_rows):
+def embed_sum_bwd(idx, col_off, perm, gout, n_table_rows, max_dim=0):
     gout = gout.contiguous()
     R, F = gout.shape
     C = idx.shape[1]
     gtable = torch.zeros(n_table_rows, F, dtype=torch.float32, device=gout.device)
-    _lib.check(_L().i3d_embed_sum_bwd(_p(idx), R, C, _p(col_off), _p(perm), _p(gout), F, _p(gtable), _s()),
+    _lib.check(_L().i3d_embed_sum_bwd(_p(idx), R, C, _p(col_off), _p(perm), _p(gout), F, _p(gtable),
+                                      int(n_table_rows) if max_dim else 0, int(max_dim), _s()),
                "i3d_embed_sum_bwd")
     return gtable
 
 
 # ----------------------------------------------------------------------------------------- gemm
-def gemm(mode, M, N, segs, C, bias=None, accumulate=False):
-    """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld)."""
+def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None):
+    """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld).
+    stats_act: activation code -> also returns fp64 [2N] column sums of act(C), act(C)^2 (fused BatchNorm statistics)."""
     arr = (_lib.gemm_seg * len(segs))()
     keep = []
     for i, s in enumerate(segs):
@@ -127,9 +129,11 @@ def gemm(mode, M, N, segs, C, bias=None, accumulate=False):
     L = _L()
     nws = int(L.i3d_gemm_ws_bytes(mode, M, N, len(segs), arr))
     ws = torch.empty(nws, dtype=torch.uint8, device=C.device) if nws else None      # tf32 hi/lo copies of B for TMA
+    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
     _lib.check(L.i3d_gemm_ex(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                             1 if accumulate else 0, _p(ws), nws, _s()), "i3d_gemm")
-    return C
+                             1 if accumulate else 0, _p(ws), nws, _p(stats), 0 if stats_act is None else stats_act,
+                             _s()), "i3d_gemm")
+    return C if stats_act is None else (C, stats)
 
 
 def transpose(x):

@@ -44,12 +44,12 @@ SIGNATURES = {
     "i3d_segment_ptr": (_I, [_P, _L, _P, _P]),
     "i3d_degree_scalers": (_I, [_P, _L, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
-    "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
+    "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "i3d_gemm_backend": (_I, [_I]),
     "i3d_transpose": (_I, [_P, _L, _I, _I, _P, _I, _P]),
     "i3d_gemm": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P]),
     "i3d_gemm_ws_bytes": (ctypes.c_size_t, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg)]),
-    "i3d_gemm_ex": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, ctypes.c_size_t, _P]),
+    "i3d_gemm_ex": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, ctypes.c_size_t, _P, _I, _P]),
     "i3d_act_colstats": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "i3d_bn_apply": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),
     "i3d_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P]),

@@ -54,10 +54,13 @@ class _FC(torch.autograd.Function):
             off += k
         if off != W.shape[1]:
             raise ValueError("segment widths %d do not add up to the weight's in_features %d" % (off, W.shape[1]))
-        K.gemm(K.NT, M, Fout, gsegs, Y, bias=b)
         save = None
+        sums = None
+        if cfg.has_bn and cfg.training:
+            _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act)    # statistics from the GEMM epilogue
+        else:
+            K.gemm(K.NT, M, Fout, gsegs, Y, bias=b)
         if cfg.has_bn:
-            sums = K.act_colstats(Y, cfg.act) if cfg.training else None
             O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
                                  cfg.momentum, cfg.eps, cfg.training, residual)
         else:
@@ -92,12 +95,12 @@ class _FC(torch.autograd.Function):
         # weight gradient, one column block per segment: dW[:, off:off+k] = dY^T (scale * gather(x))
         dW = None
         if ctx.needs_input_grad[1]:
-            dW = torch.empty_like(W)
+            dW = torch.zeros_like(W)        # one memset; the split-K column-block GEMMs below accumulate into it
             off = 0
             for s, x in zip(segs, xs):
                 k = x.shape[1]
                 K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
-                       dW[:, off:off + k])
+                       dW[:, off:off + k], accumulate=True)
                 off += k
         # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
         dxs = [None] * len(xs)
@@ -144,19 +147,21 @@ def fc(segs, W, b, act, bn=None, training=True, residual=None):
 
 class _EmbedSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, idx, col_off, perm, table):
+    def forward(ctx, idx, col_off, perm, table, max_dim):
         ctx.save_for_backward(idx, col_off, perm)
         ctx.rows = table.shape[0]
+        ctx.max_dim = max_dim
         return K.embed_sum_fwd(idx, col_off, perm, table)
 
     @staticmethod
     def backward(ctx, g):
         idx, col_off, perm = ctx.saved_tensors
-        return None, None, None, K.embed_sum_bwd(idx, col_off, perm, g, ctx.rows)
+        return None, None, None, K.embed_sum_bwd(idx, col_off, perm, g, ctx.rows, ctx.max_dim), None
 
 
-def embed_sum(idx, col_off, perm, table):
-    return _EmbedSum.apply(idx, col_off, perm, table)
+def embed_sum(idx, col_off, perm, table, max_dim=0):
+    """max_dim: largest per-column vocabulary (lets the backward pre-reduce in shared memory)."""
+    return _EmbedSum.apply(idx, col_off, perm, table, int(max_dim))
 
 
 # bench.py sets PROFILE = {"fwd": [], "bwd": []} to time every aggregation launch with CUDA events on the launch

@@ -41,13 +41,14 @@ class _SummedEmbedding(nn.Module):
             offs.append(acc)
             acc += d
         self.register_buffer("_col_off", torch.tensor(offs, dtype=torch.int32), persistent=False)
+        self._max_dim = max(dims)
 
     def forward(self, idx, perm=None):
         tables = getattr(self, self._list_name)
         # pointer plumbing only: one contiguous table so the kernel takes a single base pointer; autograd's
         # cat backward splits the table gradient back onto the per-column nn.Embedding weights
         table = torch.cat([e.weight for e in tables], dim=0)
-        return ops.embed_sum(idx.contiguous(), self._col_off, perm, table)
+        return ops.embed_sum(idx.contiguous(), self._col_off, perm, table, self._max_dim)
 
 
 class AtomEncoder(_SummedEmbedding):

@@ -76,9 +76,11 @@ int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att,
  * ---------------------------------------------------------------------------------------------- */
 int i3d_embed_sum_fwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
                       const float* table, int F, float* out, void* stream);
-/* gtable (caller-zeroed) += scatter of gout; fp32 atomics */
+/* gtable (caller-zeroed, table_rows x F) += scatter of gout.  max_dim = largest per-column vocabulary: when the
+ * column slice fits in shared memory the sums are formed per CTA first (few global atomics), else plain fp32 atomics;
+ * pass table_rows = max_dim = 0 to force the latter. */
 int i3d_embed_sum_bwd(const int64_t* idx, int64_t R, int C, const int32_t* col_off, const int32_t* perm,
-                      const float* gout, int F, float* gtable, void* stream);
+                      const float* gout, int F, float* gtable, int table_rows, int max_dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense stage.  Replaces cat + nn.Linear (cuBLAS SGEMM) at models/pna.py:249-252 (pretrans over
@@ -107,10 +109,14 @@ int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, fl
              const float* bias, int accumulate, void* stream);
 /* Same, with caller-owned device scratch: when ws_bytes >= i3d_gemm_ws_bytes(...) the NT kernel splits the dense B
  * operand (weights) into tf32 hi/lo copies once and streams them by TMA instead of staging them through threads.
- * i3d_gemm_ws_bytes returns 0 for problems that do not use scratch. */
+ * i3d_gemm_ws_bytes returns 0 for problems that do not use scratch.
+ */
 size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+/* col_stats (optional, NT without accumulate): fp64 [2N] = column sums of act(C) and act(C)^2, i.e. the train-mode
+ * BatchNorm statistics of the FCLayer tail, produced by the GEMM epilogue instead of a separate pass over C. */
 int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
-                const float* bias, int accumulate, void* ws, size_t ws_bytes, void* stream);
+                const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats, int stats_act,
+                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]
