@@ -162,3 +162,23 @@ def make_batch(seed, batch_size, shape="qm9", conformers=1, conformer_noise=0.3)
         "num_nodes3": np.array(nn3_l, dtype=np.int64), "num_edges3": np.array(ne3_l, dtype=np.int64),
         "xyz3": np.concatenate(xyz_l).astype(np.float32),
     }
+
+
+def slice_batch(b, lo, hi):
+    """Molecules [lo, hi) of a collated batch as a collated batch of their own (node ids re-based): the shard a
+    data-parallel rank works on."""
+    C = int(b["conformers"])
+    nn, ne = b["num_nodes"], b["num_edges"]
+    nn3, ne3 = b["num_nodes3"], b["num_edges3"]
+    n0, n1 = int(nn[:lo].sum()), int(nn[:hi].sum())
+    e0, e1 = int(ne[:lo].sum()), int(ne[:hi].sum())
+    m0, m1 = int(nn3[:lo * C].sum()), int(nn3[:hi * C].sum())
+    f0, f1 = int(ne3[:lo * C].sum()), int(ne3[:hi * C].sum())
+    return {
+        "batch_size": hi - lo, "conformers": C,
+        "x_atom": b["x_atom"][n0:n1], "e_attr": b["e_attr"][e0:e1],
+        "src": b["src"][e0:e1] - n0, "dst": b["dst"][e0:e1] - n0,
+        "num_nodes": nn[lo:hi], "num_edges": ne[lo:hi],
+        "src3": b["src3"][f0:f1] - m0, "dst3": b["dst3"][f0:f1] - m0, "d3": b["d3"][f0:f1],
+        "num_nodes3": nn3[lo * C:hi * C], "num_edges3": ne3[lo * C:hi * C], "xyz3": b["xyz3"][m0:m1],
+    }

@@ -306,7 +306,13 @@ def run_b200(args):
                                               % min(args.batch, 256)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured CUDA graphs hold NCCL kernels; tearing the communicator down under them deadlocks
+        # (observed on 2xB200: both ranks printed, then hung in destroy_process_group).  All collectives are complete
+        # and the result line is flushed, so leave without running NCCL / graph destructors.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -711,6 +711,8 @@ def case_full_size_properties():
     return out
 
 
+from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
+
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_golden, case_golden_qmugs, case_train_steps,
-             case_train_steps_captured, case_full_size_properties]
+             case_train_steps_captured, case_full_size_properties, case_sharded_equals_full]

@@ -1,0 +1,95 @@
+"""Multi-GPU parity of the data-parallel step (run on the GPU box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/gpu_dist_check.py
+
+Every rank computes (a) the full global batch on its own GPU and (b) its molecule shard with the all-gathered 3-D
+embeddings as the negative set, then all-reduces the shard gradients.  With BatchNorm in eval mode (statistics do not
+depend on the sharding) loss and gradients of (b) must equal (a) up to fp32 reduction order; in train mode the only
+difference is per-shard BN statistics (multi-GPU), which is reported, not asserted."""
+import importlib
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402  (seeded weights only)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    i3d = importlib.import_module("3dinfomax_b200")
+    D = importlib.import_module("3dinfomax_b200.dist")
+    cfg = importlib.import_module("3dinfomax_b200.configs")
+    syn = i3d.synthetic
+    C, per = 3, 24
+    b = syn.make_batch(77, per * world, conformers=C)
+    c2, c3 = O.pna_cfg(**cfg.PRETRAIN_QM9_MODEL_PARAMETERS), O.net3d_cfg(**cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
+    st2, st3 = O.init_pna_state(c2, 5, True), O.init_net3d_state(c3, 6, True)
+    ok = True
+    for mode in ("eval", "train"):
+        res = {}
+        for what in ("full", "shard"):
+            pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS).to(dev)
+            n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS).to(dev)
+            pna.load_state_dict(st2), n3.load_state_dict(st3)
+            pna.train(mode == "train"), n3.train(mode == "train")
+            loss_fn = i3d.NTXentMultiplePositives(tau=0.1)
+            if what == "full":
+                g2, g3 = i3d.batch_from_numpy(b, dev)
+                loss = loss_fn(pna(g2), n3(g3))
+            else:
+                lo, hi = D.shard_bounds(per * world, rank, world)
+                g2, g3 = i3d.batch_from_numpy(syn.slice_batch(b, lo, hi), dev)
+                z2, z3 = pna(g2), n3(g3)
+                loss = loss_fn(z2, D.all_gather_rows(z3), row_offset=lo, total_rows=per * world)
+            loss.backward()
+            grads = torch.cat([p.grad.reshape(-1) for p in list(pna.parameters()) + list(n3.parameters())])
+            total = loss.detach().clone()
+            if what == "shard":
+                dist.all_reduce(grads)
+                dist.all_reduce(total)
+            res[what] = (total.item(), grads)
+        dl = abs(res["full"][0] - res["shard"][0])
+        scale = res["full"][1].abs().max().item()
+        dg = (res["full"][1] - res["shard"][1]).abs().max().item() / scale
+        if rank == 0:
+            print("%s: loss full %.6f sharded %.6f |diff| %.2e ; grad max err / scale %.2e" %
+                  (mode, res["full"][0], res["shard"][0], dl, dg), flush=True)
+        if mode == "eval" and (dl > 1e-4 or dg > 2e-3):
+            ok = False
+    # one captured data-parallel step through the trainer (NCCL collectives inside the CUDA graph)
+    pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
+    pna.load_state_dict(st2), n3.load_state_dict(st3)
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXentMultiplePositives(tau=0.1), dev, {"lr": 8e-5},
+                                   process_group=dist.group.WORLD, graph_safe=True)
+    lo, hi = D.shard_bounds(per * world, rank, world)
+    g2, g3 = i3d.batch_from_numpy(syn.slice_batch(b, lo, hi), dev)
+    cap = i3d.CapturedStep(tr, g2, g3, warmup=2)
+    g2, g3 = i3d.batch_from_numpy(syn.slice_batch(b, lo, hi), dev)
+    cap.load(g2, g3)
+    l1 = cap.run().item()
+    l2 = cap.run().item()
+    w = torch.cat([p.detach().reshape(-1) for p in pna.parameters()])
+    wsum = w.double().sum()
+    chk = torch.stack([wsum, -wsum])
+    dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+    same = abs(chk[0].item() + chk[1].item()) < 1e-9 * max(1.0, abs(wsum.item()))
+    if rank == 0:
+        print("captured DP steps: local loss %.6f -> %.6f ; replicas identical after Adam: %s" % (l1, l2, same), flush=True)
+    ok = ok and same and l2 == l2
+    # captured graphs hold NCCL kernels: destroy_process_group() deadlocks under them, so leave without destructors
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
