@@ -62,7 +62,7 @@ def main():
         if rank == 0:
             print("%s: loss full %.6f sharded %.6f |diff| %.2e ; grad max err / scale %.2e" %
                   (mode, res["full"][0], res["shard"][0], dl, dg), flush=True)
-        if mode == "eval" and (dl > 1e-4 or dg > 2e-3):
+        if mode == "eval" and (dl > 1e-4 or dg > 2e-2):     # see tests/gpu_cases_dp.py for why 2e-2
             ok = False
     # one captured data-parallel step through the trainer (NCCL collectives inside the CUDA graph)
     pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
