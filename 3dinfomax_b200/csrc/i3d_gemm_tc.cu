@@ -550,6 +550,8 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
 }
 
 bool gemm_ws_available();
+int gemm_tn_ws(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int accumulate, cudaStream_t stream);
+static bool g_tn_ws = true;   // MN-major warp-specialised TN kernel (false: transposing generic kernel)
 size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream);
@@ -587,6 +589,7 @@ int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, flo
   p.kchunk = 0, p.splits = 1, p.stats = stats, p.stats_act = stats_act;
   if (mode == I3D_GEMM_NT)
     return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_NT, decltype(bn)::value>(p, stream); });
+  if (g_tn_ws) return gemm_tn_ws(M, N, segs[0], C, ldc, accumulate, stream);
   return with_bn(mode, M, N, [&](auto bn) { return launch_generic<I3D_GEMM_TN, decltype(bn)::value>(p, stream); });
 }
 

@@ -47,13 +47,16 @@ struct WsParams {
   int32_t ldb[4];
 };
 
-template <int BN>
+// OCC = CTAs resident per SM.  OCC 1: deepest ring (5 stages at BN = 208).  OCC 2: two CTAs share an SM (2-3 stages
+// each, the other CTA's MMAs cover this one's TMA latency) — used when there are more tiles than SMs, so that e.g.
+// 152 row tiles run as one wave on 148 SMs instead of two.
+template <int BN, int OCC = 1>
 struct WsLayout {
   static constexpr int A_TILE = TC_BM * WS_BK;                 // floats (hi or lo)
   static constexpr int B_TILE = BN * WS_BK;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // a_hi, a_lo, b_hi, b_lo
   static constexpr int STAGE_BYTES = STAGE * 4;
-  static constexpr int MAX_BYTES = 220 * 1024;
+  static constexpr int MAX_BYTES = OCC == 1 ? 220 * 1024 : 108 * 1024;
   static constexpr int STAGES = (MAX_BYTES / STAGE_BYTES) < 6 ? (MAX_BYTES / STAGE_BYTES) : 6;
   static constexpr int CTILE_BYTES = TC_BM * (BN + 4) * 4;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES > CTILE_BYTES ? STAGES * STAGE_BYTES : CTILE_BYTES;
@@ -80,9 +83,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(WS_THREADS, 1) gemm_tc_nt_ws_kernel(const __grid_constant__ WsParams p) {
-  using L = WsLayout<BN>;
+template <int BN, int OCC>
+__global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __grid_constant__ WsParams p) {
+  using L = WsLayout<BN, OCC>;
   constexpr int S = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -315,13 +318,13 @@ size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs) {
   return (size_t)2 * (size_t)N * (size_t)ktot * sizeof(float) + 256;
 }
 
-template <int BN>
+template <int BN, int OCC = 1>
 static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s) {
-  using L = WsLayout<BN>;
+  using L = WsLayout<BN, OCC>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm_tc_nt_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+        cudaFuncSetAttribute(gemm_tc_nt_ws_kernel<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
     if (e != cudaSuccess) {
       set_error("i3d_gemm(ws): cudaFuncSetAttribute -> %s", cudaGetErrorString(e));
       return I3D_ERR_CUDA;
@@ -334,7 +337,7 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
   }
   const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
   const int gy = (p.N + BN - 1) / BN;
-  gemm_tc_nt_ws_kernel<BN><<<dim3((unsigned)gx, gy, 1), WS_THREADS, L::BYTES, s>>>(p);
+  gemm_tc_nt_ws_kernel<BN, OCC><<<dim3((unsigned)gx, gy, 1), WS_THREADS, L::BYTES, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("i3d_gemm(ws): launch failed -> %s", cudaGetErrorString(e));
@@ -381,15 +384,19 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
   const int sms = sm_count();
   if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
   if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
-  if (N <= 112) return launch_ws<112>(p, hi, lo, ktot, stream);
+  if (N <= 112) return gx > sms ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
   if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
   if (N <= 208) {
     // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when the row tiles alone leave
     // half the SMs idle (node-level GEMMs: 72 row tiles at batch 512).
     if (2 * gx <= sms) return launch_ws<112>(p, hi, lo, ktot, stream);
+    if (gx > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);          // more tiles than SMs: co-resident pairs
     return launch_ws<208>(p, hi, lo, ktot, stream);
   }
-  if ((N + 207) / 208 <= (N + 255) / 256) return launch_ws<208>(p, hi, lo, ktot, stream);   // same tiles, less padding
+  if ((N + 207) / 208 <= (N + 255) / 256) {                                  // same tile count, less padding
+    if (gx * ((N + 207) / 208) > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);
+    return launch_ws<208>(p, hi, lo, ktot, stream);
+  }
   return launch_ws<256>(p, hi, lo, ktot, stream);
 }
 

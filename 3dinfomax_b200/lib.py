@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "i3d.h")
 SO_PATH = os.path.join(_HERE, "lib3dinfomax_b200.so")
-SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_net3d.cu", "i3d_gemm.cu", "i3d_gemm_tc.cu", "i3d_gemm_tc_ws.cu",
+SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_net3d.cu", "i3d_gemm.cu", "i3d_gemm_tc.cu", "i3d_gemm_tc_ws.cu", "i3d_gemm_tc_tn.cu",
            "i3d_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
