@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kColThreads)
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[0][i] = 0.0, acc[1][i] = 0.0;
   if (m.active) {
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
       Vec<V> y;
       y.load(Y + r * ldy + m.cg * V);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kColThreads)
     rstd[i] = m.active ? save_mean_rstd[F + m.cg * V + i] : 0.f;
   }
   if (m.active) {
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
       Vec<V> y, d;
       y.load(Y + r * ldy + m.cg * V);
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(kColThreads)
 
 static inline int col_grid(int64_t M, int FV) {
   const int RP = kColThreads / FV;
-  int64_t need = (M + (int64_t)RP * 4 - 1) / ((int64_t)RP * 4);  // ~4 rows per thread: enough CTAs to keep HBM busy
-  int64_t cap = (int64_t)sm_count() * 8;
+  int64_t need = (M + (int64_t)RP * 8 - 1) / ((int64_t)RP * 8);  // >= 8 rows per thread
+  int64_t cap = (int64_t)sm_count() * 2;   // every CTA ends with 2F same-address atomics: more CTAs serialise on them (measured)
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }

@@ -294,7 +294,9 @@ __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int
     if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = t[threadIdx.x][i];
   }
 }
-static int g_gemm_backend = 0;   // 0: tensor cores (tcgen05) where eligible, fp32 SIMT otherwise; 1: SIMT only
+static int g_gemm_backend = 0;   // 0: tensor cores (tcgen05) where eligible, fp32 SIMT otherwise; 1: SIMT only;
+                                 // 2: as 0 but weight gradients (TN) through the MN-major descriptor kernel
+extern bool g_tn_ws;
 }  // namespace i3d
 
 using namespace i3d;
@@ -313,12 +315,12 @@ extern "C" int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in,
 
 extern "C" int i3d_gemm_backend(int backend) {
   const int old = g_gemm_backend;
-  if (backend == 0 || backend == 1) g_gemm_backend = backend;
+  if (backend >= 0 && backend <= 2) g_gemm_backend = backend, g_tn_ws = backend == 2;
   return old;
 }
 
 extern "C" size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
-  if (g_gemm_backend != 0 || !segs || n_seg < 1 || n_seg > 4 || mode < 0 || mode > 2) return 0;
+  if (g_gemm_backend == 1 || !segs || n_seg < 1 || n_seg > 4 || mode < 0 || mode > 2) return 0;
   return gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
 }
 
@@ -340,7 +342,7 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     I3D_REQUIRE(segs[s].K >= 0 && (segs[s].K == 0 || (segs[s].A && segs[s].B)), "segment operand is null");
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
-  if (g_gemm_backend == 0 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
+  if (g_gemm_backend != 1 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
     if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
     return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act,
                    as_stream(stream));

@@ -253,178 +253,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
-
-// =================================================================================================================
-// NT kernel with the B operand (weights) pre-split into hi / lo [N, Kpad_total] buffers and streamed by TMA.
-// =================================================================================================================
-struct TcTmaParams {
-  CUtensorMap map_hi, map_lo;       // [N rows, Kpad_total cols] fp32, box = [BN rows x 32 cols], SWIZZLE_128B
-  const float* A[4];
-  const int32_t* a_idx[4];
-  const float* scale[4];
-  int32_t lda[4], K[4], kcol0[4];   // kcol0: first column of the segment inside the split buffers (multiple of 32)
-  int n_seg;
-  int64_t M;
-  int N;
-  float* C;
-  int ldc;
-  const float* bias;
-  int accumulate;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_nt_tma_kernel(const __grid_constant__ TcTmaParams p) {
-  using L = TcLayout<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)TC_STAGES * L::STAGE);
-  uint64_t* mma_done = bars;                      // [STAGES] stage may be overwritten
-  uint64_t* b_full = bars + TC_STAGES;            // [STAGES] TMA bytes of the stage have landed
-  uint64_t* acc_done = bars + 2 * TC_STAGES;      // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * BN;
-  const int64_t M = p.M;
-  const int N = p.N;
-
-  if (warp == 0) tmem_alloc(tmem_slot, L::TMEM_COLS);
-  if (tid == 32) {
-    for (int s = 0; s < 2 * TC_STAGES + 1; ++s) mbar_init(&bars[s], 1);
-    fence_mbar_init();
-    tma_prefetch_desc(&p.map_hi);
-    tma_prefetch_desc(&p.map_lo);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
-
-  int total = 0;
-  for (int s = 0; s < p.n_seg; ++s) total += (p.K[s] + TC_BK - 1) / TC_BK;
-
-  // A prefetch cursor (runs two k-blocks ahead of the consumer) and its per-segment row bookkeeping
-  int pf_seg = 0, pf_k0 = 0;
-  int64_t a_row[4];
-  float a_sc[4];
-  auto bind_segment = [&](int s) {
-    const int32_t* __restrict__ a_idx = p.a_idx[s];
-    const float* __restrict__ scale = p.scale[s];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t gm = m0 + i * 32 + (tid >> 3);
-      a_row[i] = -1;
-      a_sc[i] = 1.f;
-      if (gm < M) {
-        a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : gm;
-        if (scale) a_sc[i] = __ldg(scale + gm);
-      }
-    }
-  };
-  bind_segment(0);
-  // NOTE: nothing in here may consume the loaded values (the scale is applied at store time), otherwise the
-  // loads stop being a prefetch
-  auto prefetch = [&](float4 (&va)[4], float (&vs)[4]) {
-    const float* __restrict__ A = p.A[pf_seg];
-    const int lda = p.lda[pf_seg], K = p.K[pf_seg];
-    const int kc = pf_k0 + (tid & 7) * 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_row[i] >= 0 && kc < K) v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
-      va[i] = v;
-      vs[i] = a_sc[i];
-    }
-    pf_k0 += TC_BK;
-    if (pf_k0 >= K && pf_seg + 1 < p.n_seg) {
-      pf_seg += 1;
-      pf_k0 = 0;
-      bind_segment(pf_seg);
-    }
-  };
-
-  // consumer cursor: column of the current k-block inside the split B buffers
-  int cs_seg = 0, cs_k0 = 0;
-
-  auto body = [&](int it, float4 (&va)[4], float (&vs)[4]) {
-    const int st = it % TC_STAGES;
-    const int use = it / TC_STAGES;
-    float* a_hi = tiles + (size_t)st * L::STAGE;
-    float* a_lo = a_hi + L::A_TILE;
-    float* b_hi = a_lo + L::A_TILE;
-    float* b_lo = b_hi + L::B_TILE;
-    if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
-    tc_fence_after();
-    if (tid == 0) {                         // B tiles of this k-block: two TMA boxes, one transaction barrier
-      const int kcol = p.kcol0[cs_seg] + cs_k0;
-      mbar_expect_tx(&b_full[st], 2u * BN * TC_BK * 4u);
-      tma_load_2d(b_hi, &p.map_hi, kcol, n0, &b_full[st]);
-      tma_load_2d(b_lo, &p.map_lo, kcol, n0, &b_full[st]);
-    }
-    cs_k0 += TC_BK;
-    if (cs_k0 >= p.K[cs_seg] && cs_seg + 1 < p.n_seg) {
-      cs_seg += 1;
-      cs_k0 = 0;
-    }
-    const int j = tid & 7;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 v = va[i];
-      const float sc = vs[i];
-      v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-      split_store4(a_hi, a_lo, sw128_off(i * 32 + (tid >> 3), j), v);
-    }
-    fence_proxy_async();
-    if (it + 2 < total) prefetch(va, vs);   // refill this register set with the k-block two iterations ahead
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&b_full[st], (uint32_t)(use & 1));
-      tc_fence_after();
-      issue_kblock(tmem, a_hi, a_lo, b_hi, b_lo, idesc, it == 0);
-      umma_commit(&mma_done[st]);
-    }
-  };
-
-  float4 va0[4], va1[4];
-  float vs0[4], vs1[4];
-  if (total > 0) prefetch(va0, vs0);
-  if (total > 1) prefetch(va1, vs1);
-  for (int it = 0; it < total; it += 2) {
-    body(it, va0, vs0);
-    if (it + 1 < total) body(it + 1, va1, vs1);
-  }
-  if (total > 0) {
-    if (tid == 0) umma_commit(acc_done);
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-  }
-  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
-}
-
-// hi[n, col0 + c] = tf32(B[n, c]),  lo = B - hi  for c < K;  zeros for K <= c < Kpad
-__global__ void split_tf32_kernel(const float* __restrict__ B, int N, int K, int ldb, float* __restrict__ hi,
-                                  float* __restrict__ lo, int ldo, int col0, int Kpad) {
-  const int quads = Kpad >> 2;
-  const int64_t total = (int64_t)N * quads;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(t / quads);
-    const int c = (int)(t - (int64_t)n * quads) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < K) v = __ldg(reinterpret_cast<const float4*>(B + (int64_t)n * ldb + c));
-    float4 h, l;
-    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-    l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi + (int64_t)n * ldo + col0 + c) = h;
-    *reinterpret_cast<float4*>(lo + (int64_t)n * ldo + col0 + c) = l;
-  }
-}
-
 __global__ void tc_zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
   const int64_t total = M * N;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -434,36 +262,6 @@ __global__ void tc_zero_block_kernel(float* __restrict__ C, int64_t M, int N, in
 }
 
 // ------------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-static bool make_b_map(CUtensorMap* map, float* base, int N, int ktot, int bn) {
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
-  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <typename Kern>
 static int set_smem(Kern kern, size_t bytes, bool* configured) {
   if (*configured) return I3D_OK;
@@ -514,20 +312,6 @@ static int launch_generic(TcParams& p, cudaStream_t s) {
   return launched("gemm");
 }
 
-template <int BN>
-static int launch_tma(TcTmaParams& p, float* hi, float* lo, int ktot, cudaStream_t s) {
-  using L = TcLayout<BN>;
-  static bool configured = false;
-  if (int rc = set_smem(gemm_tc_nt_tma_kernel<BN>, L::BYTES, &configured)) return rc;
-  if (!make_b_map(&p.map_hi, hi, p.N, ktot, BN) || !make_b_map(&p.map_lo, lo, p.N, ktot, BN)) {
-    set_error("i3d_gemm(tc): cuTensorMapEncodeTiled failed");
-    return I3D_ERR_CUDA;
-  }
-  const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
-  const int gy = (p.N + BN - 1) / BN;
-  gemm_tc_nt_tma_kernel<BN><<<dim3((unsigned)gx, gy, 1), TC_THREADS, L::BYTES, s>>>(p);
-  return launched("gemm(tma)");
-}
 
 static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
@@ -551,7 +335,9 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
 
 bool gemm_ws_available();
 int gemm_tn_ws(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int accumulate, cudaStream_t stream);
-static bool g_tn_ws = true;   // MN-major warp-specialised TN kernel (false: transposing generic kernel)
+// true: MN-major (SWIZZLE_128B_BASE32B) warp-specialised TN kernel, i3d_gemm_backend(2).  Measured slower than the
+// transposing generic kernel on the dW shapes of this path, so it is opt-in.
+bool g_tn_ws = false;
 size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream);

@@ -101,7 +101,8 @@ typedef struct {
 
 /* segs: HOST array of n_seg (<=4) descriptors.  bias[N] optional (added once).  accumulate!=0: C +=
  * Backend: tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-level accuracy, accumulator in TMEM) for
- * the shapes it covers, the fp32 SIMT kernel otherwise.  i3d_gemm_backend(1) forces SIMT; returns the old value. */
+ * the shapes it covers, the fp32 SIMT kernel otherwise.  i3d_gemm_backend(1) forces SIMT,
+ * (2) keeps tensor cores and routes TN through the MN-major descriptor kernel; returns the old value. */
 int i3d_gemm_backend(int backend);
 /* out[c, r] = in[r, c]; used to hand W^T to the NT kernel so that dx = dy W runs on the same tensor-core path */
 int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in, float* out, int ld_out, void* stream);

@@ -253,13 +253,14 @@ def case_gemm_tc():
         ref = _gemm_ref(K.TN, M, N, [s], None, C0)
         dsegs = _to_dev([s])
         res = {}
-        for backend in (0, 1):
+        for backend in (0, 1, 2):
             L.i3d_gemm_backend(backend)
             C = C0.clone().to(DEV) if accum else torch.full((M, N), float("nan"), device=DEV)
             K.gemm(K.TN, M, N, dsegs, C, None, accum)
             res[backend] = C
         L.i3d_gemm_backend(0)
         out += [("gemm_tc/tn_%s/vs_fp64" % tag, rel(res[0], ref), 3e-5),
+                ("gemm_tc/tn_%s/mn_major_vs_fp64" % tag, rel(res[2], ref), 3e-5),
                 ("gemm_tc/tn_%s/simt_vs_fp64" % tag, rel(res[1], ref), 2e-5)]
     x = rn(777, 200)
     out.append(("transpose", exact(K.transpose(x.to(DEV)[:, 8:72]), x[:, 8:72].t().contiguous()), 0))
