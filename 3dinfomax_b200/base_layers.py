@@ -32,6 +32,8 @@ class _Linear(nn.Module):
         super().__init__()
         self.weight = nn.Parameter(torch.empty(out_dim, in_dim))
         self.bias = nn.Parameter(torch.zeros(out_dim))
+        # lets FusedAdam hand this weight a view of its flat gradient buffer that ops._FC accumulates into directly
+        self.weight._i3d_direct_grad = True
 
 
 class _BatchNorm(nn.Module):

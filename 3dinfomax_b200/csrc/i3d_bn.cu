@@ -4,6 +4,7 @@
 // Column statistics are accumulated in fp64: Net3D's BN inputs have mean^2 >> var,
 // where an fp32 E[x^2]-E[x]^2 loses the variance.  All kernels are HBM-bound row streams: a thread owns one
 // 16-byte column group and walks rows with a fixed stride, so column partials stay in registers.
+#include <cstdlib>
 #include <initializer_list>
 
 #include "i3d_vec.cuh"
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// rows are walked kColBatch at a time: all loads of a batch are issued before any arithmetic, so a thread keeps
+// 2*kColBatch 16-byte requests in flight (these kernels are latency-bound at 2 CTAs/SM otherwise)
+constexpr int kColBatch = 4;
+
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
     bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
@@ -155,11 +160,36 @@ __global__ void __launch_bounds__(kColThreads)
     rstd[i] = m.active ? save_mean_rstd[F + m.cg * V + i] : 0.f;
   }
   if (m.active) {
-#pragma unroll 4
-    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
+    const int64_t stride = (int64_t)gridDim.x * m.RP;
+    const float* yp = Y + m.cg * V;
+    const float* dp = dO + m.cg * V;
+    int64_t r = (int64_t)blockIdx.x * m.RP + m.rg;
+    for (; r + (kColBatch - 1) * stride < M; r += kColBatch * stride) {
+      Vec<V> y[kColBatch], d[kColBatch];
+#pragma unroll
+      for (int j = 0; j < kColBatch; ++j) {
+        y[j].load(yp + (r + j * stride) * ldy);
+        d[j].load(dp + (r + j * stride) * ldd);
+      }
+      // fp32 inside a batch of 4 rows, fp64 across batches
+      float s0[V], s1[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) s0[i] = 0.f, s1[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kColBatch; ++j)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xhat = (act_apply(y[j].v[i], act) - mean[i]) * rstd[i];
+          s0[i] += d[j].v[i];
+          s1[i] = fmaf(d[j].v[i], xhat, s1[i]);
+        }
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[0][i] += (double)s0[i], acc[1][i] += (double)s1[i];
+    }
+    for (; r < M; r += stride) {
       Vec<V> y, d;
-      y.load(Y + r * ldy + m.cg * V);
-      d.load(dO + r * ldd + m.cg * V);
+      y.load(yp + r * ldy);
+      d.load(dp + r * ldd);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float xhat = (act_apply(y.v[i], act) - mean[i]) * rstd[i];
@@ -200,10 +230,12 @@ __global__ void __launch_bounds__(kColThreads)
     }
   }
   if (m.active) {
-    for (int64_t r = (int64_t)blockIdx.x * m.RP + m.rg; r < M; r += (int64_t)gridDim.x * m.RP) {
-      Vec<V> y, d, o;
-      y.load(Y + r * ldy + m.cg * V);
-      d.load(dO + r * ldd + m.cg * V);
+    const int64_t stride = (int64_t)gridDim.x * m.RP;
+    const float* yp = Y + m.cg * V;
+    const float* dp = dO + m.cg * V;
+    float* op = dY + m.cg * V;
+    auto one = [&](const Vec<V>& y, const Vec<V>& d, int64_t row) {
+      Vec<V> o;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         float dh = d.v[i];
@@ -215,7 +247,24 @@ __global__ void __launch_bounds__(kColThreads)
         o.v[i] = dy;
         db[i] += dy;
       }
-      o.store(dY + r * lddy + m.cg * V);
+      o.store(op + row * lddy);
+    };
+    int64_t r = (int64_t)blockIdx.x * m.RP + m.rg;
+    for (; r + (kColBatch - 1) * stride < M; r += kColBatch * stride) {
+      Vec<V> y[kColBatch], d[kColBatch];
+#pragma unroll
+      for (int j = 0; j < kColBatch; ++j) {
+        y[j].load(yp + (r + j * stride) * ldy);
+        d[j].load(dp + (r + j * stride) * ldd);
+      }
+#pragma unroll
+      for (int j = 0; j < kColBatch; ++j) one(y[j], d[j], r + j * stride);
+    }
+    for (; r < M; r += stride) {
+      Vec<V> y, d;
+      y.load(yp + r * ldy);
+      d.load(dp + r * ldd);
+      one(y, d, r);
     }
   }
   if (dbias) {
@@ -279,8 +328,16 @@ __global__ void __launch_bounds__(kColThreads)
 
 static inline int col_grid(int64_t M, int FV) {
   const int RP = kColThreads / FV;
+  // every CTA ends with 2F same-address atomics (LTS serialises them per address), so the grid is capped at a few
+  // CTAs per SM; I3D_COL_CTAS_PER_SM overrides the cap for tuning runs
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("I3D_COL_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 2;
+    if (per_sm < 1 || per_sm > 16) per_sm = 2;
+  }
   int64_t need = (M + (int64_t)RP * 8 - 1) / ((int64_t)RP * 8);  // >= 8 rows per thread
-  int64_t cap = (int64_t)sm_count() * 2;   // every CTA ends with 2F same-address atomics: more CTAs serialise on them (measured)
+  int64_t cap = (int64_t)sm_count() * per_sm;
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }

@@ -324,6 +324,47 @@ extern "C" size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const
   return gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
 }
 
+namespace i3d {
+bool gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+int gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transposed, void* ws, int tile0,
+                       i3d_prep_item* out, int* tiles_out);
+int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, cudaStream_t stream);
+int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared);
+}  // namespace i3d
+
+extern "C" int i3d_gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transposed, void* ws, int tile0,
+                                      i3d_prep_item* items_out, int* tiles_out) {
+  I3D_REQUIRE(N > 0 && n_seg >= 1 && n_seg <= 4 && segs && ws && items_out && tiles_out && tile0 >= 0,
+              "invalid argument");
+  for (int s = 0; s < n_seg; ++s)
+    I3D_REQUIRE(segs[s].K > 0 && segs[s].B && segs[s].ldb >= (transposed ? N : segs[s].K), "invalid segment");
+  return gemm_prep_describe(N, n_seg, segs, transposed, ws, tile0, items_out, tiles_out);
+}
+
+extern "C" int i3d_gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, void* stream) {
+  I3D_REQUIRE(n_items >= 0 && total_tiles >= 0 && (n_items == 0 || dev_items), "invalid argument");
+  if (n_items == 0 || total_tiles == 0) return I3D_OK;
+  return gemm_prep_run(dev_items, n_items, total_tiles, as_stream(stream));
+}
+
+extern "C" int i3d_gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
+  return (g_gemm_backend != 1 && segs && gemm_nt_prepared_ok(M, N, n_seg, segs)) ? 1 : 0;
+}
+
+extern "C" int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                                    const float* bias, int accumulate, const void* ws, double* col_stats,
+                                    int stats_act, void* stream) {
+  I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N && ws, "invalid shape");
+  I3D_REQUIRE(!col_stats || !accumulate, "col_stats needs accumulate == 0");
+  if (M == 0 || N == 0) return I3D_OK;
+  I3D_REQUIRE(C != nullptr, "C is null");
+  I3D_REQUIRE(i3d_gemm_nt_prepared_ok(M, N, n_seg, segs), "shape not eligible for prepared operands");
+  if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+  return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, const_cast<void*>(ws), col_stats, stats_act,
+                    as_stream(stream), true);
+}
+
 extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                         const float* bias, int accumulate, void* stream) {
   return i3d_gemm_ex(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, nullptr, 0, nullptr, 0, stream);

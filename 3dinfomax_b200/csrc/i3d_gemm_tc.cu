@@ -313,6 +313,7 @@ static int launch_generic(TcParams& p, cudaStream_t s) {
 }
 
 
+bool gemm_ws_available();
 static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 // problems the tensor-core kernels take: 16-byte aligned operands, float4-divisible extents (float4 staging)
@@ -333,14 +334,21 @@ bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg*
   return false;
 }
 
-bool gemm_ws_available();
+// prepared B operands: only the A side, the shape and the TMA entry point decide
+bool gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
+  if (M < 256 || N < 16 || n_seg < 1 || n_seg > 4 || !gemm_ws_available()) return false;
+  for (int s = 0; s < n_seg; ++s)
+    if (segs[s].K <= 0 || (segs[s].K & 3) || (segs[s].lda & 3) || !al16(segs[s].A) || segs[s].b_idx) return false;
+  return true;
+}
+
 int gemm_tn_ws(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int accumulate, cudaStream_t stream);
 // true: MN-major (SWIZZLE_128B_BASE32B) warp-specialised TN kernel, i3d_gemm_backend(2).  Measured slower than the
 // transposing generic kernel on the dW shapes of this path, so it is opt-in.
 bool g_tn_ws = false;
 size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream);
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared);
 
 // bytes of scratch that let the NT kernel stream the B operand by TMA (hi + lo copies, K padded per segment)
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
@@ -367,7 +375,7 @@ int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, flo
             int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream) {
   const size_t need = gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
   if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && gemm_ws_available())
-    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stats, stats_act, stream);
+    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stats, stats_act, stream, false);
   TcParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];

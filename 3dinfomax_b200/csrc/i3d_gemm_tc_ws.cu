@@ -347,9 +347,86 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
   return I3D_OK;
 }
 
+// ---- batched preparation of many B operands (one launch per optimizer step) ---------------------------------
+// item: one K-segment of one GEMM; 32x32 tiles over (n, padded k).  transposed items read B[c * ldb + n].
+__global__ void __launch_bounds__(256) ws_prep_kernel(const i3d_prep_item* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  // locate the item of this tile: items are sorted by tile0
+  int lo_i = 0, hi_i = n_items - 1;
+  const int t = blockIdx.x;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (items[mid].tile0 <= t) lo_i = mid; else hi_i = mid - 1;
+  }
+  const i3d_prep_item it = items[lo_i];
+  const int ktiles = it.kpad >> 5;
+  const int lt = t - it.tile0;
+  const int n0 = (lt / ktiles) << 5, c0 = (lt % ktiles) << 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  if (it.transposed) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, n = n0 + tx;
+      tile[ty + 8 * i][tx] = (c < it.K && n < it.N) ? __ldg(it.B + (int64_t)c * it.ldb + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i, c = c0 + tx;
+      if (n < it.N) {
+        const float v = tile[tx][ty + 8 * i];
+        const float h = to_tf32(v);
+        it.hi[(int64_t)n * it.ldo + it.col0 + c] = h;
+        it.lo[(int64_t)n * it.ldo + it.col0 + c] = v - h;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i, c = c0 + tx;
+      if (n < it.N) {
+        const float v = c < it.K ? __ldg(it.B + (int64_t)n * it.ldb + c) : 0.f;
+        const float h = to_tf32(v);
+        it.hi[(int64_t)n * it.ldo + it.col0 + c] = h;
+        it.lo[(int64_t)n * it.ldo + it.col0 + c] = v - h;
+      }
+    }
+  }
+}
+
+int gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transposed, void* ws, int tile0,
+                       i3d_prep_item* out, int* tiles_out) {
+  int ktot = 0;
+  for (int s = 0; s < n_seg; ++s) ktot += ws_kpad(segs[s].K);
+  float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
+  float* lo = hi + (size_t)N * ktot;
+  int col0 = 0, tiles = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    i3d_prep_item& it = out[s];
+    it.B = segs[s].B, it.hi = hi, it.lo = lo;
+    it.ldb = segs[s].ldb, it.N = N, it.K = segs[s].K, it.kpad = ws_kpad(segs[s].K), it.ldo = ktot, it.col0 = col0;
+    it.transposed = transposed ? 1 : 0, it.tile0 = tile0 + tiles;
+    col0 += it.kpad;
+    tiles += ((N + 31) / 32) * (it.kpad / 32);
+  }
+  *tiles_out = tiles;
+  return I3D_OK;
+}
+
+int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, cudaStream_t stream) {
+  ws_prep_kernel<<<total_tiles, 256, 0, stream>>>(dev_items, n_items);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("i3d_gemm_prep_run: launch failed -> %s", cudaGetErrorString(e));
+    return I3D_ERR_CUDA;
+  }
+  count_launch();
+  return I3D_OK;
+}
+
 // NT GEMM through the warp-specialised kernel.  ws: device scratch of gemm_ws_bytes(...) for the hi/lo weight copies.
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream) {
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared) {
   WsParams p;
   memset(&p, 0, sizeof(p));
   int ktot = 0;
@@ -362,7 +439,7 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
   p.stats = stats, p.stats_act = stats_act;
   float* hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~(uintptr_t)127);
   float* lo = hi + (size_t)N * ktot;
-  {
+  if (!prepared) {
     WsSplitArgs a;
     memset(&a, 0, sizeof(a));
     int kmax = 0;

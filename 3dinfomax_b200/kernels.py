@@ -111,29 +111,116 @@ def embed_sum_bwd(idx, col_off, perm, gout, n_table_rows, max_dim=0):
 
 
 # ----------------------------------------------------------------------------------------- gemm
-def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None):
-    """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld).
-    stats_act: activation code -> also returns fp64 [2N] column sums of act(C), act(C)^2 (fused BatchNorm statistics)."""
+def _seg_array(segs, need_b=True):
     arr = (_lib.gemm_seg * len(segs))()
-    keep = []
     for i, s in enumerate(segs):
         pa, lda = _mat(s["A"], "A")
-        pb, ldb = _mat(s["B"], "B")
-        arr[i].A, arr[i].B = pa, pb
+        arr[i].A = pa
+        if need_b:
+            arr[i].B, ldb = _mat(s["B"], "B")
+            arr[i].ldb = int(ldb)
         arr[i].a_idx = _vec(s.get("a_idx"), torch.int32, "a_idx")
         arr[i].b_idx = _vec(s.get("b_idx"), torch.int32, "b_idx")
         arr[i].scale = _vec(s.get("scale"), torch.float32, "scale")
-        arr[i].K, arr[i].lda, arr[i].ldb = int(s["K"]), int(lda), int(ldb)
-        keep.append(s)
+        arr[i].K, arr[i].lda = int(s["K"]), int(lda)
+    return arr
+
+
+def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepared=None):
+    """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld).
+    stats_act: activation code -> also returns fp64 [2N] column sums of act(C), act(C)^2 (fused BatchNorm statistics).
+    prepared: a ready ``PreparedB`` (NT only): B comes from its scratch, the segments need no "B"."""
     pc, ldc = _mat(C, "C")
     L = _L()
+    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
+    if prepared is not None:
+        if mode != NT:
+            raise ValueError("prepared operands are for NT GEMMs")
+        arr = _seg_array(segs, need_b=False)
+        _lib.check(L.i3d_gemm_nt_prepared(M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                                          1 if accumulate else 0, _p(prepared.ws), _p(stats),
+                                          0 if stats_act is None else stats_act, _s()), "i3d_gemm_nt_prepared")
+        return C if stats_act is None else (C, stats)
+    arr = _seg_array(segs)
     nws = int(L.i3d_gemm_ws_bytes(mode, M, N, len(segs), arr))
     ws = torch.empty(nws, dtype=torch.uint8, device=C.device) if nws else None      # tf32 hi/lo copies of B for TMA
-    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
     _lib.check(L.i3d_gemm_ex(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
                              1 if accumulate else 0, _p(ws), nws, _p(stats), 0 if stats_act is None else stats_act,
                              _s()), "i3d_gemm")
     return C if stats_act is None else (C, stats)
+
+
+def gemm_nt_prepared_ok(M, N, segs):
+    return bool(_L().i3d_gemm_nt_prepared_ok(M, N, len(segs), _seg_array(segs, need_b=False)))
+
+
+class PreparedB:
+    """Persistent tf32 hi/lo scratch of one NT GEMM's B operand (a weight, or column blocks of it read transposed)."""
+    __slots__ = ("W", "ws", "items", "n_items", "epoch", "w_version")
+
+
+class WeightPrep:
+    """Registry of prepared weight operands refreshed by ONE kernel launch per optimizer step.
+
+    ``entry`` is called by ops._FC with the weight views a GEMM would otherwise split on the fly; ``refresh`` (start
+    of a step) rewrites every registered scratch from the current weights; ``invalidate`` (after an optimizer step
+    that bypasses torch's version counter, i.e. FusedAdam) marks them stale.  An entry is used only while
+    ``ready(entry)``: same epoch AND the weight's autograd version unchanged, so a foreign in-place update of the
+    weight silently falls back to the per-call split instead of computing with stale copies."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.entries = {}
+        self.epoch = 0
+        self._table = None
+        self._pinned = []
+        self._tiles = 0
+
+    def entry(self, W, key, N, b_views, transposed):
+        """b_views: list of (2-D view of W as the kernel would read it, K).  transposed: views are [K, N]."""
+        k = (W.data_ptr(), key, bool(transposed))
+        e = self.entries.get(k)
+        if e is not None:
+            return e
+        arr = (_lib.gemm_seg * len(b_views))()
+        for i, (b, kk) in enumerate(b_views):
+            arr[i].B, ldb = _mat(b, "B")
+            arr[i].ldb, arr[i].K = int(ldb), int(kk)
+        ktot = sum((kk + 31) // 32 * 32 for _, kk in b_views)
+        e = PreparedB()
+        e.W = W
+        e.ws = torch.empty(2 * N * ktot * 4 + 256, dtype=torch.uint8, device=self.device)
+        e.items = (_lib.prep_item * len(b_views))()
+        e.n_items = len(b_views)
+        tiles = ctypes.c_int(0)
+        _lib.check(_L().i3d_gemm_prep_describe(N, len(b_views), arr, 1 if transposed else 0, _p(e.ws), self._tiles,
+                                               e.items, ctypes.byref(tiles)), "i3d_gemm_prep_describe")
+        self._tiles += tiles.value
+        e.epoch, e.w_version = -1, -1
+        self.entries[k] = e
+        self._table = None
+        return e
+
+    def ready(self, e):
+        return e.epoch == self.epoch and e.w_version == e.W._version
+
+    def invalidate(self):
+        self.epoch += 1
+
+    def refresh(self):
+        if not self.entries:
+            return
+        ents = list(self.entries.values())
+        if self._table is None:
+            raw = b"".join(bytes(e.items) for e in ents)
+            host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+            self._pinned.append(host)                       # a captured graph re-reads it on replay
+            self._table = torch.empty(len(raw), dtype=torch.uint8, device=self.device)
+            self._table.copy_(host, non_blocking=True)
+            self._n_items = sum(e.n_items for e in ents)
+        _lib.check(_L().i3d_gemm_prep_run(_p(self._table), self._n_items, self._tiles, _s()), "i3d_gemm_prep_run")
+        for e in ents:
+            e.epoch, e.w_version = self.epoch, e.W._version
 
 
 def transpose(x):

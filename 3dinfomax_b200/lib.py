@@ -32,6 +32,13 @@ class gemm_seg(ctypes.Structure):
                 ("lda", ctypes.c_int32), ("ldb", ctypes.c_int32)]
 
 
+class prep_item(ctypes.Structure):
+    """struct i3d_prep_item of include/i3d.h"""
+    _fields_ = [("B", ctypes.c_void_p), ("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("ldb", ctypes.c_int32),
+                ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("kpad", ctypes.c_int32), ("ldo", ctypes.c_int32),
+                ("col0", ctypes.c_int32), ("transposed", ctypes.c_int32), ("tile0", ctypes.c_int32)]
+
+
 _P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
 # name -> (restype, argtypes); must cover every function declared in include/i3d.h (tests check this)
@@ -50,6 +57,11 @@ SIGNATURES = {
     "i3d_gemm": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P]),
     "i3d_gemm_ws_bytes": (ctypes.c_size_t, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg)]),
     "i3d_gemm_ex": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, ctypes.c_size_t, _P, _I, _P]),
+    "i3d_gemm_prep_describe": (_I, [_I, _I, ctypes.POINTER(gemm_seg), _I, _P, _I, ctypes.POINTER(prep_item),
+                                    ctypes.POINTER(ctypes.c_int)]),
+    "i3d_gemm_prep_run": (_I, [_P, _I, _I, _P]),
+    "i3d_gemm_nt_prepared_ok": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg)]),
+    "i3d_gemm_nt_prepared": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, _P, _I, _P]),
     "i3d_act_colstats": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "i3d_bn_apply": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),
     "i3d_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P]),

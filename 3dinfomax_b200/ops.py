@@ -54,12 +54,19 @@ class _FC(torch.autograd.Function):
             off += k
         if off != W.shape[1]:
             raise ValueError("segment widths %d do not add up to the weight's in_features %d" % (off, W.shape[1]))
+        # weights prepared once per step by the trainer's WeightPrep (one launch for all layers) when available
+        prep = getattr(W, "_i3d_prep", None)
+        ready = None
+        if prep is not None and K.gemm_nt_prepared_ok(M, Fout, gsegs):
+            ent = prep.entry(W, ("f",) + tuple(g["K"] for g in gsegs), Fout, [(g["B"], g["K"]) for g in gsegs], False)
+            ready = ent if prep.ready(ent) else None
         save = None
         sums = None
         if cfg.has_bn and cfg.training:
-            _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act)    # statistics from the GEMM epilogue
+            # statistics from the GEMM epilogue
+            _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act, prepared=ready)
         else:
-            K.gemm(K.NT, M, Fout, gsegs, Y, bias=b)
+            K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, prepared=ready)
         if cfg.has_bn:
             O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
                                  cfg.momentum, cfg.eps, cfg.training, residual)
@@ -70,6 +77,7 @@ class _FC(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.M = M
         ctx.has_res = residual is not None
+        ctx.w_param = W           # the Parameter object itself: backward looks for FusedAdam's gradient view on it
         ctx.save_for_backward(W, Y, save, gamma, *xs)
         return O
 
@@ -95,13 +103,17 @@ class _FC(torch.autograd.Function):
         # weight gradient, one column block per segment: dW[:, off:off+k] = dY^T (scale * gather(x))
         dW = None
         if ctx.needs_input_grad[1]:
-            dW = torch.zeros_like(W)        # one memset; the split-K column-block GEMMs below accumulate into it
+            # FusedAdam gives FC weights a view of its flat (pre-zeroed) gradient buffer: accumulate straight into it
+            # and hand autograd nothing; otherwise one memset and the split-K column-block GEMMs accumulate into dW
+            direct = getattr(ctx.w_param, "_i3d_grad_view", None)
+            acc = direct if direct is not None else torch.zeros_like(W)
             off = 0
             for s, x in zip(segs, xs):
                 k = x.shape[1]
                 K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
-                       dW[:, off:off + k], accumulate=True)
+                       acc[:, off:off + k], accumulate=True)
                 off += k
+            dW = None if direct is not None else acc
         # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
         dxs = [None] * len(xs)
         groups = {}
@@ -112,23 +124,32 @@ class _FC(torch.autograd.Function):
                 groups.setdefault(x.data_ptr(), []).append((i, s, x, off))
             off += k
         Wt = None
+        prep = getattr(ctx.w_param, "_i3d_prep", None)
         for members in groups.values():
             x0 = members[0][2]
             R, k = x0.shape
             dx = torch.empty(R, k, dtype=torch.float32, device=W.device)
-            # dx = dy W is fed to the tensor-core NT kernel as dy (W^T)^T: one small transpose of the weight per
-            # backward instead of a second operand-staging variant
+            # dx = dy W is fed to the tensor-core NT kernel as dy (W^T)^T: the transposed hi/lo copies come from the
+            # per-step WeightPrep when there is one, else from one small transpose of the weight per backward
             via_nt = R >= 256 and Fout % 4 == 0 and k % 4 == 0
-            if via_nt and Wt is None:
-                Wt = K.transpose(W)                                  # [in_features, out_features]
             nn = []
             for (_i, s, _x, o) in members:
                 if s.idx is None:
                     a = dY
                 else:
                     a = K.segment_sum_fwd(dY, s.inv_rowptr, s.inv_idx)
-                nn.append({"A": a, "B": Wt[o:o + k, :] if via_nt else W[:, o:o + k], "K": Fout, "scale": s.scale})
-            K.gemm(K.NT if via_nt else K.NN, R, k, nn, dx)
+                nn.append({"A": a, "K": Fout, "scale": s.scale, "_o": o})
+            ready = None
+            if via_nt and prep is not None and K.gemm_nt_prepared_ok(R, k, nn):
+                ent = prep.entry(ctx.w_param, ("b", k) + tuple(m[3] for m in members), k,
+                                 [(W[:, m[3]:m[3] + k], Fout) for m in members], True)
+                ready = ent if prep.ready(ent) else None
+            if ready is None:
+                if via_nt and Wt is None:
+                    Wt = K.transpose(W)                                  # [in_features, out_features]
+                for g in nn:
+                    g["B"] = Wt[g["_o"]:g["_o"] + k, :] if via_nt else W[:, g["_o"]:g["_o"] + k]
+            K.gemm(K.NT if via_nt else K.NN, R, k, nn, dx, prepared=ready)
             dxs[members[0][0]] = dx
         dres = dO if (ctx.has_res and ctx.needs_input_grad[5]) else None
         return (None, dW, db, dgamma, dbeta, dres) + tuple(dxs)

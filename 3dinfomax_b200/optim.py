@@ -7,6 +7,10 @@ with a foreach loop.  Here each group's parameters are re-homed as views into ON
 
     one multi-tensor pack of the gradients -> [one NCCL all-reduce when data parallel] -> one Adam kernel per group.
 
+FC weights (flagged ``_i3d_direct_grad`` by base_layers._Linear) skip even the pack: their ``.grad`` IS a view of the
+flat gradient buffer and ``ops._FC.backward`` accumulates the weight-gradient GEMM into it, so ``zero_grad()`` is one
+memset per group and must be called between steps (the reference loop does, trainer/trainer.py:121-123).
+
 ``param_groups`` keeps torch's layout (list of dicts with 'params', 'lr', 'betas', 'eps', 'weight_decay'), so the
 reference's ``WarmUpWrapper`` (trainer/lr_schedulers.py), which rewrites ``group['lr']`` every step, drives it as is.
 """
@@ -33,6 +37,8 @@ class FusedAdam:
             self.param_groups.append(pg)
             self._flat.append(self._flatten(pg["params"]))
         self._step = 0
+        self._needs_zero = False
+        self.post_step_hooks = []          # e.g. WeightPrep.invalidate: the Adam kernel bypasses tensor versions
         dev = self._device()
         self._step_dev = torch.ones(1, dtype=torch.int64, device=dev) if graph_safe else None
         self._hyper_dev = [torch.zeros(6, dtype=torch.float64, device=dev) for _ in self.param_groups] \
@@ -64,7 +70,15 @@ class FusedAdam:
                     raise TypeError("fp32 parameters only")
                 flat[o:o + n].copy_(p.data.reshape(-1))
                 p.data = flat[o:o + n].view(p.shape)
-        return {"p": flat, "g": torch.zeros_like(flat), "m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
+        gflat = torch.zeros_like(flat)
+        direct = []
+        for p, o, n in zip(params, offs, sizes):
+            d = bool(getattr(p, "_i3d_direct_grad", False))
+            direct.append(d)
+            if d:
+                p._i3d_grad_view = gflat[o:o + n].view(p.shape)
+                p.grad = p._i3d_grad_view
+        return {"p": flat, "g": gflat, "m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "direct": direct,
                 "off": torch.tensor(offs, dtype=torch.int64, device=dev),
                 "len": torch.tensor(sizes, dtype=torch.int64, device=dev), "offs": offs, "sizes": sizes,
                 "ptr_key": None, "ptrs": None}
@@ -78,32 +92,37 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self, grad_scale=1.0):
+        if self._needs_zero:
+            raise RuntimeError("FusedAdam: call optimizer.zero_grad() between steps — FC weight gradients accumulate "
+                               "in place in the flat buffer (module.zero_grad() does not clear it)")
         self._step += 1
         for gi, (g, fl) in enumerate(zip(self.param_groups, self._flat)):
             if fl is None:
                 continue
             params = g["params"]
             self._check_views(params, fl)
-            grads = [p.grad for p in params]
-            if any(x is None for x in grads):
-                # parameters that took no part in the step keep a zero gradient (Adam still decays its moments)
-                fl["g"].zero_()
+            # directly-accumulated weights already live in fl["g"]; parameters that took no part in the step keep
+            # the zeros zero_grad() left there (Adam still decays their moments)
+            gbase = fl["g"].data_ptr()
+            grads = [None if (d or p.grad is None or p.grad.data_ptr() == gbase + 4 * o) else p.grad
+                     for p, d, o in zip(params, fl["direct"], fl["offs"])]
+            self._needs_zero = self._needs_zero or any(fl["direct"])
             key = tuple(0 if x is None else x.data_ptr() for x in grads)
             if key != fl["ptr_key"]:
                 for x in grads:
                     if x is not None and (not x.is_contiguous() or x.dtype != torch.float32):
                         raise RuntimeError("gradients must be contiguous fp32")
                 live = [i for i, x in enumerate(grads) if x is not None]
-                # pinned staging + async copy: legal inside CUDA-graph capture (the graph re-reads the pinned table)
-                host = torch.tensor([key[i] for i in live], dtype=torch.int64).pin_memory()
-                fl["ptrs_host"] = fl.get("ptrs_host", []) + [host]      # keep alive for graph replays
-                fl["ptrs"] = torch.empty(len(live), dtype=torch.int64, device=fl["p"].device)
-                fl["ptrs"].copy_(host, non_blocking=True)
-                if len(live) == len(grads):
-                    fl["poff"], fl["plen"] = fl["off"], fl["len"]
-                else:
-                    fl["poff"] = fl["off"][live].contiguous()
-                    fl["plen"] = fl["len"][live].contiguous()
+                # one pinned table (pointers, offsets, lengths) + async copy: legal inside CUDA-graph capture (the
+                # graph re-reads the pinned host memory on replay, so it is kept alive)
+                host = torch.tensor([[key[i] for i in live], [fl["offs"][i] for i in live],
+                                     [fl["sizes"][i] for i in live]], dtype=torch.int64).reshape(3, len(live))
+                if live:
+                    host = host.pin_memory()
+                fl["ptrs_host"] = fl.get("ptrs_host", []) + [host]
+                table = torch.empty(3, len(live), dtype=torch.int64, device=fl["p"].device)
+                table.copy_(host, non_blocking=True)
+                fl["ptrs"], fl["poff"], fl["plen"] = table[0], table[1], table[2]
                 fl["ptr_key"] = key
             if fl["ptrs"].numel():
                 K.multi_copy(fl["ptrs"], fl["poff"], fl["plen"], fl["g"], True)
@@ -122,6 +141,8 @@ class FusedAdam:
                             grad_scale, self._step)
         if self.graph_safe:
             K.add_i64(self._step_dev, 1)
+        for hook in self.post_step_hooks:
+            hook()
 
     def _upload_hyper(self, gi, hyper):
         host = torch.tensor(hyper, dtype=torch.float64).pin_memory()
@@ -138,9 +159,15 @@ class FusedAdam:
                 self._upload_hyper(gi, hyper)
 
     def zero_grad(self, set_to_none=True):
-        for g in self.param_groups:
-            for p in g["params"]:
-                if p.grad is not None:
+        self._needs_zero = False
+        for g, fl in zip(self.param_groups, self._flat):
+            if fl is None:
+                continue
+            fl["g"].zero_()                                   # one memset: packed copies and direct views alike
+            for p, d in zip(g["params"], fl["direct"]):
+                if d:
+                    p.grad = p._i3d_grad_view                 # undo a module.zero_grad() that dropped the view
+                elif p.grad is not None:
                     if set_to_none:
                         p.grad = None
                     else:

@@ -17,6 +17,7 @@ import torch
 
 from . import dist as D
 from .graph import GraphBatch
+from .kernels import WeightPrep
 from .optim import FusedAdam
 
 
@@ -41,8 +42,15 @@ class SelfSupervisedTrainer:
         self.optim = FusedAdam([{"params": batch_norm_params, "weight_decay": 0}, {"params": normal_params}],
                                process_group=self.process_group if self.world > 1 else None, graph_safe=graph_safe,
                                **optimizer_params)
+        # FC weights get their tf32 hi/lo operand copies (plain and transposed) from one launch per step
+        self.prep = WeightPrep(self.device)
+        for _, v in named:
+            if getattr(v, "_i3d_direct_grad", False):
+                v._i3d_prep = self.prep
+        self.optim.post_step_hooks.append(self.prep.invalidate)
 
     def forward_pass(self, batch):
+        self.prep.refresh()
         info2d, info3d, *rest = tuple(batch)
         view2d = self.model(*info2d)
         view3d = self.model3d(*info3d)
@@ -95,12 +103,10 @@ class CapturedStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.tr.optim.zero_grad(set_to_none=True)
                 self._step_body()
                 self.tr.optim_steps += 1
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.tr.optim.zero_grad(set_to_none=True)
         from . import lib as _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
@@ -116,6 +122,7 @@ class CapturedStep:
         return g2, g3
 
     def _step_body(self):
+        self.tr.optim.zero_grad(set_to_none=True)   # inside the graph: one memset per parameter group
         g2, g3 = self._graphs()
         loss, _, _ = self.tr.forward_pass(([g2], [g3]))
         loss.backward()

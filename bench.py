@@ -199,6 +199,7 @@ def run_b200(args):
             caps = [i3d.CapturedStep(tr, *fresh(p), warmup=2 if i == 0 else 1) for i, p in enumerate(resident)]
         except Exception as e:   # capture is an optimisation, not a requirement: fall back to eager launches
             note = "graph capture failed (%s); eager launches" % (str(e).splitlines()[0][:120],)
+            print("bench.py WARNING: " + note, file=sys.stderr, flush=True)
             caps = None
             torch.cuda.synchronize()
             tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=TAU), dev, {"lr": LR},

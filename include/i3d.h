@@ -119,6 +119,30 @@ int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs,
                 const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats, int stats_act,
                 void* stream);
 
+/* Weights change once per optimizer step, not once per GEMM: a caller that owns persistent scratch can prepare the
+ * hi/lo copies of MANY GEMMs' B operands with ONE launch (after the optimizer step) and then run each GEMM with
+ * i3d_gemm_nt_prepared, which skips the per-call split (and, for `transposed` operands, the weight transpose that
+ * dx = dy W [models/base_layers.py:100 backward] otherwise needs).
+ *   i3d_gemm_prep_describe  host-only: fills items_out[0..n_seg) for one GEMM whose scratch is `ws`
+ *                           (i3d_gemm_ws_bytes of the same N / segments).  transposed != 0: segs[s].B points at the
+ *                           operand stored as [K, N] (ld = ldb), e.g. a column block W[:, o:o+k] of a weight used as
+ *                           the B of dx = dy W.  tile0: running tile offset; *tiles_out: tiles this GEMM adds.
+ *   i3d_gemm_prep_run       dev_items: the described items copied to DEVICE memory by the caller. */
+typedef struct i3d_prep_item {
+  const float* B;
+  float* hi;
+  float* lo;
+  int32_t ldb, N, K, kpad, ldo, col0, transposed, tile0;
+} i3d_prep_item;
+int i3d_gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transposed, void* ws, int tile0,
+                           i3d_prep_item* items_out, int* tiles_out);
+int i3d_gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, void* stream);
+/* NT GEMM on the tensor-core path with B taken from prepared scratch (segs[s].B / ldb are ignored).  Fails with
+ * I3D_ERR_INVALID when the shape is not eligible for that path (use i3d_gemm_nt_prepared_ok to ask first). */
+int i3d_gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+                         int accumulate, const void* ws, double* col_stats, int stats_act, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]
  *   h = act(Y);  O = gamma*(h-mean)*rstd + beta (+ residual)

@@ -268,6 +268,54 @@ def case_gemm_tc():
 
 
 # --------------------------------------------------------------------------------------- FC tail (BN)
+def case_weight_prep():
+    """Operands prepared once per step (kernels.WeightPrep, one launch for all weights) must give bit-identical
+    GEMMs to the per-call split, plain and transposed, and must go stale on any update of the weight."""
+    g = gen(41)
+    out = []
+    rn = lambda *s: torch.randn(*s, generator=g)
+    prep = K.WeightPrep(DEV)
+    W = rn(200, 616).to(DEV)                     # 600 used + an unused tail, like a wider weight
+    W2 = rn(100, 2600).to(DEV)
+    M = 3000
+    xs = [rn(M, k).to(DEV) for k in (200, 200, 200)]
+    sc = rn(M).to(DEV)
+    segs = [{"A": xs[0], "K": 200, "B": W[:, 0:200]}, {"A": xs[1], "K": 200, "B": W[:, 200:400], "scale": sc},
+            {"A": xs[2], "K": 200, "B": W[:, 400:600]}]
+    e1 = prep.entry(W, ("f", 200, 200, 200), 200, [(sg["B"], 200) for sg in segs], False)
+    # transposed: dx = dy W[:, 200:400] -> N = 200, K = 200 rows of W
+    dy = rn(M, 200).to(DEV)
+    e2 = prep.entry(W, ("b", 200, 200), 200, [(W[:, 200:400], 200)], True)
+    # K not a multiple of 32, N not a multiple of 32
+    x3 = rn(M, 36).to(DEV)
+    e3 = prep.entry(W2, ("f", 36), 100, [(W2[:, 4:40], 36)], False)
+    dy3 = rn(M, 100).to(DEV)
+    e4 = prep.entry(W2, ("b", 36, 4), 36, [(W2[:, 4:40], 100)], True)
+    out.append(("weight_prep/stale_before_refresh", float(prep.ready(e1)), 0))
+    prep.refresh()
+    out.append(("weight_prep/ready_after_refresh", 1.0 - float(prep.ready(e1) and prep.ready(e4)), 0))
+    ref = K.gemm(K.NT, M, 200, segs, torch.empty(M, 200, device=DEV))
+    got = K.gemm(K.NT, M, 200, segs, torch.empty(M, 200, device=DEV), prepared=e1)
+    out.append(("weight_prep/plain_bit_exact", exact(got, ref), 0))
+    Wt = K.transpose(W)
+    ref = K.gemm(K.NT, M, 200, [{"A": dy, "K": 200, "B": Wt[200:400, :]}], torch.empty(M, 200, device=DEV))
+    got = K.gemm(K.NT, M, 200, [{"A": dy, "K": 200}], torch.empty(M, 200, device=DEV), prepared=e2)
+    out.append(("weight_prep/transposed_bit_exact", exact(got, ref), 0))
+    ref = K.gemm(K.NT, M, 100, [{"A": x3, "K": 36, "B": W2[:, 4:40]}], torch.empty(M, 100, device=DEV))
+    got = K.gemm(K.NT, M, 100, [{"A": x3, "K": 36}], torch.empty(M, 100, device=DEV), prepared=e3)
+    out.append(("weight_prep/ragged_bit_exact", exact(got, ref), 0))
+    W2t = K.transpose(W2)
+    ref = K.gemm(K.NT, M, 36, [{"A": dy3, "K": 100, "B": W2t[4:40, :]}], torch.empty(M, 36, device=DEV))
+    got = K.gemm(K.NT, M, 36, [{"A": dy3, "K": 100}], torch.empty(M, 36, device=DEV), prepared=e4)
+    out.append(("weight_prep/ragged_transposed_bit_exact", exact(got, ref), 0))
+    W.add_(1.0)                                   # torch-visible update -> version counter
+    out.append(("weight_prep/stale_after_inplace_update", float(prep.ready(e1)), 0))
+    prep.refresh()
+    prep.invalidate()                             # what FusedAdam's post-step hook does
+    out.append(("weight_prep/stale_after_invalidate", float(prep.ready(e1)), 0))
+    return out
+
+
 def case_bn():
     g = gen(5)
     out = []
@@ -714,6 +762,6 @@ def case_full_size_properties():
 
 from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 
-ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
+ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_golden, case_golden_qmugs, case_train_steps,
              case_train_steps_captured, case_full_size_properties, case_sharded_equals_full]
