@@ -50,6 +50,7 @@ __device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
     act_colstats_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, double* __restrict__ sums) {
+  pdl_grid_sync();
   const int FV = F / V;
   const ColMap m = col_map(FV);
   double acc[2][V];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256)
                     const float* __restrict__ beta, float momentum, float eps, int training,
                     float* __restrict__ save_mean_rstd, const float* __restrict__ residual, float* __restrict__ O,
                     int ldo) {
+  pdl_grid_sync();
   extern __shared__ float shf[];  // alpha[F], beta[F]
   float* s_alpha = shf;
   float* s_beta = shf + F;
@@ -149,6 +151,7 @@ template <int V>
 __global__ void __launch_bounds__(kColThreads)
     bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
                          int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2) {
+  pdl_grid_sync();
   const int FV = F / V;
   const ColMap m = col_map(FV);
   double acc[2][V];
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(kColThreads)
                         int act, int has_bn, int training, const float* __restrict__ save_mean_rstd,
                         const float* __restrict__ gamma, const double* __restrict__ sums2, float* __restrict__ dY,
                         int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_grid_sync();
   const int FV = F / V;
   const ColMap m = col_map(FV);
   float mean[V], rstd[V], k1[V], k2[V], gr[V], db[V];
@@ -285,11 +289,13 @@ __global__ void __launch_bounds__(kColThreads)
 }
 
 __global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = act_apply(x[i], act);
 }
 __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, int64_t n, int act,
                                float* __restrict__ gx) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     gx[i] = gy[i] * act_grad(x[i], act);
 }
@@ -298,6 +304,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
     colsum_kernel(const float* __restrict__ x, int ldx, int64_t M, int F, float* __restrict__ out) {
+  pdl_grid_sync();
   const int FV = F / V;
   const ColMap m = col_map(FV);
   float acc[V];
@@ -358,9 +365,9 @@ int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double*
   I3D_REQUIRE(FV <= kColThreads, "feature width too large (F <= 1024 when 16B-aligned, else F <= 256)");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
   if (v4)
-    act_colstats_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(Y, M, F, ldy, act, sums);
+    launch(act_colstats_kernel<4>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums);
   else
-    act_colstats_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(Y, M, F, ldy, act, sums);
+    launch(act_colstats_kernel<1>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -379,11 +386,11 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
   const size_t smem = sizeof(float) * 2 * F;
   cudaStream_t s = as_stream(stream);
   if (v4)
-    bn_apply_kernel<4><<<grid_for(work, 256), 256, smem, s>>>(Y, M, F, ldy, act, sums, running_mean, running_var,
+    launch(bn_apply_kernel<4>, grid_for(work, 256), 256, smem, s, Y, M, F, ldy, act, sums, running_mean, running_var,
                                                               num_batches_tracked, gamma, beta, momentum, eps,
                                                               training, save_mean_rstd, residual, O, ldo);
   else
-    bn_apply_kernel<1><<<grid_for(work, 256), 256, smem, s>>>(Y, M, F, ldy, act, sums, running_mean, running_var,
+    launch(bn_apply_kernel<1>, grid_for(work, 256), 256, smem, s, Y, M, F, ldy, act, sums, running_mean, running_var,
                                                               num_batches_tracked, gamma, beta, momentum, eps,
                                                               training, save_mean_rstd, residual, O, ldo);
   I3D_LAUNCHED();
@@ -402,10 +409,10 @@ int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t
   I3D_REQUIRE(FV <= kColThreads, "feature width too large");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
   if (v4)
-    bn_bwd_reduce_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+    launch(bn_bwd_reduce_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
                                                                       sums2);
   else
-    bn_bwd_reduce_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+    launch(bn_bwd_reduce_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
                                                                       sums2);
   I3D_LAUNCHED();
   return I3D_OK;
@@ -423,11 +430,11 @@ int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t 
   const size_t smem = sizeof(float) * V * kColThreads;
   cudaStream_t s = as_stream(stream);
   if (v4)
-    bn_bwd_apply_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, has_bn, training,
+    launch(bn_bwd_apply_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
                                                                      dgamma, dbeta);
   else
-    bn_bwd_apply_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(dO, ldd, Y, ldy, M, F, act, has_bn, training,
+    launch(bn_bwd_apply_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
                                                                      dgamma, dbeta);
   I3D_LAUNCHED();
@@ -437,7 +444,7 @@ int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t 
 int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream) {
   I3D_REQUIRE(n >= 0 && (n == 0 || (x && y)), "invalid argument");
   if (n == 0) return I3D_OK;
-  act_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, act, y);
+  launch(act_fwd_kernel, grid_for(n, 256), 256, 0, as_stream(stream), x, n, act, y);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -445,7 +452,7 @@ int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream) {
 int i3d_act_bwd(const float* gy, const float* x, int64_t n, int act, float* gx, void* stream) {
   I3D_REQUIRE(n >= 0 && (n == 0 || (gy && x && gx)), "invalid argument");
   if (n == 0) return I3D_OK;
-  act_bwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(gy, x, n, act, gx);
+  launch(act_bwd_kernel, grid_for(n, 256), 256, 0, as_stream(stream), gy, x, n, act, gx);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -460,9 +467,9 @@ int i3d_colsum(const float* x, int ldx, int64_t M, int F, float* out, void* stre
   I3D_REQUIRE(FV <= kColThreads, "feature width too large");
   const size_t smem = sizeof(float) * V * kColThreads;
   if (v4)
-    colsum_kernel<4><<<col_grid(M, FV), kColThreads, smem, s>>>(x, ldx, M, F, out);
+    launch(colsum_kernel<4>, col_grid(M, FV), kColThreads, smem, s, x, ldx, M, F, out);
   else
-    colsum_kernel<1><<<col_grid(M, FV), kColThreads, smem, s>>>(x, ldx, M, F, out);
+    launch(colsum_kernel<1>, col_grid(M, FV), kColThreads, smem, s, x, ldx, M, F, out);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/i3d.h"
 
@@ -12,7 +13,34 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
 
+bool pdl_enabled();   // programmatic dependent launch for every kernel of the library (I3D_PDL=0 turns it off)
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Every kernel of the library starts with pdl_grid_sync() and is launched through launch(): with programmatic stream
+// serialization the next kernel's CTAs are scheduled as soon as all CTAs of the running one have started, and block
+// in griddepcontrol.wait until that grid has completed and its writes are visible.  The step is ~300 dependent
+// launches of 5-50 us, so the launch/drain gap between them is a measurable share of it.
+// Rule: a kernel never touches global memory before pdl_grid_sync(); kernels that are not ours (torch, NCCL, memset
+// nodes) carry no attribute and serialise fully on both sides.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError()
+}
 
 #define I3D_REQUIRE(cond, msg)                                   \
   do {                                                           \

@@ -33,6 +33,7 @@ __device__ __forceinline__ bool is_al16(const void* p) { return (reinterpret_cas
 
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmParams p) {
+  pdl_grid_sync();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
 }
 
 __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
+  pdl_grid_sync();
   const int64_t total = M * N;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = t / N;
@@ -279,6 +281,7 @@ size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_se
 // out[c, r] = in[r, c]  (32x32 shared-memory tiles, coalesced on both sides)
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in,
                                  float* __restrict__ out, int ld_out) {
+  pdl_grid_sync();
   __shared__ float t[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -308,7 +311,7 @@ extern "C" int i3d_transpose(const float* in, int64_t rows, int cols, int ld_in,
   const int64_t gx = (rows + 31) / 32;
   const int gy = (cols + 31) / 32;
   I3D_REQUIRE(gx < (1ll << 31) && gy <= 65535, "matrix too large");
-  transpose_kernel<<<dim3((unsigned)gx, gy), dim3(32, 8), 0, as_stream(stream)>>>(in, rows, cols, ld_in, out, ld_out);
+  launch(transpose_kernel, dim3((unsigned)gx, gy), dim3(32, 8), 0, as_stream(stream), in, rows, cols, ld_in, out, ld_out);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -421,18 +424,18 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     p.kchunk = kchunk;
     p.splits = K > 0 ? (K + kchunk - 1) / kchunk : 1;
     if (p.splits > 1 && !accumulate) {
-      zero_block_kernel<<<grid_for(M * N, 256), 256, 0, s>>>(C, M, N, ldc);
+      launch(zero_block_kernel, grid_for(M * N, 256), 256, 0, s, C, M, N, ldc);
       I3D_LAUNCHED();
     }
-    gemm_kernel<I3D_GEMM_TN><<<dim3((unsigned)gx, gy, p.splits), GEMM_THREADS, 0, s>>>(p);
+    launch(gemm_kernel<I3D_GEMM_TN>, dim3((unsigned)gx, gy, p.splits), GEMM_THREADS, 0, s, p);
   } else if (mode == I3D_GEMM_NT) {
-    gemm_kernel<I3D_GEMM_NT><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
+    launch(gemm_kernel<I3D_GEMM_NT>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);
     if (col_stats) {
       I3D_LAUNCHED();
       return i3d_act_colstats(C, M, N, ldc, stats_act, col_stats, stream);
     }
   } else {
-    gemm_kernel<I3D_GEMM_NN><<<dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s>>>(p);
+    launch(gemm_kernel<I3D_GEMM_NN>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);
   }
   I3D_LAUNCHED();
   return I3D_OK;

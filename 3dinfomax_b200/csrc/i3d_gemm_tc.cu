@@ -46,6 +46,7 @@ struct TcParams {
 // =================================================================================================================
 template <int MODE, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  pdl_grid_sync();
   using L = TcLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 __global__ void tc_zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
+  pdl_grid_sync();
   const int64_t total = M * N;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = t / N;
@@ -304,11 +306,11 @@ static int launch_generic(TcParams& p, cudaStream_t s) {
     p.splits = (K + kchunk - 1) / kchunk;
     gz = p.splits;
     if (p.splits > 1 && !p.accumulate) {
-      tc_zero_block_kernel<<<grid_for(p.M * p.N, 256), 256, 0, s>>>(p.C, p.M, p.N, p.ldc);
+      launch(tc_zero_block_kernel, grid_for(p.M * p.N, 256), 256, 0, s, p.C, p.M, p.N, p.ldc);
       if (int rc = launched("zero")) return rc;
     }
   }
-  gemm_tc_kernel<MODE, BN><<<dim3((unsigned)gx, gy, gz), TC_THREADS, L::BYTES, s>>>(p);
+  launch(gemm_tc_kernel<MODE, BN>, dim3((unsigned)gx, gy, gz), TC_THREADS, L::BYTES, s, p);
   return launched("gemm");
 }
 

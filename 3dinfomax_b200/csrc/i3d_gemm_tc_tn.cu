@@ -80,6 +80,7 @@ __device__ __forceinline__ int mn_off(int kk, int q, int atoms) {
 
 template <int BN>
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tc_tn_ws_kernel(const __grid_constant__ TnParams p) {
+  pdl_grid_sync();
   using L = TnLayout<BN>;
   constexpr int S = L::STAGES;
   constexpr int A_ATOMS = TC_BM / 32, B_ATOMS = BN / 32;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tc_tn_ws_kernel(const __gr
 }
 
 __global__ void tn_zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
+  pdl_grid_sync();
   const int64_t total = M * N;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = t / N;
@@ -278,10 +280,10 @@ static int launch_tn(TnParams& p, cudaStream_t s) {
   p.kchunk = kchunk;
   p.splits = (p.K + kchunk - 1) / kchunk;
   if (p.splits > 1 && !p.accumulate) {
-    tn_zero_block_kernel<<<grid_for(p.M * p.N, 256), 256, 0, s>>>(p.C, p.M, p.N, p.ldc);
+    launch(tn_zero_block_kernel, grid_for(p.M * p.N, 256), 256, 0, s, p.C, p.M, p.N, p.ldc);
     count_launch();
   }
-  gemm_tc_tn_ws_kernel<BN><<<dim3((unsigned)gx, gy, p.splits), TN_THREADS, L::BYTES, s>>>(p);
+  launch(gemm_tc_tn_ws_kernel<BN>, dim3((unsigned)gx, gy, p.splits), TN_THREADS, L::BYTES, s, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("i3d_gemm(tn): launch failed -> %s", cudaGetErrorString(e));

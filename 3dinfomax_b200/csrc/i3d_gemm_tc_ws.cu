@@ -85,6 +85,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
 
 template <int BN, int OCC>
 __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __grid_constant__ WsParams p) {
+  pdl_grid_sync();
   using L = WsLayout<BN, OCC>;
   constexpr int S = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -259,6 +260,7 @@ struct WsSplitArgs {
   int N, ldo;
 };
 __global__ void ws_split_tf32_kernel(const WsSplitArgs a, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_grid_sync();
   const int sg = blockIdx.y;
   const float* __restrict__ B = a.B[sg];
   const int K = a.K[sg], ldb = a.ldb[sg], col0 = a.kcol0[sg];
@@ -337,7 +339,7 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
   }
   const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
   const int gy = (p.N + BN - 1) / BN;
-  gemm_tc_nt_ws_kernel<BN, OCC><<<dim3((unsigned)gx, gy, 1), WS_THREADS, L::BYTES, s>>>(p);
+  launch(gemm_tc_nt_ws_kernel<BN, OCC>, dim3((unsigned)gx, gy, 1), WS_THREADS, L::BYTES, s, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("i3d_gemm(ws): launch failed -> %s", cudaGetErrorString(e));
@@ -350,6 +352,7 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
 // ---- batched preparation of many B operands (one launch per optimizer step) ---------------------------------
 // item: one K-segment of one GEMM; 32x32 tiles over (n, padded k).  transposed items read B[c * ldb + n].
 __global__ void __launch_bounds__(256) ws_prep_kernel(const i3d_prep_item* __restrict__ items, int n_items) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   // locate the item of this tile: items are sorted by tile0
   int lo_i = 0, hi_i = n_items - 1;
@@ -414,7 +417,7 @@ int gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transpose
 }
 
 int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, cudaStream_t stream) {
-  ws_prep_kernel<<<total_tiles, 256, 0, stream>>>(dev_items, n_items);
+  launch(ws_prep_kernel, total_tiles, 256, 0, stream, dev_items, n_items);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("i3d_gemm_prep_run: launch failed -> %s", cudaGetErrorString(e));
@@ -449,7 +452,7 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
       kmax = a.kpad[s] > kmax ? a.kpad[s] : kmax;
     }
     a.N = N, a.ldo = ktot;
-    ws_split_tf32_kernel<<<dim3(grid_for((int64_t)N * (kmax / 4), 256), n_seg), 256, 0, stream>>>(a, hi, lo);
+    launch(ws_split_tf32_kernel, dim3(grid_for((int64_t)N * (kmax / 4), 256), n_seg), 256, 0, stream, a, hi, lo);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("i3d_gemm(ws): split launch failed -> %s", cudaGetErrorString(e));

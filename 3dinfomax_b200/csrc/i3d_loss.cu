@@ -22,6 +22,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 __global__ void row_norms_kernel(const float* __restrict__ z, int64_t R, int D, float* __restrict__ norms) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256)
     ntxent_rows_fwd_kernel(float* __restrict__ P, int64_t B, int64_t Bc, int C, const float* __restrict__ n1,
                            const float* __restrict__ n2, int norm, float eps, float tau, int64_t row_offset,
                            float* __restrict__ rowstats, float* __restrict__ loss_rows) {
+  pdl_grid_sync();
   __shared__ float sh[32];
   const int64_t ncol = Bc * C;
   for (int64_t i = blockIdx.x; i < B; i += gridDim.x) {
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256)
                            const float* __restrict__ n2, int norm, float eps, float tau, int64_t row_offset,
                            const float* __restrict__ rowstats, const float* __restrict__ gout, float inv_B,
                            float* __restrict__ dn1, float* __restrict__ dn2) {
+  pdl_grid_sync();
   __shared__ float sh[32];
   const int64_t ncol = Bc * C;
   const float gl = gout[0] * inv_B;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void sum_scaled_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float sh[32];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -114,6 +118,7 @@ __global__ void sum_scaled_kernel(const float* __restrict__ x, int64_t n, float 
 
 __global__ void norm_bwd_accum_kernel(const float* __restrict__ z, const float* __restrict__ norms,
                                       const float* __restrict__ dn, int64_t R, int D, float* __restrict__ dz) {
+  pdl_grid_sync();
   const int64_t total = R * D;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / D;
@@ -130,6 +135,7 @@ struct AdamHyper {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, AdamHyper h, int64_t step,
                             const double* __restrict__ hyper_dev, const int64_t* __restrict__ step_dev) {
+  pdl_grid_sync();
   __shared__ float sc[7];
   if (threadIdx.x == 0) {
     if (hyper_dev) {
@@ -162,10 +168,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-__global__ void add_i64_kernel(int64_t* x, int64_t d) { x[0] += d; }
+__global__ void add_i64_kernel(int64_t* x, int64_t d) {
+  pdl_grid_sync(); x[0] += d; }
 
 __global__ void multi_copy_kernel(const uint64_t* __restrict__ ptrs, const int64_t* __restrict__ off,
                                   const int64_t* __restrict__ len, float* __restrict__ flat, int to_flat) {
+  pdl_grid_sync();
   const int t = blockIdx.y;
   float* tp = reinterpret_cast<float*>(ptrs[t]);
   float* fp = flat + off[t];
@@ -185,7 +193,7 @@ extern "C" {
 int i3d_row_norms(const float* z, int64_t R, int D, float* norms, void* stream) {
   I3D_REQUIRE(R >= 0 && D > 0 && (R == 0 || (z && norms)), "invalid argument");
   if (R == 0) return I3D_OK;
-  row_norms_kernel<<<grid_for(R * 32, 256), 256, 0, as_stream(stream)>>>(z, R, D, norms);
+  launch(row_norms_kernel, grid_for(R * 32, 256), 256, 0, as_stream(stream), z, R, D, norms);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -197,7 +205,7 @@ int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1,
               "invalid argument");
   if (B == 0) return I3D_OK;
   const int grid = (int)(B < 65535 ? B : 65535);
-  ntxent_rows_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
+  launch(ntxent_rows_fwd_kernel, grid, 256, 0, as_stream(stream), P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
                                                               rowstats, loss_rows);
   I3D_LAUNCHED();
   return I3D_OK;
@@ -205,7 +213,7 @@ int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1,
 
 int i3d_sum_scaled(const float* x, int64_t n, float scale, float* out, void* stream) {
   I3D_REQUIRE(n >= 0 && out && (n == 0 || x), "invalid argument");
-  sum_scaled_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, scale, out);
+  launch(sum_scaled_kernel, 1, 1024, 0, as_stream(stream), x, n, scale, out);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -218,7 +226,7 @@ int i3d_ntxent_rows_bwd(float* P, int64_t B, int64_t Bc, int C, const float* n1,
               "invalid argument");
   if (B == 0) return I3D_OK;
   const int grid = (int)(B < 65535 ? B : 65535);
-  ntxent_rows_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
+  launch(ntxent_rows_bwd_kernel, grid, 256, 0, as_stream(stream), P, B, Bc, C, n1, n2, norm, eps, tau, row_offset,
                                                               rowstats, gout, inv_B, dn1, dn2);
   I3D_LAUNCHED();
   return I3D_OK;
@@ -228,7 +236,7 @@ int i3d_norm_bwd_accum(const float* z, const float* norms, const float* dn, int6
                        void* stream) {
   I3D_REQUIRE(R >= 0 && D > 0 && (R == 0 || (z && norms && dn && dz)), "invalid argument");
   if (R == 0) return I3D_OK;
-  norm_bwd_accum_kernel<<<grid_for(R * D, 256), 256, 0, as_stream(stream)>>>(z, norms, dn, R, D, dz);
+  launch(norm_bwd_accum_kernel, grid_for(R * D, 256), 256, 0, as_stream(stream), z, norms, dn, R, D, dz);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -239,14 +247,14 @@ int i3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, doubl
   I3D_REQUIRE(n >= 0 && (step_dev || step >= 1) && (n == 0 || (p && g && m && v)), "invalid argument");
   if (n == 0) return I3D_OK;
   AdamHyper h{lr, beta1, beta2, eps, weight_decay, grad_scale};
-  adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, h, step, hyper_dev, step_dev);
+  launch(adam_kernel, grid_for(n, 256), 256, 0, as_stream(stream), p, g, m, v, n, h, step, hyper_dev, step_dev);
   I3D_LAUNCHED();
   return I3D_OK;
 }
 
 int i3d_add_i64(int64_t* x, int64_t delta, void* stream) {
   I3D_REQUIRE(x != nullptr, "invalid argument");
-  add_i64_kernel<<<1, 1, 0, as_stream(stream)>>>(x, delta);
+  launch(add_i64_kernel, 1, 1, 0, as_stream(stream), x, delta);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -255,7 +263,7 @@ int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len,
                    void* stream) {
   I3D_REQUIRE(T >= 0 && T <= 65535 && (T == 0 || (ptrs && off && len && flat)), "invalid argument");
   if (T == 0) return I3D_OK;
-  multi_copy_kernel<<<dim3(16, T, 1), 256, 0, as_stream(stream)>>>(ptrs, off, len, flat, to_flat);
+  launch(multi_copy_kernel, dim3(16, T, 1), 256, 0, as_stream(stream), ptrs, off, len, flat, to_flat);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -9,6 +9,7 @@ namespace i3d {
 
 __global__ void fourier_encode_kernel(const float* __restrict__ dist, const int32_t* __restrict__ perm, int64_t E,
                                       int k, float* __restrict__ out) {
+  pdl_grid_sync();
   const int W = 2 * k + 1;
   const int64_t total = E * W;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void fourier_encode_kernel(const float* __restrict__ dist, const int3
 // one thread per edge row; H is small (20) so a row is 80 contiguous bytes
 __global__ void soft_gate_fwd_kernel(const float* __restrict__ msg, int64_t E, int H, const float* __restrict__ ws,
                                      const float* __restrict__ bs, float* __restrict__ m, float* __restrict__ w) {
+  pdl_grid_sync();
   extern __shared__ float s_ws[];
   for (int i = threadIdx.x; i < H; i += blockDim.x) s_ws[i] = ws[i];
   __syncthreads();
@@ -49,6 +51,7 @@ __global__ void soft_gate_fwd_kernel(const float* __restrict__ msg, int64_t E, i
 __global__ void soft_gate_bwd_kernel(const float* __restrict__ gm, const float* __restrict__ msg,
                                      const float* __restrict__ w, int64_t E, int H, const float* __restrict__ ws,
                                      float* __restrict__ gmsg, float* __restrict__ gws, float* __restrict__ gbs) {
+  pdl_grid_sync();
   extern __shared__ float s_ws[];  // ws[H] then block partials gws[H], gbs
   float* s_acc = s_ws + H;
   for (int i = threadIdx.x; i < H; i += blockDim.x) s_ws[i] = ws[i];
@@ -85,6 +88,7 @@ __global__ void soft_gate_bwd_kernel(const float* __restrict__ gm, const float* 
 }
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ vec, int64_t M, int F, float* __restrict__ out) {
+  pdl_grid_sync();
   const int64_t total = M * F;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
     out[t] = __ldg(vec + (t % F));
@@ -92,6 +96,7 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ vec, int64_t M, 
 
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                            float* __restrict__ y) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __fadd_rn(a[i], b[i]);
 }
@@ -105,7 +110,7 @@ extern "C" {
 int i3d_fourier_encode(const float* dist, const int32_t* perm, int64_t E, int k, float* out, void* stream) {
   I3D_REQUIRE(E >= 0 && k >= 0 && k <= 16 && (E == 0 || (dist && out)), "invalid argument");
   if (E == 0) return I3D_OK;
-  fourier_encode_kernel<<<grid_for(E * (2 * k + 1), 256), 256, 0, as_stream(stream)>>>(dist, perm, E, k, out);
+  launch(fourier_encode_kernel, grid_for(E * (2 * k + 1), 256), 256, 0, as_stream(stream), dist, perm, E, k, out);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -114,7 +119,7 @@ int i3d_soft_gate_fwd(const float* msg, int64_t E, int H, const float* ws, const
                       void* stream) {
   I3D_REQUIRE(E >= 0 && H > 0 && H <= 1024 && ws && bs && (E == 0 || (msg && m && w)), "invalid argument");
   if (E == 0) return I3D_OK;
-  soft_gate_fwd_kernel<<<grid_for(E, 128), 128, sizeof(float) * H, as_stream(stream)>>>(msg, E, H, ws, bs, m, w);
+  launch(soft_gate_fwd_kernel, grid_for(E, 128), 128, sizeof(float) * H, as_stream(stream), msg, E, H, ws, bs, m, w);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -124,7 +129,7 @@ int i3d_soft_gate_bwd(const float* gm, const float* msg, const float* w, int64_t
   I3D_REQUIRE(E >= 0 && H > 0 && H <= 1024 && ws && gws && gbs && (E == 0 || (gm && msg && w && gmsg)),
               "invalid argument");
   if (E == 0) return I3D_OK;
-  soft_gate_bwd_kernel<<<grid_for(E, 128, 4), 128, sizeof(float) * (2 * H + 1), as_stream(stream)>>>(
+  launch(soft_gate_bwd_kernel, grid_for(E, 128, 4), 128, sizeof(float) * (2 * H + 1), as_stream(stream), 
       gm, msg, w, E, H, ws, gmsg, gws, gbs);
   I3D_LAUNCHED();
   return I3D_OK;
@@ -133,7 +138,7 @@ int i3d_soft_gate_bwd(const float* gm, const float* msg, const float* w, int64_t
 int i3d_broadcast_rows(const float* vec, int64_t M, int F, float* out, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && vec && (M == 0 || out), "invalid argument");
   if (M == 0) return I3D_OK;
-  broadcast_rows_kernel<<<grid_for(M * F, 256), 256, 0, as_stream(stream)>>>(vec, M, F, out);
+  launch(broadcast_rows_kernel, grid_for(M * F, 256), 256, 0, as_stream(stream), vec, M, F, out);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -141,7 +146,7 @@ int i3d_broadcast_rows(const float* vec, int64_t M, int F, float* out, void* str
 int i3d_add(const float* a, const float* b, int64_t n, float* y, void* stream) {
   I3D_REQUIRE(n >= 0 && (n == 0 || (a && b && y)), "invalid argument");
   if (n == 0) return I3D_OK;
-  add_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(a, b, n, y);
+  launch(add_kernel, grid_for(n, 256), 256, 0, as_stream(stream), a, b, n, y);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -17,6 +17,7 @@ template <int V>
 __global__ void embed_sum_fwd_kernel(const int64_t* __restrict__ idx, int64_t R, int C,
                                      const int32_t* __restrict__ col_off, const int32_t* __restrict__ perm,
                                      const float* __restrict__ table, int F, float* __restrict__ out) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = R * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -40,6 +41,7 @@ template <int V>
 __global__ void embed_sum_bwd_kernel(const int64_t* __restrict__ idx, int64_t R, int C,
                                      const int32_t* __restrict__ col_off, const int32_t* __restrict__ perm,
                                      const float* __restrict__ gout, int F, float* __restrict__ gtable) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = R * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(256)
     embed_sum_bwd_smem_kernel(const int64_t* __restrict__ idx, int64_t R, int C, const int32_t* __restrict__ col_off,
                               const int32_t* __restrict__ perm, const float* __restrict__ gout, int F,
                               float* __restrict__ gtable, int table_rows, int rows_per_cta) {
+  pdl_grid_sync();
   extern __shared__ float acc[];          // [dim][F]
   __shared__ unsigned touched[8];
   const int c = blockIdx.y;
@@ -109,6 +112,7 @@ template <int V>
 __global__ void __launch_bounds__(256)
     pna_aggregate_fwd_kernel(const float* __restrict__ msg, const int32_t* __restrict__ rowptr, int64_t N, int F,
                              float* __restrict__ out, int ldo) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = N * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(256)
     pna_aggregate_bwd_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ msg,
                              const float* __restrict__ out, int ldo, const int32_t* __restrict__ rowptr, int64_t N,
                              int F, float* __restrict__ dmsg) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = N * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -239,6 +244,7 @@ struct RoOps {
 template <int V>
 __global__ void segment_readout_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ ptr,
                                            int64_t B, int F, RoOps ops, float* __restrict__ out) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = B * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -279,6 +285,7 @@ template <int V>
 __global__ void segment_readout_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, int ldx,
                                            const float* __restrict__ out, const int32_t* __restrict__ ptr, int64_t B,
                                            int F, RoOps ops, float* __restrict__ dx, int lddx) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = B * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -330,6 +337,7 @@ template <int V>
 __global__ void segment_sum_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rowptr,
                                        const int32_t* __restrict__ idx, int64_t N, int F, int mean,
                                        const float* __restrict__ addend, int lda, float* __restrict__ out, int ldo) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = N * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -364,6 +372,7 @@ template <int V>
 __global__ void segment_sum_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ rowptr,
                                        const int32_t* __restrict__ rowid, int64_t E, int F, int mean,
                                        float* __restrict__ gx) {
+  pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = E * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -388,9 +397,9 @@ using namespace i3d;
 #define I3D_DISPATCH_VEC(vec_ok, KERNEL, grid, block, stream, ...)          \
   do {                                                                       \
     if (vec_ok)                                                              \
-      KERNEL<4><<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
+      launch(KERNEL<4>, grid, block, 0, stream, __VA_ARGS__);                    \
     else                                                                     \
-      KERNEL<1><<<grid, block, 0, stream>>>(__VA_ARGS__);                    \
+      launch(KERNEL<1>, grid, block, 0, stream, __VA_ARGS__);                    \
   } while (0)
 
 extern "C" {
@@ -426,10 +435,10 @@ int i3d_embed_sum_bwd(const int64_t* idx, int64_t R, int C, const int32_t* col_o
     chunks = (R + rows_per_cta - 1) / rows_per_cta;
     const dim3 grid((unsigned)chunks, C);
     if (v4)
-      embed_sum_bwd_smem_kernel<4><<<grid, 256, smem, as_stream(stream)>>>(idx, R, C, col_off, perm, gout, F, gtable,
+      launch(embed_sum_bwd_smem_kernel<4>, grid, 256, smem, as_stream(stream), idx, R, C, col_off, perm, gout, F, gtable,
                                                                             table_rows, rows_per_cta);
     else
-      embed_sum_bwd_smem_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(idx, R, C, col_off, perm, gout, F, gtable,
+      launch(embed_sum_bwd_smem_kernel<1>, grid, 256, smem, as_stream(stream), idx, R, C, col_off, perm, gout, F, gtable,
                                                                             table_rows, rows_per_cta);
     I3D_LAUNCHED();
     return I3D_OK;

@@ -1,5 +1,6 @@
 // Library runtime: error string, launch counter, device attributes.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -32,9 +33,24 @@ int sm_count() {
   return n;
 }
 
+static int g_pdl = -1;   // -1: not decided yet (I3D_PDL env, default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("I3D_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 }  // namespace i3d
 
 extern "C" {
+
+int i3d_set_pdl(int enabled) {
+  const int old = i3d::pdl_enabled() ? 1 : 0;
+  i3d::g_pdl = enabled ? 1 : 0;
+  return old;
+}
 
 int i3d_version(void) { return 100; }
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "i3d_version": (_I, []),
     "i3d_last_error_string": (ctypes.c_char_p, []),
     "i3d_launch_count": (_L, []),
+    "i3d_set_pdl": (_I, [_I]),
     "i3d_csr_build": (_I, [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
     "i3d_csr_build_i32": (_I, [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
     "i3d_segment_ptr": (_I, [_P, _L, _P, _P]),

@@ -47,6 +47,9 @@ int i3d_version(void);
 const char* i3d_last_error_string(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
 int64_t i3d_launch_count(void);
+/* Programmatic dependent launch (griddepcontrol) between consecutive kernels of the library: on by default
+ * (environment I3D_PDL=0 disables); returns the previous setting.  Results are identical either way. */
+int i3d_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph structure.  Replaces DGL's per-call degree bucketing (host numpy sort + sync) behind
