@@ -6,6 +6,8 @@
 // because messages are produced in CSR order (see DESIGN.md "data layout").
 #include <initializer_list>
 
+#include <cstdlib>
+
 #include "i3d_vec.cuh"
 
 namespace i3d {
@@ -108,65 +110,92 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 constexpr float kAggEps = 1e-5f;  // EPS, models/pna.py:14
 
+// One thread owns one (node, 16-byte column group).  Bond graphs have in-degree <= 4 almost always, so the fast path
+// issues every row load of the item before any arithmetic (predicated, no loop) and a thread works on kAggItems
+// items at once: the kernel is a latency chain rowptr -> rows -> stores, and memory-level parallelism per thread is
+// what moves it towards the HBM roofline.  Sums run in edge order j = 0..D-1 in both paths and in the backward
+// kernel (the relu gate on var must see the same bits).
+
 template <int V>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void agg_finish(const Vec<V>& s, const Vec<V>& q, const Vec<V>& mx, const Vec<V>& mn,
+                                           int D, float* o, int F) {
+  const float fd = (float)D;
+  Vec<V> mean, sd;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mean.v[i] = __fdiv_rn(s.v[i], fd);
+    const float msq = __fdiv_rn(q.v[i], fd);
+    const float var = fmaxf(__fsub_rn(msq, __fmul_rn(mean.v[i], mean.v[i])), 0.f);
+    sd.v[i] = __fsqrt_rn(__fadd_rn(var, kAggEps));
+  }
+  mean.store_cs(o), mx.store_cs(o + F), mn.store_cs(o + 2 * F), sd.store_cs(o + 3 * F);
+}
+
+template <int V, int kAggItems, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     pna_aggregate_fwd_kernel(const float* __restrict__ msg, const int32_t* __restrict__ rowptr, int64_t N, int F,
                              float* __restrict__ out, int ldo) {
   pdl_grid_sync();
   const int FV = F / V;
   const int64_t total = N * FV;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t v = t / FV;
-    const int c0 = (int)(t - v * FV) * V;
-    const int32_t b = __ldg(rowptr + v), e = __ldg(rowptr + v + 1);
-    const int D = e - b;
-    float* o = out + v * (int64_t)ldo + c0;
-    Vec<V> s, q, mx, mn;
-    if (D <= 0) {
-      s.fill(0.f);
-      s.store_cs(o), s.store_cs(o + F), s.store_cs(o + 2 * F), s.store_cs(o + 3 * F);
-      continue;
-    }
-    s.fill(0.f), q.fill(0.f), mx.fill(-INFINITY), mn.fill(INFINITY);
-    const float* p = msg + (int64_t)b * F + c0;
-    int k = 0;
-    // 4 independent 16-byte loads in flight per thread (bond graphs have D <= 4 almost always)
-    for (; k + 4 <= D; k += 4) {
-      Vec<V> x0, x1, x2, x3;
-      x0.load(p + (int64_t)(k + 0) * F), x1.load(p + (int64_t)(k + 1) * F);
-      x2.load(p + (int64_t)(k + 2) * F), x3.load(p + (int64_t)(k + 3) * F);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t0 < total; t0 += stride * kAggItems) {
+    int64_t v[kAggItems];
+    int c0[kAggItems], D[kAggItems];
+    const float* p[kAggItems];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s.v[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.v[i], x0.v[i]), x1.v[i]), x2.v[i]), x3.v[i]);
-        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x0.v[i], x0.v[i]));
-        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x1.v[i], x1.v[i]));
-        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x2.v[i], x2.v[i]));
-        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x3.v[i], x3.v[i]));
-        mx.v[i] = fmaxf(fmaxf(mx.v[i], x0.v[i]), fmaxf(x1.v[i], fmaxf(x2.v[i], x3.v[i])));
-        mn.v[i] = fminf(fminf(mn.v[i], x0.v[i]), fminf(x1.v[i], fminf(x2.v[i], x3.v[i])));
+    for (int u = 0; u < kAggItems; ++u) {
+      const int64_t t = t0 + u * stride;
+      D[u] = -1;                                        // -1: no item
+      if (t < total) {
+        v[u] = t / FV;
+        c0[u] = (int)(t - v[u] * FV) * V;
+        const int32_t b = __ldg(rowptr + v[u]), e = __ldg(rowptr + v[u] + 1);
+        D[u] = e - b;
+        p[u] = msg + (int64_t)b * F + c0[u];
       }
     }
-    for (; k < D; ++k) {
-      Vec<V> x;
-      x.load(p + (int64_t)k * F);
+    Vec<V> x[kAggItems][4];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s.v[i] = __fadd_rn(s.v[i], x.v[i]);
-        q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x.v[i], x.v[i]));
-        mx.v[i] = fmaxf(mx.v[i], x.v[i]);
-        mn.v[i] = fminf(mn.v[i], x.v[i]);
+    for (int u = 0; u < kAggItems; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < D[u]) x[u][j].load(p[u] + (int64_t)j * F);
+#pragma unroll
+    for (int u = 0; u < kAggItems; ++u) {
+      if (D[u] < 0) continue;
+      float* o = out + v[u] * (int64_t)ldo + c0[u];
+      Vec<V> s, q, mx, mn;
+      if (D[u] == 0) {
+        s.fill(0.f);
+        s.store_cs(o), s.store_cs(o + F), s.store_cs(o + 2 * F), s.store_cs(o + 3 * F);
+        continue;
       }
-    }
-    const float fd = (float)D;
-    Vec<V> mean, sd;
+      s.fill(0.f), q.fill(0.f), mx.fill(-INFINITY), mn.fill(INFINITY);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      mean.v[i] = __fdiv_rn(s.v[i], fd);
-      const float msq = __fdiv_rn(q.v[i], fd);
-      const float var = fmaxf(__fsub_rn(msq, __fmul_rn(mean.v[i], mean.v[i])), 0.f);
-      sd.v[i] = __fsqrt_rn(__fadd_rn(var, kAggEps));
+      for (int j = 0; j < 4; ++j)
+        if (j < D[u]) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            s.v[i] = __fadd_rn(s.v[i], x[u][j].v[i]);
+            q.v[i] = __fadd_rn(q.v[i], __fmul_rn(x[u][j].v[i], x[u][j].v[i]));
+            mx.v[i] = fmaxf(mx.v[i], x[u][j].v[i]);
+            mn.v[i] = fminf(mn.v[i], x[u][j].v[i]);
+          }
+        }
+      for (int k = 4; k < D[u]; ++k) {                  // rare: in-degree > 4
+        Vec<V> y;
+        y.load(p[u] + (int64_t)k * F);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          s.v[i] = __fadd_rn(s.v[i], y.v[i]);
+          q.v[i] = __fadd_rn(q.v[i], __fmul_rn(y.v[i], y.v[i]));
+          mx.v[i] = fmaxf(mx.v[i], y.v[i]);
+          mn.v[i] = fminf(mn.v[i], y.v[i]);
+        }
+      }
+      agg_finish<V>(s, q, mx, mn, D[u], o, F);
     }
-    mean.store_cs(o), mx.store_cs(o + F), mn.store_cs(o + 2 * F), sd.store_cs(o + 3 * F);
   }
 }
 
@@ -394,6 +423,17 @@ __global__ void segment_sum_bwd_kernel(const float* __restrict__ g, const int32_
 
 using namespace i3d;
 
+// grid = enough 256-thread CTAs for work/items, capped at what is co-resident (occupancy x SMs): one full wave
+template <typename Kern>
+static int occ_grid(Kern kern, int64_t work, int items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  int64_t need = (work + (int64_t)items * 256 - 1) / ((int64_t)items * 256);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
 #define I3D_DISPATCH_VEC(vec_ok, KERNEL, grid, block, stream, ...)          \
   do {                                                                       \
     if (vec_ok)                                                              \
@@ -456,8 +496,14 @@ int i3d_pna_aggregate_fwd(const float* msg, const int32_t* rowptr, int64_t N, in
   if (N == 0) return I3D_OK;
   const bool v4 = can_vec4({msg, out}, {F, ldo});
   const int64_t work = N * (F / (v4 ? 4 : 1));
-  I3D_DISPATCH_VEC(v4, pna_aggregate_fwd_kernel, grid_for(work, 256, 8), 256, as_stream(stream), msg, rowptr, N, F, out,
-                   ldo);
+  // 2 items per thread at >= 3 CTAs/SM: the best of the variants measured on B200 (tests/gpu_agg_bench.py)
+  cudaStream_t st = as_stream(stream);
+  if (v4)
+    launch(pna_aggregate_fwd_kernel<4, 2, 3>, occ_grid(pna_aggregate_fwd_kernel<4, 2, 3>, work, 2), 256, 0, st, msg,
+           rowptr, N, F, out, ldo);
+  else
+    launch(pna_aggregate_fwd_kernel<1, 2, 3>, occ_grid(pna_aggregate_fwd_kernel<1, 2, 3>, work, 2), 256, 0, st, msg,
+           rowptr, N, F, out, ldo);
   I3D_LAUNCHED();
   return I3D_OK;
 }

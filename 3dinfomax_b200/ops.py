@@ -185,28 +185,10 @@ def embed_sum(idx, col_off, perm, table, max_dim=0):
     return _EmbedSum.apply(idx, col_off, perm, table, int(max_dim))
 
 
-# bench.py sets PROFILE = {"fwd": [], "bwd": []} to time every aggregation launch with CUDA events on the launch
-# stream; each entry is (start_event, end_event, algorithmic_bytes) with the byte model of SURVEY.md §8d.
-PROFILE = None
-
-
-def _timed(kind, nbytes, fn):
-    if PROFILE is None:
-        return fn()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    out = fn()
-    e1.record()
-    PROFILE[kind].append((e0, e1, nbytes))
-    return out
-
-
 class _PNAAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, msg, rowptr):
-        E, F = msg.shape
-        N = rowptr.numel() - 1
-        out = _timed("fwd", 4 * F * E + 4 * E + 4 * (N + 1) + 16 * F * N, lambda: K.pna_aggregate_fwd(msg, rowptr))
+        out = K.pna_aggregate_fwd(msg, rowptr)
         ctx.save_for_backward(msg, out, rowptr)
         return out
 
@@ -215,10 +197,7 @@ class _PNAAggregate(torch.autograd.Function):
         msg, out, rowptr = ctx.saved_tensors
         if g.stride(1) != 1:
             g = g.contiguous()
-        E, F = msg.shape
-        N = rowptr.numel() - 1
-        return _timed("bwd", 32 * F * N + 8 * F * E + 4 * (N + 1),
-                      lambda: K.pna_aggregate_bwd(g, msg, out, rowptr)), None
+        return K.pna_aggregate_bwd(g, msg, out, rowptr), None
 
 
 def pna_aggregate(msg, rowptr):

@@ -23,7 +23,7 @@ from .optim import FusedAdam
 
 class SelfSupervisedTrainer:
     def __init__(self, model, model3d, loss_func, device="cuda", optimizer_params=None, lr_scheduler=None,
-                 process_group=None, graph_safe=False):
+                 process_group=None, graph_safe=False, overlap_encoders=True):
         self.device = torch.device(device)
         self.model = model.to(self.device)
         self.model3d = model3d.to(self.device)      # moved before the optimizer is built (self_supervised_trainer.py:16)
@@ -33,6 +33,10 @@ class SelfSupervisedTrainer:
         self.rank = torch.distributed.get_rank(process_group) if D.is_distributed() else 0
         self.optim_steps = 0
         self.lr_scheduler = lr_scheduler
+        # the 2-D and 3-D encoders share nothing until the loss: the 3-D one (small, latency-bound kernels) runs on
+        # its own stream, forward and backward (autograd replays a node on the stream its forward ran on), and fills
+        # the SMs the 2-D encoder's one-CTA-per-SM GEMMs leave idle.  Inside a captured step this is a forked branch.
+        self.stream3d = torch.cuda.Stream(device=self.device) if overlap_encoders else None
         self.initialize_optimizer(optimizer_params or {"lr": 8e-5}, graph_safe)
 
     def initialize_optimizer(self, optimizer_params, graph_safe=False):
@@ -52,8 +56,17 @@ class SelfSupervisedTrainer:
     def forward_pass(self, batch):
         self.prep.refresh()
         info2d, info3d, *rest = tuple(batch)
-        view2d = self.model(*info2d)
-        view3d = self.model3d(*info3d)
+        if self.stream3d is not None:
+            main = torch.cuda.current_stream(self.device)
+            self.stream3d.wait_stream(main)
+            with torch.cuda.stream(self.stream3d):
+                view3d = self.model3d(*info3d)
+            view2d = self.model(*info2d)
+            main.wait_stream(self.stream3d)
+            view3d.record_stream(main)
+        else:
+            view2d = self.model(*info2d)
+            view3d = self.model3d(*info3d)
         if self.world > 1:
             # global negative set: every rank's 3-D embeddings; the local rows sit at row_offset in column space
             b_local = view2d.shape[0]
