@@ -74,6 +74,23 @@ class FCLayer(nn.Module):
             bn = (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
         return ops.fc(segs, self.linear.weight, self.linear.bias, self.act, bn, self.training, residual)
 
+    def forward_merged(self, plan, h, agg, residual=None):
+        """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""
+        from .kernels import MergedPosttransWeights
+        W = self.linear.weight
+        # one persistent scratch per (bucket count, device): a captured CUDA graph keeps pointing at the one it was
+        # recorded with, so scratch is never re-allocated or shared between different bucket counts
+        cache = self.__dict__.setdefault("_merged", {})
+        key = (plan.n_buckets, h.shape[1], str(W.device))
+        m = cache.get(key)
+        if m is None:
+            m = cache[key] = MergedPosttransWeights(self.out_dim, h.shape[1], plan.n_buckets, W.device)
+        bn = None
+        if self.batch_norm is not None:
+            b = self.batch_norm
+            bn = (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
+        return ops.fc_post_merged(plan, m, h, agg, W, self.linear.bias, self.act, bn, self.training, residual)
+
 
 class MLP(nn.Module):
     def __init__(self, in_dim, out_dim, layers, hidden_size=None, mid_activation="relu", last_activation="none",

@@ -39,6 +39,10 @@ struct TcParams {
   int splits;   // TN: gridDim.z
   double* stats;    // optional fused BatchNorm statistics [2N] (NT only)
   int stats_act;
+  // TN over a degree plan (i3d_gemm_tn_chunked): CTA z reduces rows [tab[3z], +tab[3z+1]) of the virtual row order
+  // into the output block of bucket tab[3z+2] (C + bucket * c_bucket_stride); always atomic, caller pre-zeroes C
+  const int32_t* chunk_tab;
+  int64_t c_bucket_stride;
 };
 
 // =================================================================================================================
@@ -58,6 +62,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int n0 = blockIdx.y * BN;
   const int64_t M = p.M;
   const int N = p.N;
+  float* Cout = p.C;
+  int chunk_k0 = 0, chunk_rows = 0;
+  if (MODE == I3D_GEMM_TN && p.chunk_tab) {
+    chunk_k0 = __ldg(p.chunk_tab + 3 * blockIdx.z);
+    chunk_rows = __ldg(p.chunk_tab + 3 * blockIdx.z + 1);
+    if (chunk_rows <= 0) return;        // unused chunk of the degree plan (whole CTA, before any allocation)
+    Cout += (int64_t)__ldg(p.chunk_tab + 3 * blockIdx.z + 2) * p.c_bucket_stride;
+  }
 
   if (warp == 0) tmem_alloc(tmem_slot, L::TMEM_COLS);
   if (tid == 32) {
@@ -76,8 +88,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (MODE == I3D_GEMM_NT) {
     for (int s = 0; s < p.n_seg; ++s) total += (p.seg[s].K + TC_BK - 1) / TC_BK;
   } else {
-    kbeg = blockIdx.z * p.kchunk;
-    kend = min(p.seg[0].K, kbeg + p.kchunk);
+    kbeg = p.chunk_tab ? chunk_k0 : blockIdx.z * p.kchunk;
+    kend = min(p.seg[0].K, kbeg + (p.chunk_tab ? chunk_rows : p.kchunk));
     total = kend > kbeg ? (kend - kbeg + TC_BK - 1) / TC_BK : 0;
   }
   int cur_seg = 0, cur_k0 = (MODE == I3D_GEMM_NT) ? 0 : kbeg;
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     tc_fence_after();
   }
   const bool atomic = (MODE == I3D_GEMM_TN) && p.splits > 1;
-  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc,
+  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, Cout, p.ldc,
                   (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic,
                   MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act);
   tc_fence_before();
@@ -371,6 +383,26 @@ static int with_bn(int mode, int64_t M, int N, F&& f) {
   if (N <= 208) return f(std::integral_constant<int, 208>());
   if ((N + 207) / 208 <= (N + 255) / 256) return f(std::integral_constant<int, 208>());   // same tiles, less padding
   return f(std::integral_constant<int, 256>());
+}
+
+// dW of a degree-bucketed GEMM: C[bucket] += A[a_idx[k], :]^T B[b_idx[k], :] over the chunks of the degree plan
+int gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int64_t c_bucket_stride,
+                    const int32_t* chunk_tab, int n_chunks, cudaStream_t stream) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.seg[0] = sg;
+  p.n_seg = 1, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = nullptr, p.accumulate = 1;
+  p.kchunk = 0, p.splits = 2 /* atomic epilogue */, p.chunk_tab = chunk_tab, p.c_bucket_stride = c_bucket_stride;
+  return with_bn(I3D_GEMM_TN, M, N, [&](auto bn) {
+    constexpr int BN = decltype(bn)::value;
+    using L = TcLayout<BN>;
+    static bool configured = false;
+    if (int rc = set_smem(gemm_tc_kernel<I3D_GEMM_TN, BN>, L::BYTES, &configured)) return rc;
+    const int64_t gx = (M + TC_BM - 1) / TC_BM;
+    const int gy = (N + BN - 1) / BN;
+    launch(gemm_tc_kernel<I3D_GEMM_TN, BN>, dim3((unsigned)gx, gy, n_chunks), TC_THREADS, L::BYTES, stream, p);
+    return launched("gemm(tn chunked)");
+  });
 }
 
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,

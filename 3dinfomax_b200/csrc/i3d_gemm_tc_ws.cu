@@ -45,6 +45,11 @@ struct WsParams {
   // B split (one launch for all segments)
   const float* Bsrc[4];
   int32_t ldb[4];
+  // degree-bucketed mode (i3d_gemm_nt_bucketed): row tile t multiplies the weight block of bucket tile_bucket[t]
+  // (rows [bucket * N, bucket * N + N) of the prepared B); row_map[m] is the output row of virtual row m, -1 = padding
+  const int32_t* tile_bucket;
+  const int32_t* row_map;
+  int b_rows_total;                 // rows of the prepared B (n_buckets * N); 0 = plain mode (N rows)
 };
 
 // OCC = CTAs resident per SM.  OCC 1: deepest ring (5 stages at BN = 208).  OCC 2: two CTAs share an SM (2-3 stages
@@ -102,6 +107,13 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
   const int n0 = blockIdx.y * BN;
   const int64_t M = p.M;
   const int N = p.N;
+  int b_row0 = n0;                      // first row of this CTA's B tile inside the prepared operand
+  if (p.tile_bucket) {
+    const int bucket = __ldg(p.tile_bucket + blockIdx.x);
+    if (bucket < 0) return;             // unused tail tile of the degree plan (whole CTA, before any allocation)
+    b_row0 += bucket * N;
+  }
+  const int32_t* __restrict__ row_map = p.row_map;
 
   if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
   if (tid == 256) {
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
         a_row[i] = -1;
         a_sc[i] = 1.f;
         if (gm < M) {
-          a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : gm;
+          a_row[i] = a_idx ? (int64_t)__ldg(a_idx + gm) : ((row_map && __ldg(row_map + gm) < 0) ? -1 : gm);
           if (scale) a_sc[i] = __ldg(scale + gm);
         }
       }
@@ -202,8 +214,8 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
         if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
         const int kcol = p.kcol0[seg] + k0;
         mbar_expect_tx(&b_full[st], 2u * BN * WS_BK * 4u);
-        tma_load_2d(b_hi, &p.map_hi, kcol, n0, &b_full[st]);
-        tma_load_2d(b_lo, &p.map_lo, kcol, n0, &b_full[st]);
+        tma_load_2d(b_hi, &p.map_hi, kcol, b_row0, &b_full[st]);
+        tma_load_2d(b_lo, &p.map_lo, kcol, b_row0, &b_full[st]);
         k0 += WS_BK;
         if (k0 >= p.K[seg] && seg + 1 < p.n_seg) {
           seg += 1;
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
   }
   __syncthreads();      // every role has left the operand ring before it is reused as the output tile
   tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false,
-                                     p.stats, p.stats_act);
+                                     p.stats, p.stats_act, row_map);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -333,7 +345,8 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
     }
     configured = true;
   }
-  if (!ws_make_b_map(&p.map_hi, hi, p.N, ktot, BN) || !ws_make_b_map(&p.map_lo, lo, p.N, ktot, BN)) {
+  const int b_rows = p.b_rows_total > 0 ? p.b_rows_total : p.N;
+  if (!ws_make_b_map(&p.map_hi, hi, b_rows, ktot, BN) || !ws_make_b_map(&p.map_lo, lo, b_rows, ktot, BN)) {
     set_error("i3d_gemm(ws): cuTensorMapEncodeTiled failed");
     return I3D_ERR_CUDA;
   }
@@ -427,6 +440,30 @@ int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, 
   return I3D_OK;
 }
 
+// tile shape by output width and number of row tiles
+static int ws_dispatch(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t stream) {
+  const int64_t M = p.M;
+  const int N = p.N;
+  const int64_t gx = (M + TC_BM - 1) / TC_BM;
+  const int sms = sm_count();
+  if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
+  if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
+  if (N <= 112) return gx > sms ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
+  if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
+  if (N <= 208) {
+    // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when the row tiles alone leave
+    // half the SMs idle (node-level GEMMs: 72 row tiles at batch 512).
+    if (2 * gx <= sms) return launch_ws<112>(p, hi, lo, ktot, stream);
+    if (gx > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);          // more tiles than SMs: co-resident pairs
+    return launch_ws<208>(p, hi, lo, ktot, stream);
+  }
+  if ((N + 207) / 208 <= (N + 255) / 256) {                                  // same tile count, less padding
+    if (gx * ((N + 207) / 208) > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);
+    return launch_ws<208>(p, hi, lo, ktot, stream);
+  }
+  return launch_ws<256>(p, hi, lo, ktot, stream);
+}
+
 // NT GEMM through the warp-specialised kernel.  ws: device scratch of gemm_ws_bytes(...) for the hi/lo weight copies.
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared) {
@@ -460,24 +497,26 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
     }
     count_launch();
   }
-  const int64_t gx = (M + TC_BM - 1) / TC_BM;
-  const int sms = sm_count();
-  if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
-  if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
-  if (N <= 112) return gx > sms ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
-  if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
-  if (N <= 208) {
-    // One accumulator covers the F = 200 outputs of a PNA layer.  Split N over two CTAs when the row tiles alone leave
-    // half the SMs idle (node-level GEMMs: 72 row tiles at batch 512).
-    if (2 * gx <= sms) return launch_ws<112>(p, hi, lo, ktot, stream);
-    if (gx > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);          // more tiles than SMs: co-resident pairs
-    return launch_ws<208>(p, hi, lo, ktot, stream);
+  return ws_dispatch(p, hi, lo, ktot, stream);
+}
+
+// Degree-bucketed NT GEMM (see i3d_degree_plan / i3d_posttrans_merge): M = virtual rows (multiple of 128), B = the
+// prepared [n_buckets * N, ktot] hi/lo operands, output rows scattered through row_map.
+int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+                        const float* hi, const float* lo, int n_buckets, const int32_t* tile_bucket,
+                        const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream) {
+  WsParams p;
+  memset(&p, 0, sizeof(p));
+  int ktot = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;
+    p.lda[s] = segs[s].lda, p.K[s] = segs[s].K, p.kcol0[s] = ktot;
+    ktot += ws_kpad(segs[s].K);
   }
-  if ((N + 207) / 208 <= (N + 255) / 256) {                                  // same tile count, less padding
-    if (gx * ((N + 207) / 208) > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);
-    return launch_ws<208>(p, hi, lo, ktot, stream);
-  }
-  return launch_ws<256>(p, hi, lo, ktot, stream);
+  p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = 0;
+  p.stats = stats, p.stats_act = stats_act;
+  p.tile_bucket = tile_bucket, p.row_map = row_map, p.b_rows_total = n_buckets * N;
+  return ws_dispatch(p, const_cast<float*>(hi), const_cast<float*>(lo), ktot, stream);
 }
 
 }  // namespace i3d

@@ -150,6 +150,119 @@ __global__ void degree_scalers_kernel(const int32_t* __restrict__ rowptr, int64_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Degree plan (models/pna.py:57-68,232): the three degree scalers of a node are functions of its in-degree D only,
+// so cat[A, A*amp_D, A*att_D] W^T == A (W_id + amp_D W_amp + att_D W_att)^T.  Grouping the nodes of a batch by D lets
+// the posttrans GEMM run with K = F + 4F instead of F + 12F, one merged weight per degree bucket.  This kernel lays
+// the nodes out as "virtual rows": bucket b (= degree b) owns whole 128-row tiles, nodes keep their id order inside
+// a bucket (deterministic), unused rows are -1.
+//   perm[128*T]        virtual row -> node id or -1                     T = ceil(N/128) + NB  (static upper bound)
+//   tile_bucket[T]     bucket of each row tile, -1 for the unused tail
+//   chunk_tab[3*CH]    split-K chunks for dW: (first virtual row, rows (0 = unused), bucket); a chunk never crosses a
+//                      bucket and covers at most chunk_tiles tiles          CH = ceil(ceil(N/128)/chunk_tiles) + NB
+//   overflow[1]        set to 1 if a node has D >= NB (it is then clamped into the last bucket: results invalid)
+// One CTA: every thread owns a contiguous node range, per-bucket block scans give its first slot in every bucket.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+constexpr int kMaxBuckets = 16;
+
+__global__ void __launch_bounds__(kPlanThreads) degree_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N,
+                                                                   int NB, int32_t* __restrict__ perm,
+                                                                   int32_t* __restrict__ tile_bucket, int T,
+                                                                   int32_t* __restrict__ chunk_tab, int CH,
+                                                                   int chunk_tiles, int32_t* __restrict__ overflow) {
+  pdl_grid_sync();
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t bucket_tot[kMaxBuckets], bucket_row0[kMaxBuckets + 1], bucket_chunk0[kMaxBuckets + 1];
+  __shared__ int32_t s_over;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (N + kPlanThreads - 1) / kPlanThreads;
+  const int64_t v0 = (int64_t)tid * per, v1 = v0 + per < N ? v0 + per : N;
+  if (tid == 0) s_over = 0;
+  for (int64_t i = tid; i < (int64_t)T * 128; i += kPlanThreads) perm[i] = -1;
+  int32_t cnt[kMaxBuckets], off[kMaxBuckets];
+#pragma unroll
+  for (int b = 0; b < kMaxBuckets; ++b) cnt[b] = 0;
+  bool over = false;
+  for (int64_t v = v0; v < v1; ++v) {
+    int d = rowptr[v + 1] - rowptr[v];
+    if (d >= NB) d = NB - 1, over = true;
+#pragma unroll
+    for (int b = 0; b < kMaxBuckets; ++b) cnt[b] += (b == d);
+  }
+  __syncthreads();
+  if (over) s_over = 1;
+  // exclusive block scan of cnt[b] for every bucket
+#pragma unroll
+  for (int b = 0; b < kMaxBuckets; ++b) {
+    if (b >= NB) continue;                       // NB is uniform: the barriers below stay convergent
+    int x = cnt[b];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;                       // inclusive over warps
+    }
+    __syncthreads();
+    off[b] = x - cnt[b] + (warp > 0 ? warp_tot[warp - 1] : 0);
+    if (tid == kPlanThreads - 1) bucket_tot[b] = off[b] + cnt[b];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int row0 = 0, ch0 = 0;
+    for (int b = 0; b < NB; ++b) {
+      bucket_row0[b] = row0;
+      bucket_chunk0[b] = ch0;
+      const int tiles = (bucket_tot[b] + 127) / 128;
+      row0 += tiles * 128;
+      ch0 += (tiles + chunk_tiles - 1) / chunk_tiles;
+    }
+    bucket_row0[NB] = row0;
+    bucket_chunk0[NB] = ch0;
+    *overflow = s_over;
+  }
+  __syncthreads();
+  for (int64_t v = v0; v < v1; ++v) {
+    int d = rowptr[v + 1] - rowptr[v];
+    if (d >= NB) d = NB - 1;
+#pragma unroll
+    for (int b = 0; b < kMaxBuckets; ++b)
+      if (b == d) {
+        perm[bucket_row0[b] + off[b]] = (int32_t)v;
+        off[b] += 1;
+      }
+  }
+  for (int t = tid; t < T; t += kPlanThreads) {
+    int bk = -1;
+    for (int b = 0; b < NB; ++b)
+      if (t * 128 >= bucket_row0[b] && t * 128 < bucket_row0[b + 1]) bk = b;
+    tile_bucket[t] = bk;
+  }
+  for (int c = tid; c < CH; c += kPlanThreads) {
+    int bk = -1;
+    for (int b = 0; b < NB; ++b)
+      if (c >= bucket_chunk0[b] && c < bucket_chunk0[b + 1]) bk = b;
+    int r0 = 0, rows = 0;
+    if (bk >= 0) {
+      const int j = c - bucket_chunk0[bk];
+      r0 = bucket_row0[bk] + j * chunk_tiles * 128;
+      rows = min(chunk_tiles * 128, bucket_row0[bk + 1] - r0);
+    }
+    chunk_tab[3 * c] = r0, chunk_tab[3 * c + 1] = rows, chunk_tab[3 * c + 2] = bk < 0 ? 0 : bk;
+  }
+}
+
 }  // namespace i3d
 
 extern "C" {
@@ -180,6 +293,19 @@ int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att,
   I3D_REQUIRE(N >= 0 && rowptr && (N == 0 || (amp && att)), "invalid argument");
   if (N == 0) return I3D_OK;
   i3d::launch(i3d::degree_scalers_kernel, i3d::grid_for(N, 256), 256, 0, i3d::as_stream(stream), rowptr, N, amp, att);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_degree_plan(const int32_t* rowptr, int64_t N, int n_buckets, int chunk_tiles, int32_t* perm,
+                    int32_t* tile_bucket, int32_t* chunk_tab, int32_t* overflow, void* stream) {
+  I3D_REQUIRE(N >= 0 && N < (1ll << 30) && rowptr && perm && tile_bucket && chunk_tab && overflow, "invalid argument");
+  I3D_REQUIRE(n_buckets >= 1 && n_buckets <= i3d::kMaxBuckets && chunk_tiles >= 1, "n_buckets must be in [1, 16]");
+  const int tiles = (int)((N + 127) / 128);
+  const int T = tiles + n_buckets;
+  const int CH = (tiles + chunk_tiles - 1) / chunk_tiles + n_buckets;
+  i3d::launch(i3d::degree_plan_kernel, 1, i3d::kPlanThreads, 0, i3d::as_stream(stream), rowptr, N, n_buckets, perm,
+              tile_bucket, T, chunk_tab, CH, chunk_tiles, overflow);
   I3D_LAUNCHED();
   return I3D_OK;
 }

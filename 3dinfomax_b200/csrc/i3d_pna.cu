@@ -199,6 +199,141 @@ __global__ void __launch_bounds__(256, MINB)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Aggregation forward, bulk-copy staged ("TMA" 1-D: cp.async.bulk global -> shared, mbarrier complete_tx).
+// Messages are in CSR order, so the mailboxes of a block of consecutive nodes are ONE contiguous byte range of `msg`:
+// a single elected thread moves it with one bulk copy per block, two blocks in flight per CTA (double buffer), and
+// the 256 threads reduce out of shared memory.  Memory-level parallelism no longer costs registers (the LDG variant
+// holds 2 items x 4 rows x 16 B per thread): ~50 KB per CTA are in flight from the first microsecond, which is what
+// a ~10 us kernel needs to approach the HBM roofline.  Persistent grid (<= 2 CTAs per SM), block = kAggNodes nodes;
+// a block whose mailbox does not fit a stage (very high degrees) is reduced straight from global memory.
+// Sums run in edge order j = 0..D-1 exactly like the LDG kernel and the backward (bit-identical results).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAggNodes = 16;      // nodes per block: 16 x in-degree <= 4 x 800 B = at most 51 KB per stage at F = 200
+
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// mean | max | min | std of the D rows starting at p (row stride F floats) for one 16-byte column group
+__device__ __forceinline__ void agg_reduce_rows(const float* p, int D, int F, float* o) {
+  Vec<4> s, q, mx, mn;
+  s.fill(0.f), q.fill(0.f), mx.fill(-INFINITY), mn.fill(INFINITY);
+  for (int k = 0; k < D; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(p + (int64_t)k * F);
+    const float x[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s.v[j] = __fadd_rn(s.v[j], x[j]);
+      q.v[j] = __fadd_rn(q.v[j], __fmul_rn(x[j], x[j]));
+      mx.v[j] = fmaxf(mx.v[j], x[j]);
+      mn.v[j] = fminf(mn.v[j], x[j]);
+    }
+  }
+  agg_finish<4>(s, q, mx, mn, D, o, F);
+}
+
+__global__ void __launch_bounds__(256, 2)
+    pna_aggregate_fwd_tma_kernel(const float* __restrict__ msg, const int32_t* __restrict__ rowptr, int64_t N, int F,
+                                 float* __restrict__ out, int ldo, int stage_rows) {
+  pdl_grid_sync();
+  extern __shared__ __align__(128) uint8_t agg_smem[];
+  float* stage0 = reinterpret_cast<float*>(agg_smem);
+  const size_t stage_floats = (size_t)stage_rows * F;
+  uint64_t* full = reinterpret_cast<uint64_t*>(agg_smem + 2 * stage_floats * sizeof(float));   // [2]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(full + 2);                                        // [2][kAggNodes + 1]
+  int32_t* s_direct = s_rp + 2 * (kAggNodes + 1);                                              // [2]
+  const int tid = threadIdx.x;
+  const int FV = F >> 2;
+  const int64_t n_blocks = (N + kAggNodes - 1) / kAggNodes;
+  const int64_t G = gridDim.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(agg_smem_u32(&full[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(agg_smem_u32(&full[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // thread 0: request mailbox rows [b, e) into stage st (one bulk copy, completion counted in bytes on full[st])
+  auto issue = [&](int32_t b, int32_t e, int st) {
+    const int rows = e - b;
+    const uint32_t bar = agg_smem_u32(&full[st]);
+    if (rows > 0 && rows <= stage_rows) {
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)F * 4u;
+      s_direct[st] = 0;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       agg_smem_u32(stage0 + (size_t)st * stage_floats)),
+                   "l"(msg + (int64_t)b * F), "r"(bytes), "r"(bar)
+                   : "memory");
+    } else {
+      s_direct[st] = 1;                 // empty block, or too many rows for a stage: reduce from global memory
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+  };
+  auto block_rows = [&](int64_t blk, int32_t* b, int32_t* e) {
+    const int64_t v0 = blk * kAggNodes;
+    const int64_t v1 = v0 + kAggNodes < N ? v0 + kAggNodes : N;
+    *b = __ldg(rowptr + v0), *e = __ldg(rowptr + v1);
+  };
+
+  if (tid == 0) {                       // both stages are requested before any reduction starts
+    int32_t b0, e0, b1, e1;
+    const int64_t blk0 = blockIdx.x, blk1 = blk0 + G;
+    if (blk0 < n_blocks) block_rows(blk0, &b0, &e0);
+    if (blk1 < n_blocks) block_rows(blk1, &b1, &e1);
+    if (blk0 < n_blocks) issue(b0, e0, 0);
+    if (blk1 < n_blocks) issue(b1, e1, 1);
+  }
+  int it = 0;
+  for (int64_t blk = blockIdx.x; blk < n_blocks; blk += G, ++it) {
+    const int st = it & 1;
+    const int64_t v0 = blk * kAggNodes;
+    const int nodes = (int)(v0 + kAggNodes < N ? kAggNodes : N - v0);
+    // rows of the block that will reuse this stage: loaded now, consumed after the reduction (no stall on the way)
+    const int64_t nxt = blk + 2 * G;
+    int32_t nb = 0, ne = 0;
+    if (tid == 0 && nxt < n_blocks) block_rows(nxt, &nb, &ne);
+    if (tid <= nodes) s_rp[st * (kAggNodes + 1) + tid] = __ldg(rowptr + v0 + tid);
+    {   // wait for the bulk copy of this stage (the phase parity flips on every reuse of the stage)
+      const uint32_t bar = agg_smem_u32(&full[st]);
+      const uint32_t parity = (uint32_t)((it >> 1) & 1);
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "AGG_WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra AGG_DONE_%=;\n"
+          "bra AGG_WAIT_%=;\n"
+          "AGG_DONE_%=:\n"
+          "}\n" ::"r"(bar),
+          "r"(parity)
+          : "memory");
+    }
+    __syncthreads();                    // s_rp / s_direct of this stage visible to every thread
+    const int32_t* rp = s_rp + st * (kAggNodes + 1);
+    const int32_t row0 = rp[0];
+    const bool direct = s_direct[st] != 0;
+    const float* staged = stage0 + (size_t)st * stage_floats;
+    for (int idx = tid; idx < nodes * FV; idx += 256) {
+      const int i = idx / FV;
+      const int c0 = (idx - i * FV) << 2;
+      const int32_t b = rp[i];
+      const int D = rp[i + 1] - b;
+      float* o = out + (v0 + i) * (int64_t)ldo + c0;
+      if (D <= 0) {
+        Vec<4> z;
+        z.fill(0.f);
+        z.store_cs(o), z.store_cs(o + F), z.store_cs(o + 2 * F), z.store_cs(o + 3 * F);
+      } else if (!direct) {
+        agg_reduce_rows(staged + (size_t)(b - row0) * F + c0, D, F, o);
+      } else {
+        agg_reduce_rows(msg + (int64_t)b * F + c0, D, F, o);
+      }
+    }
+    __syncthreads();                    // every thread is done with this stage before it is refilled
+    if (tid == 0 && nxt < n_blocks) issue(nb, ne, st);
+  }
+}
+
 // backward: g = [g_mean | g_max | g_min | g_std] already folded over the degree scalers by the GEMM backward
 template <int V>
 __global__ void __launch_bounds__(256)
@@ -259,6 +394,85 @@ __global__ void __launch_bounds__(256)
       }
       d.store_cs(dp + (int64_t)k * F);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Degree-merged posttrans weights (models/pna.py:57-68,207-211,232).  For a node of in-degree D the posttrans input
+// is cat[h, A, A*a_D, A*t_D] with a_D = (float)ln(D+1), t_D = (float)(1/ln(D+1)) (A = [mean|max|min|std], 4F wide), so
+//   cat[...] W^T = h Wh^T + A (W_id + a_D W_amp + t_D W_att)^T
+// One merged weight per degree bucket turns the K = 13F GEMM into K = 5F.  merge writes the tf32 hi/lo operands the
+// bucketed NT kernel streams by TMA, for the forward ([NB*Fout, kpad(F)+kpad(4F)], K-major) and for dx = dy Wm
+// ([NB*5F, kpad(Fout)], i.e. Wm^T); unmerge folds the per-bucket weight gradients back onto W's three column blocks.
+// Pad columns of the scratch are never written (the caller zero-fills the buffers once).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bucket_scalers(int b, float* a, float* t) {
+  if (b <= 0) {
+    *a = 0.f, *t = 0.f;                 // D = 0: the aggregation row is all zeros (DGL zero fill), any finite factor works
+  } else {
+    const double l = log((double)b + 1.0);
+    *a = (float)l, *t = (float)(1.0 / l);
+  }
+}
+
+__device__ __forceinline__ int kpad32(int k) { return (k + 31) / 32 * 32; }
+__device__ __forceinline__ float to_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256)
+    posttrans_merge_kernel(const float* __restrict__ W, int ldw, int Fout, int F, int NB, float* __restrict__ fwd_hi,
+                           float* __restrict__ fwd_lo, float* __restrict__ bwd_hi, float* __restrict__ bwd_lo) {
+  pdl_grid_sync();
+  const int F4 = 4 * F, K5 = 5 * F;
+  const int ktf = kpad32(F) + kpad32(F4), ktb = kpad32(Fout);
+  const int64_t total = (int64_t)NB * Fout * K5;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % K5);
+    const int n = (int)((t / K5) % Fout);
+    const int b = (int)(t / ((int64_t)K5 * Fout));
+    const float* w = W + (int64_t)n * ldw;
+    float m;
+    int col;
+    if (j < F) {
+      m = __ldg(w + j);
+      col = j;
+    } else {
+      float a, tt;
+      bucket_scalers(b, &a, &tt);
+      const int c = j - F;
+      m = __ldg(w + F + c) + a * __ldg(w + F + F4 + c) + tt * __ldg(w + F + 2 * F4 + c);
+      col = kpad32(F) + c;
+    }
+    const float h = to_tf32_rna(m);
+    const float l = m - h;
+    const int64_t of = ((int64_t)b * Fout + n) * ktf + col;
+    fwd_hi[of] = h, fwd_lo[of] = l;
+    const int64_t ob = ((int64_t)b * K5 + j) * ktb + n;
+    bwd_hi[ob] = h, bwd_lo[ob] = l;
+  }
+}
+
+// dW[n, F + c] += sum_b dWb[b,n,c];  dW[n, 5F + c] += sum_b a_b dWb[b,n,c];  dW[n, 9F + c] += sum_b t_b dWb[b,n,c]
+__global__ void __launch_bounds__(256)
+    posttrans_unmerge_kernel(const float* __restrict__ dWb, int NB, int Fout, int F, float* __restrict__ dW, int ldw) {
+  pdl_grid_sync();
+  const int F4 = 4 * F;
+  const int64_t total = (int64_t)Fout * F4;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % F4);
+    const int n = (int)(t / F4);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < NB; ++b) {
+      float a, tt;
+      bucket_scalers(b, &a, &tt);
+      const float g = __ldg(dWb + ((int64_t)b * Fout + n) * F4 + c);
+      s0 += g, s1 += a * g, s2 += tt * g;
+    }
+    float* d = dW + (int64_t)n * ldw + F + c;
+    d[0] += s0, d[F4] += s1, d[2 * F4] += s2;
   }
 }
 
@@ -496,8 +710,32 @@ int i3d_pna_aggregate_fwd(const float* msg, const int32_t* rowptr, int64_t N, in
   if (N == 0) return I3D_OK;
   const bool v4 = can_vec4({msg, out}, {F, ldo});
   const int64_t work = N * (F / (v4 ? 4 : 1));
-  // 2 items per thread at >= 3 CTAs/SM: the best of the variants measured on B200 (tests/gpu_agg_bench.py)
   cudaStream_t st = as_stream(stream);
+  // default: bulk-copy (TMA 1-D) staged kernel; I3D_AGG_FWD=ldg selects the register-staged variant
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("I3D_AGG_FWD");
+    variant = (e && e[0] == 'l') ? 0 : 1;
+  }
+  if (variant == 1 && v4 && N >= kAggNodes) {
+    // two stages per CTA, two CTAs per SM: a stage holds a block of kAggNodes nodes of in-degree <= 4 (64 rows),
+    // fewer if F is wide; blocks with more rows take the in-kernel global-memory path
+    int stage_rows = 4 * kAggNodes;
+    while (stage_rows > 8 && (size_t)2 * stage_rows * F * 4 > 100 * 1024) stage_rows -= 8;
+    const size_t smem = (size_t)2 * stage_rows * F * 4 + 2 * sizeof(uint64_t) + (2 * (kAggNodes + 1) + 2) * sizeof(int32_t);
+    static size_t configured = 0;
+    if (smem > configured) {
+      I3D_CUDA(cudaFuncSetAttribute(pna_aggregate_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const int64_t n_blocks = (N + kAggNodes - 1) / kAggNodes;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    launch(pna_aggregate_fwd_tma_kernel, (int)(n_blocks < cap ? n_blocks : cap), 256, smem, st, msg, rowptr, N, F, out,
+           ldo, stage_rows);
+    I3D_LAUNCHED();
+    return I3D_OK;
+  }
+  // 2 items per thread at >= 3 CTAs/SM: the best of the LDG variants measured on B200 (tests/gpu_agg_bench.py)
   if (v4)
     launch(pna_aggregate_fwd_kernel<4, 2, 3>, occ_grid(pna_aggregate_fwd_kernel<4, 2, 3>, work, 2), 256, 0, st, msg,
            rowptr, N, F, out, ldo);
@@ -576,6 +814,26 @@ int i3d_segment_sum_bwd(const float* g, const int32_t* rowptr, const int32_t* ro
   const int64_t work = E * (F / (v4 ? 4 : 1));
   I3D_DISPATCH_VEC(v4, segment_sum_bwd_kernel, grid_for(work, 256), 256, as_stream(stream), g, rowptr, rowid, E, F,
                    mean, gx);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_posttrans_merge(const float* W, int ldw, int Fout, int F, int n_buckets, float* fwd_hi, float* fwd_lo,
+                        float* bwd_hi, float* bwd_lo, void* stream) {
+  I3D_REQUIRE(W && Fout > 0 && F > 0 && ldw >= 13 * F && n_buckets >= 1 && n_buckets <= 16 && fwd_hi && fwd_lo &&
+                  bwd_hi && bwd_lo, "invalid argument");
+  const int64_t work = (int64_t)n_buckets * Fout * 5 * F;
+  launch(posttrans_merge_kernel, grid_for(work, 256), 256, 0, as_stream(stream), W, ldw, Fout, F, n_buckets, fwd_hi,
+         fwd_lo, bwd_hi, bwd_lo);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_posttrans_unmerge(const float* dWb, int n_buckets, int Fout, int F, float* dW, int ldw, void* stream) {
+  I3D_REQUIRE(dWb && dW && Fout > 0 && F > 0 && ldw >= 13 * F && n_buckets >= 1 && n_buckets <= 16,
+              "invalid argument");
+  launch(posttrans_unmerge_kernel, grid_for((int64_t)Fout * 4 * F, 256), 256, 0, as_stream(stream), dWb, n_buckets,
+         Fout, F, dW, ldw);
   I3D_LAUNCHED();
   return I3D_OK;
 }

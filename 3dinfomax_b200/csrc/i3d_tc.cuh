@@ -153,7 +153,13 @@ template <int BN, int NTHR = TC_THREADS>
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N, int64_t m0,
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
                                             int accumulate, bool atomic, double* __restrict__ stats = nullptr,
-                                            int stats_act = 0) {
+                                            int stats_act = 0, const int32_t* __restrict__ row_map = nullptr) {
+  // row_map (degree-bucketed GEMMs): tile row r is written to output row row_map[m0 + r]; negative = padding row that
+  // is neither stored nor counted in the statistics
+  __shared__ int32_t s_row[TC_BM];
+  if (row_map) {
+    for (int r = threadIdx.x; r < TC_BM; r += blockDim.x) s_row[r] = (m0 + r < M) ? __ldg(row_map + m0 + r) : -1;
+  }
   constexpr int LDT = BN + 4;               // row stride (floats): 16-byte aligned, conflict-free for per-row STS.128
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
@@ -183,6 +189,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       const float b = bias ? __ldg(bias + n0 + c) : 0.f;
       double s1 = 0.0, s2 = 0.0;
       for (int r = 0; r < rows; ++r) {
+        if (row_map && s_row[r] < 0) continue;
         const double h = (double)act_apply(ctile[r * LDT + c] + b, stats_act);
         s1 += h;
         s2 += h * h;
@@ -198,8 +205,13 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
     const int64_t gm = m0 + r;
     const int gn = n0 + c;
     if (gm >= M || gn >= N) continue;
+    int64_t gm_out = gm;
+    if (row_map) {
+      gm_out = s_row[r];
+      if (gm_out < 0) continue;
+    }
     float4 v = *reinterpret_cast<const float4*>(ctile + r * LDT + c);
-    float* out = C + gm * ldc + gn;
+    float* out = C + gm_out * ldc + gn;
     if (vec) {
       if (bias) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gn));

@@ -12,6 +12,8 @@ The reference feeds ``PNA.forward`` / ``Net3D.forward`` a batched ``dgl.DGLGraph
 ``GraphStructure`` is what replaces DGL's per-call degree bucketing (models/pna.py:206): a destination-sorted,
 edge-id-stable int32 CSR built ON THE DEVICE once per batch and cached on the graph object.
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -20,7 +22,11 @@ from . import kernels as K
 class GraphBatch:
     """Batched graph: node ids of graph k are offset by the cumulative node counts (dgl.batch semantics)."""
 
-    def __init__(self, src, dst, batch_num_nodes, batch_num_edges=None, ndata=None, edata=None, num_nodes=None):
+    def __init__(self, src, dst, batch_num_nodes, batch_num_edges=None, ndata=None, edata=None, num_nodes=None,
+                 max_in_degree=None):
+        # max_in_degree: optional HOST integer known at collate time; lets the 2-D encoder group nodes by in-degree
+        # (degree-merged posttrans weights) without a device->host sync.  None: the generic 13F-wide path is used.
+        self.max_in_degree = None if max_in_degree is None else int(max_in_degree)
         self._src = src
         self._dst = dst
         self._bnn = batch_num_nodes
@@ -61,7 +67,8 @@ class GraphBatch:
     def to(self, device, non_blocking=False):
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         g = GraphBatch(mv(self._src), mv(self._dst), mv(self._bnn), mv(self._bne),
-                       {k: mv(v) for k, v in self.ndata.items()}, {k: mv(v) for k, v in self.edata.items()}, self._n)
+                       {k: mv(v) for k, v in self.ndata.items()}, {k: mv(v) for k, v in self.edata.items()}, self._n,
+                       self.max_in_degree)
         if self._i3d_struct is not None and torch.device(device) == self.device:
             g._i3d_struct = self._i3d_struct
         return g
@@ -69,14 +76,17 @@ class GraphBatch:
     def pin_memory(self):
         pm = lambda t: None if t is None else t.pin_memory()
         return GraphBatch(pm(self._src), pm(self._dst), pm(self._bnn), pm(self._bne),
-                          {k: pm(v) for k, v in self.ndata.items()}, {k: pm(v) for k, v in self.edata.items()}, self._n)
+                          {k: pm(v) for k, v in self.ndata.items()}, {k: pm(v) for k, v in self.edata.items()}, self._n,
+                          self.max_in_degree)
 
 
 def batch_from_numpy(b, device="cpu", pin=False):
     """numpy batch dict (synthetic.make_batch layout) -> (graph2d, graph3d) GraphBatch pair on ``device``."""
     t = lambda a: torch.from_numpy(a)
+    import numpy as np
+    max_deg = int(np.bincount(b["dst"]).max()) if len(b["dst"]) else 0
     g2 = GraphBatch(t(b["src"]), t(b["dst"]), t(b["num_nodes"]), t(b["num_edges"]),
-                    {"feat": t(b["x_atom"])}, {"feat": t(b["e_attr"])})
+                    {"feat": t(b["x_atom"])}, {"feat": t(b["e_attr"])}, max_in_degree=max_deg)
     g3 = GraphBatch(t(b["src3"]), t(b["dst3"]), t(b["num_nodes3"]), t(b["num_edges3"]), {}, {"d": t(b["d3"])})
     if pin:
         g2, g3 = g2.pin_memory(), g3.pin_memory()
@@ -93,9 +103,12 @@ class GraphStructure:
     out_rowptr[N+1], out_pos[E]                      out-edges of node v as POSITIONS into the CSR edge order
     graph_ptr[B+1]                                   node range of each molecule
     amp[N], att[N]                                   ln(D+1), 1/ln(D+1) degree scalers (fp32)
+    plan                                             kernels.DegreePlan (nodes grouped by in-degree) or None
     """
 
-    def __init__(self, src, dst, batch_num_nodes, num_nodes, need_out=True, need_scalers=True):
+    MAX_PLAN_BUCKETS = 16
+
+    def __init__(self, src, dst, batch_num_nodes, num_nodes, need_out=True, need_scalers=True, max_in_degree=None):
         if not src.is_cuda:
             raise RuntimeError("graph tensors must live on a CUDA device: the 3dinfomax_b200 path has no CPU fallback")
         src = src.contiguous()
@@ -116,6 +129,31 @@ class GraphStructure:
             self.amp, self.att = K.degree_scalers(self.rowptr)
         else:
             self.amp = self.att = None
+        self.plan = None
+        use_plan = os.environ.get("I3D_POSTTRANS", "merged") != "generic"
+        min_nodes = int(os.environ.get("I3D_PLAN_MIN_NODES", "256"))     # tiny batches: padding to whole tiles per
+        if (need_scalers and use_plan and max_in_degree is not None and self.N >= min_nodes      # bucket outweighs K
+                and int(max_in_degree) + 1 <= self.MAX_PLAN_BUCKETS):
+            self.plan = K.DegreePlan(self.rowptr, int(max_in_degree) + 1)
+
+    def check_plan(self):
+        """Host check (device->host sync) that no node exceeded the ``max_in_degree`` the plan was built for."""
+        if self.plan is not None and int(self.plan.overflow.item()) != 0:
+            raise RuntimeError("a node's in-degree exceeds the graph's max_in_degree hint (%d): the degree-merged "
+                               "posttrans results are invalid" % (self.plan.n_buckets - 1))
+
+
+def annotate_max_in_degree(graph):
+    """Set ``graph.max_in_degree`` from the edge list (one device->host sync if the graph lives on the GPU).  Call it
+    at collate time for graphs that do not come from ``batch_from_numpy`` (e.g. a DGLGraph) to enable the degree plan."""
+    _, dst = graph.edges()
+    n = graph.number_of_nodes()
+    md = int(torch.bincount(dst.long(), minlength=max(n, 1)).max().item()) if dst.numel() else 0
+    try:
+        graph.max_in_degree = md
+    except AttributeError:
+        pass
+    return md
 
 
 def graph_structure(graph, need_out=True, need_scalers=True):
@@ -124,7 +162,10 @@ def graph_structure(graph, need_out=True, need_scalers=True):
     if st is not None and (st.out_pos is not None or not need_out) and (st.amp is not None or not need_scalers):
         return st
     src, dst = graph.edges()
-    st = GraphStructure(src, dst, graph.batch_num_nodes(), graph.number_of_nodes(), need_out, need_scalers)
+    st = GraphStructure(src, dst, graph.batch_num_nodes(), graph.number_of_nodes(), need_out, need_scalers,
+                        getattr(graph, "max_in_degree", None))
+    if st.plan is not None and os.environ.get("I3D_CHECK_PLAN", "0") == "1":
+        st.check_plan()
     try:
         graph._i3d_struct = st
     except AttributeError:

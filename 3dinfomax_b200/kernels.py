@@ -87,6 +87,86 @@ def degree_scalers(rowptr):
     return amp, att
 
 
+class DegreePlan:
+    """Device arrays of i3d_degree_plan (include/i3d.h): nodes grouped by in-degree into whole 128-row tiles."""
+    CHUNK_TILES = 4        # split-K chunk of the weight-gradient GEMM: at most 512 virtual rows
+
+    def __init__(self, rowptr, n_buckets):
+        N = rowptr.numel() - 1
+        dev = rowptr.device
+        tiles = (N + 127) // 128
+        self.n_buckets = int(n_buckets)
+        self.N = N
+        self.T = tiles + self.n_buckets
+        self.Mv = 128 * self.T
+        self.CH = (tiles + self.CHUNK_TILES - 1) // self.CHUNK_TILES + self.n_buckets
+        self.perm = torch.empty(self.Mv, dtype=torch.int32, device=dev)
+        self.tile_bucket = torch.empty(self.T, dtype=torch.int32, device=dev)
+        self.chunk_tab = torch.empty(3 * self.CH, dtype=torch.int32, device=dev)
+        self.overflow = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(_L().i3d_degree_plan(_vec(rowptr, torch.int32, "rowptr"), N, self.n_buckets, self.CHUNK_TILES,
+                                        _p(self.perm), _p(self.tile_bucket), _p(self.chunk_tab), _p(self.overflow),
+                                        _s()), "i3d_degree_plan")
+
+
+def kpad32(k):
+    return (k + 31) // 32 * 32
+
+
+class MergedPosttransWeights:
+    """Persistent tf32 hi/lo scratch of the degree-merged posttrans weights of ONE layer (i3d_posttrans_merge)."""
+
+    def __init__(self, Fout, F, n_buckets, device):
+        self.Fout, self.F, self.n_buckets = int(Fout), int(F), int(n_buckets)
+        self.ktf = kpad32(F) + kpad32(4 * F)
+        self.ktb = kpad32(Fout)
+        z = lambda r, c: torch.zeros(r, c, dtype=torch.float32, device=device)     # pad columns stay zero for good
+        self.fwd_hi, self.fwd_lo = z(n_buckets * Fout, self.ktf), z(n_buckets * Fout, self.ktf)
+        self.bwd_hi, self.bwd_lo = z(n_buckets * 5 * F, self.ktb), z(n_buckets * 5 * F, self.ktb)
+
+    def refresh(self, W):
+        pw, ldw = _mat(W, "W")
+        if W.shape != (self.Fout, 13 * self.F):
+            raise ValueError("posttrans weight must be [Fout, 13F]")
+        _lib.check(_L().i3d_posttrans_merge(pw, ldw, self.Fout, self.F, self.n_buckets, _p(self.fwd_hi),
+                                            _p(self.fwd_lo), _p(self.bwd_hi), _p(self.bwd_lo), _s()),
+                   "i3d_posttrans_merge")
+
+
+def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None):
+    """C[plan.perm[m], :] = bias + sum_s A_s[a_idx_s[m] or m, :] @ B[bucket(m)]^T over the plan's virtual rows."""
+    pc, ldc = _mat(C, "C")
+    arr = _seg_array(segs, need_b=False)
+    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
+    _lib.check(_L().i3d_gemm_nt_bucketed(plan.Mv, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                                         _p(b_hi), _p(b_lo), plan.n_buckets, _p(plan.tile_bucket), _p(plan.perm),
+                                         _p(stats), 0 if stats_act is None else stats_act, _s()),
+               "i3d_gemm_nt_bucketed")
+    return C if stats_act is None else (C, stats)
+
+
+def gemm_tn_chunked(plan, A, B, C):
+    """C[b] += sum_{virtual rows m of bucket b} A[perm[m], :]^T B[perm[m], :];  C [n_buckets, A.cols, B.cols] zeroed."""
+    pa, lda = _mat(A, "A")
+    pb, ldb = _mat(B, "B")
+    M, N = A.shape[1], B.shape[1]
+    if C.shape != (plan.n_buckets, M, N) or not C.is_contiguous():
+        raise ValueError("C must be a contiguous [n_buckets, %d, %d] tensor" % (M, N))
+    seg = (_lib.gemm_seg * 1)()
+    seg[0].A, seg[0].B, seg[0].a_idx, seg[0].b_idx = pa, pb, _p(plan.perm), _p(plan.perm)
+    seg[0].scale = None
+    seg[0].K, seg[0].lda, seg[0].ldb = plan.Mv, int(lda), int(ldb)
+    _lib.check(_L().i3d_gemm_tn_chunked(M, N, seg, _p(C), N, M * N, _p(plan.chunk_tab), plan.CH, _s()),
+               "i3d_gemm_tn_chunked")
+    return C
+
+
+def posttrans_unmerge(dWb, dW, F):
+    nb, Fout, F4 = dWb.shape
+    pd, ldw = _mat(dW, "dW")
+    _lib.check(_L().i3d_posttrans_unmerge(_p(dWb), nb, Fout, F, pd, ldw, _s()), "i3d_posttrans_unmerge")
+
+
 # ------------------------------------------------------------------------------------ embedding
 def embed_sum_fwd(idx, col_off, perm, table):
     _vec(idx, torch.int64, "idx"), _vec(col_off, torch.int32, "col_off"), _vec(perm, torch.int32, "perm")

@@ -100,6 +100,14 @@ class _FC(torch.autograd.Function):
         else:
             dY = dO
             db = K.colsum(dO) if need_b else None
+        sums_cache = {}
+
+        def row_sums(i, s):
+            """[R, Fout]: for every row r of a gathered segment's source, the sum of dY over the output rows reading it"""
+            if i not in sums_cache:
+                sums_cache[i] = K.segment_sum_fwd(dY, s.inv_rowptr, s.inv_idx)
+            return sums_cache[i]
+
         # weight gradient, one column block per segment: dW[:, off:off+k] = dY^T (scale * gather(x))
         dW = None
         if ctx.needs_input_grad[1]:
@@ -108,10 +116,16 @@ class _FC(torch.autograd.Function):
             direct = getattr(ctx.w_param, "_i3d_grad_view", None)
             acc = direct if direct is not None else torch.zeros_like(W)
             off = 0
-            for s, x in zip(segs, xs):
+            for i, (s, x) in enumerate(zip(segs, xs)):
                 k = x.shape[1]
-                K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
-                       acc[:, off:off + k], accumulate=True)
+                if s.idx is not None and x.shape[0] < M:
+                    # dY^T x[idx] == (sum of the dY rows that read each x row)^T x: reduce over the gather first (the
+                    # same row sums feed dx below), then a GEMM over the R source rows instead of the M gathered ones
+                    K.gemm(K.TN, Fout, k, [{"A": row_sums(i, s), "B": x, "K": x.shape[0]}], acc[:, off:off + k],
+                           accumulate=True)
+                else:
+                    K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
+                           acc[:, off:off + k], accumulate=True)
                 off += k
             dW = None if direct is not None else acc
         # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
@@ -134,10 +148,7 @@ class _FC(torch.autograd.Function):
             via_nt = R >= 256 and Fout % 4 == 0 and k % 4 == 0
             nn = []
             for (_i, s, _x, o) in members:
-                if s.idx is None:
-                    a = dY
-                else:
-                    a = K.segment_sum_fwd(dY, s.inv_rowptr, s.inv_idx)
+                a = dY if s.idx is None else row_sums(_i, s)
                 nn.append({"A": a, "K": Fout, "scale": s.scale, "_o": o})
             ready = None
             if via_nt and prep is not None and K.gemm_nt_prepared_ok(R, k, nn):
@@ -164,6 +175,86 @@ def fc(segs, W, b, act, bn=None, training=True, residual=None):
         gamma, beta, rm, rv, nbt, mom, eps = bn
         cfg = FCConfig(segs, act, True, training, rm, rv, nbt, mom, eps)
     return _FC.apply(cfg, W, b, gamma, beta, residual, *[s.x for s in segs])
+
+
+class _FCPostMerged(torch.autograd.Function):
+    """FCLayer over cat[h, agg, agg*amp_D, agg*att_D] (models/pna.py:207-211,232) evaluated as [h | agg] @ Wm_D^T with
+    one merged weight per in-degree bucket (kernels.DegreePlan / MergedPosttransWeights): K = 5F instead of 13F in the
+    forward, in dx and in dW.  Same tail as ``_FC`` (activation -> BatchNorm, residual)."""
+
+    @staticmethod
+    def forward(ctx, cfg, plan, merged, W, b, gamma, beta, residual, h, agg):
+        N, F = h.shape
+        Fout = W.shape[0]
+        if agg.shape != (N, 4 * F) or W.shape[1] != 13 * F:
+            raise ValueError("merged posttrans expects agg [N,4F] and a [Fout,13F] weight")
+        merged.refresh(W)
+        Y = torch.empty(N, Fout, dtype=torch.float32, device=W.device)
+        segs = [{"A": h, "K": F, "a_idx": plan.perm}, {"A": agg, "K": 4 * F, "a_idx": plan.perm}]
+        sums = save = None
+        if cfg.has_bn and cfg.training:
+            _, sums = K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo, stats_act=cfg.act)
+        else:
+            K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo)
+        if cfg.has_bn:
+            O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
+                                 cfg.momentum, cfg.eps, cfg.training, residual)
+        else:
+            O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
+            if residual is not None:
+                O = K.add(O, residual)
+        ctx.cfg, ctx.plan, ctx.merged, ctx.w_param = cfg, plan, merged, W
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(W, Y, save, gamma, h, agg)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        cfg, plan, merged = ctx.cfg, ctx.plan, ctx.merged
+        W, Y, save, gamma, h, agg = ctx.saved_tensors
+        N, F = h.shape
+        Fout = W.shape[0]
+        if dO.dim() != 2 or dO.stride(1) != 1:
+            dO = dO.contiguous()
+        need_b = ctx.needs_input_grad[4]
+        dgamma = dbeta = None
+        if cfg.has_bn:
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save)
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b)
+        elif cfg.act != 0:
+            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
+        else:
+            dY = dO
+            db = K.colsum(dO) if need_b else None
+        dW = None
+        if ctx.needs_input_grad[3]:
+            direct = getattr(ctx.w_param, "_i3d_grad_view", None)
+            acc = direct if direct is not None else torch.zeros_like(W)
+            K.gemm(K.TN, Fout, F, [{"A": dY, "B": h, "K": N}], acc[:, :F], accumulate=True)
+            dWb = torch.zeros(plan.n_buckets, Fout, 4 * F, dtype=torch.float32, device=W.device)
+            K.gemm_tn_chunked(plan, dY, agg, dWb)
+            K.posttrans_unmerge(dWb, acc, F)
+            dW = None if direct is not None else acc
+        dh = dagg = None
+        if ctx.needs_input_grad[8] or ctx.needs_input_grad[9]:
+            # d[h | agg] = dY Wm_D, rows scattered back to node order by the epilogue
+            buf = torch.empty(N, 5 * F, dtype=torch.float32, device=W.device)
+            K.gemm_nt_bucketed(plan, 5 * F, [{"A": dY, "K": Fout, "a_idx": plan.perm}], buf, None, merged.bwd_hi,
+                               merged.bwd_lo)
+            dh, dagg = buf[:, :F], buf[:, F:]
+        dres = dO if (ctx.has_res and ctx.needs_input_grad[7]) else None
+        return None, None, None, dW, db, dgamma, dbeta, dres, dh, dagg
+
+
+def fc_post_merged(plan, merged, h, agg, W, b, act, bn=None, training=True, residual=None):
+    """Degree-merged posttrans FCLayer; arguments as ``fc``."""
+    if bn is None:
+        cfg = FCConfig(None, act, False, training)
+        gamma = beta = None
+    else:
+        gamma, beta, rm, rv, nbt, mom, eps = bn
+        cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps)
+    return _FCPostMerged.apply(cfg, plan, merged, W, b, gamma, beta, residual, h, agg)
 
 
 class _EmbedSum(torch.autograd.Function):

@@ -94,8 +94,17 @@ class PNALayer(nn.Module):
         # models/pna.py:206,221-235
         agg = ops.pna_aggregate(msg, st.rowptr)
         # models/pna.py:207-211 — cat[h, agg, agg*amp, agg*att] -> posttrans -> + h
+        res = h if self.residual else None
+        if st.plan is not None:
+            # the degree scalers depend on the in-degree only: nodes grouped by degree share one merged weight
+            # W_id + amp_D W_amp + att_D W_att, and the first posttrans FC runs with K = 5F instead of 13F
+            fcs = self.posttrans.fully_connected
+            x = fcs[0].forward_merged(st.plan, h, agg, res if len(fcs) == 1 else None)
+            for i in range(1, len(fcs)):
+                x = fcs[i](x, res if i == len(fcs) - 1 else None)
+            return x, msg
         return self.posttrans([ops.Seg(h), ops.Seg(agg), ops.Seg(agg, scale=st.amp), ops.Seg(agg, scale=st.att)],
-                              residual=h if self.residual else None), msg
+                              residual=res), msg
 
 
 class PNAGNN(nn.Module):

@@ -110,6 +110,7 @@ class CapturedStep:
             "bnn3": example_g3.batch_num_nodes().clone(), "d3": example_g3.edata["d"].clone(),
         }
         self.n2, self.n3 = example_g2.number_of_nodes(), example_g3.number_of_nodes()
+        self.max_in_degree = getattr(example_g2, "max_in_degree", None)   # sizes the degree plan inside the graph
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph = None
         side = torch.cuda.Stream(device=dev)
@@ -130,7 +131,8 @@ class CapturedStep:
 
     def _graphs(self):
         s = self.static
-        g2 = GraphBatch(s["src"], s["dst"], s["bnn"], None, {"feat": s["x"]}, {"feat": s["e"]}, self.n2)
+        g2 = GraphBatch(s["src"], s["dst"], s["bnn"], None, {"feat": s["x"]}, {"feat": s["e"]}, self.n2,
+                        self.max_in_degree)
         g3 = GraphBatch(s["src3"], s["dst3"], s["bnn3"], None, {}, {"d": s["d3"]}, self.n3)
         return g2, g3
 
@@ -145,6 +147,11 @@ class CapturedStep:
     def load(self, g2, g3):
         """Copy a new batch of IDENTICAL shape into the static buffers (async on the current stream)."""
         s = self.static
+        if self.max_in_degree is not None:
+            md = getattr(g2, "max_in_degree", None)
+            if md is None or md > self.max_in_degree:
+                raise ValueError("captured step was built for max_in_degree <= %d, the new batch has %r"
+                                 % (self.max_in_degree, md))
         pairs = [("src", g2.edges()[0]), ("dst", g2.edges()[1]), ("bnn", g2.batch_num_nodes()),
                  ("x", g2.ndata["feat"]), ("e", g2.edata["feat"]), ("src3", g3.edges()[0]), ("dst3", g3.edges()[1]),
                  ("bnn3", g3.batch_num_nodes()), ("d3", g3.edata["d"])]

@@ -193,7 +193,7 @@ def run_b200(args):
     def fresh(pair):          # forward consumes the graph object (ndata['feat'] is overwritten, as in the reference)
         g2, g3 = pair
         a = i3d.GraphBatch(*g2.edges(), g2.batch_num_nodes(), None, {"feat": g2.ndata["feat"]},
-                           {"feat": g2.edata["feat"]}, g2.number_of_nodes())
+                           {"feat": g2.edata["feat"]}, g2.number_of_nodes(), g2.max_in_degree)
         b = i3d.GraphBatch(*g3.edges(), g3.batch_num_nodes(), None, {}, {"d": g3.edata["d"]}, g3.number_of_nodes())
         return a, b
 

@@ -72,6 +72,21 @@ int i3d_segment_ptr(const int64_t* counts, int64_t B, int32_t* ptr, void* stream
  * scale_amplification / scale_attenuation with avg_d["log"]=1.0  [models/pna.py:61-68,153]          */
 int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att, void* stream);
 
+/* Degree plan: the reference evaluates the posttrans FC on cat[h, A, A*amp_D, A*att_D] (13F columns,
+ * models/pna.py:207,232); amp_D / att_D depend on the in-degree D only (models/pna.py:57-68), so nodes grouped by D
+ * can share one merged weight W_id + amp_D W_amp + att_D W_att and the GEMM runs with K = 5F.  (DGL itself buckets
+ * nodes by degree inside update_all; here the buckets feed the tensor-core tiles instead of ~25 launches each.)
+ * Bucket b = nodes of in-degree b, b < n_buckets <= 16; every bucket owns whole 128-row tiles of a "virtual row"
+ * order, node ids ascending inside a bucket.  With tiles = ceil(N/128):
+ *   perm[128 * (tiles + n_buckets)]       virtual row -> node id, -1 for padding rows
+ *   tile_bucket[tiles + n_buckets]        bucket of each row tile, -1 for unused tail tiles
+ *   chunk_tab[3 * (ceil(tiles / chunk_tiles) + n_buckets)]   split-K chunks for the weight gradient:
+ *                                         (first virtual row, rows, bucket); rows = 0 for unused chunks
+ *   overflow[1]                           1 if some node has D >= n_buckets (clamped into the last bucket: the
+ *                                         caller must not use the results)                                      */
+int i3d_degree_plan(const int32_t* rowptr, int64_t N, int n_buckets, int chunk_tiles, int32_t* perm,
+                    int32_t* tile_bucket, int32_t* chunk_tab, int32_t* overflow, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * AtomEncoder / BondEncoder  [commons/mol_encoder.py:34-42,65-73; models/pna.py:162-163]
  *   out[r,:] = sum_c table[col_off[c] + idx[perm ? perm[r] : r, c], :]
@@ -145,6 +160,28 @@ int i3d_gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_til
 int i3d_gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                          int accumulate, const void* ws, double* col_stats, int stats_act, void* stream);
+
+/* Degree-bucketed GEMMs over an i3d_degree_plan (posttrans FC of PNALayer, models/pna.py:207-211, and its backward).
+ *   i3d_posttrans_merge    W [Fout, 13F] (ld = ldw) -> tf32 hi/lo operands of the merged weights
+ *                          Wm_b = [Wh | W_id + a_b W_amp + t_b W_att], a_b = (float)ln(b+1), t_b = (float)(1/ln(b+1)):
+ *                          fwd_hi/lo [n_buckets*Fout, kpad(F)+kpad(4F)]  (B of y = [h|A] Wm_b^T; kpad = round up to 32)
+ *                          bwd_hi/lo [n_buckets*5F, kpad(Fout)]          (B of d[h|A] = dy Wm_b)
+ *                          pad columns are not written: zero-fill the buffers once when allocating them.
+ *   i3d_gemm_nt_bucketed   C[row_map[m], n] = bias[n] + sum_s sum_k A_s[a_idx_s[m] or m, k] * B[bucket(m)*N + n, k]
+ *                          for the Mv = 128*(tiles+n_buckets) virtual rows; rows with row_map[m] < 0 are skipped (and
+ *                          excluded from col_stats).  Segments: unscaled, K % 4 == 0; a_idx entries < 0 read zeros.
+ *   i3d_gemm_tn_chunked    C[bucket] (+)= sum over the chunk's virtual rows k of A[a_idx[k], :]^T B[b_idx[k], :]
+ *                          (C + bucket * c_bucket_stride; vector atomics: zero C before the call); seg->K = Mv.
+ *   i3d_posttrans_unmerge  dW[:, F:5F] += sum_b dWb[b]; dW[:, 5F:9F] += sum_b a_b dWb[b]; dW[:, 9F:13F] += sum_b t_b dWb[b]
+ *                          with dWb [n_buckets, Fout, 4F] dense.                                                  */
+int i3d_posttrans_merge(const float* W, int ldw, int Fout, int F, int n_buckets, float* fwd_hi, float* fwd_lo,
+                        float* bwd_hi, float* bwd_lo, void* stream);
+int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+                         const float* b_hi, const float* b_lo, int n_buckets, const int32_t* tile_bucket,
+                         const int32_t* row_map, double* col_stats, int stats_act, void* stream);
+int i3d_gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg* seg, float* C, int ldc, int64_t c_bucket_stride,
+                        const int32_t* chunk_tab, int n_chunks, void* stream);
+int i3d_posttrans_unmerge(const float* dWb, int n_buckets, int Fout, int F, float* dW, int ldw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]

@@ -605,6 +605,144 @@ def case_fc():
     return out
 
 
+# ------------------------------------------------------------------------------- degree-merged posttrans
+def _degree_plan_ref(rowptr, NB, CT):
+    """numpy restatement of i3d_degree_plan (include/i3d.h): nodes grouped by in-degree into whole 128-row tiles."""
+    deg = np.diff(np.asarray(rowptr, dtype=np.int64))
+    N = len(deg)
+    over = int((deg >= NB).any())
+    d = np.minimum(deg, NB - 1)
+    tiles = (N + 127) // 128
+    T, CH = tiles + NB, (tiles + CT - 1) // CT + NB
+    perm = -np.ones(T * 128, dtype=np.int32)
+    tile_bucket = -np.ones(T, dtype=np.int32)
+    chunk = np.zeros(3 * CH, dtype=np.int32)
+    row0 = ch0 = 0
+    for b in range(NB):
+        nodes = np.nonzero(d == b)[0]
+        perm[row0:row0 + len(nodes)] = nodes
+        tb = (len(nodes) + 127) // 128
+        tile_bucket[row0 // 128:row0 // 128 + tb] = b
+        for j in range((tb + CT - 1) // CT):
+            r0 = row0 + j * CT * 128
+            chunk[3 * ch0:3 * ch0 + 3] = (r0, min(CT * 128, row0 + tb * 128 - r0), b)
+            ch0 += 1
+        row0 += tb * 128
+    return perm, tile_bucket, chunk, over
+
+
+def case_degree_plan():
+    out = []
+    cases = {"bond_like": (3000, 6100, None), "tiny": (5, 9, None), "one_bucket": (300, 0, 1),
+             "overflow": (400, 3000, 4)}
+    for tag, (n, e, nb) in cases.items():
+        src, dst = random_graph(3, n, e) if e else (torch.zeros(0, dtype=torch.long),) * 2
+        rowptr, _, _ = O.csr_reference(src.numpy(), dst.numpy(), n)
+        NB = nb if nb is not None else int(np.diff(rowptr).max()) + 1
+        plan = K.DegreePlan(torch.from_numpy(np.asarray(rowptr, dtype=np.int32)).to(DEV), NB)
+        perm, tb, ch, over = _degree_plan_ref(rowptr, NB, K.DegreePlan.CHUNK_TILES)
+        out += [("degree_plan/%s/perm" % tag, exact(plan.perm, perm), 0),
+                ("degree_plan/%s/tile_bucket" % tag, exact(plan.tile_bucket, tb), 0),
+                ("degree_plan/%s/chunk_tab" % tag, exact(plan.chunk_tab, ch), 0),
+                ("degree_plan/%s/overflow" % tag, abs(int(plan.overflow.item()) - over), 0)]
+    b = syn.make_batch(5, 512)
+    rowptr, _, _ = O.csr_reference(b["src"], b["dst"], len(b["x_atom"]))
+    NB = int(np.diff(rowptr).max()) + 1
+    plan = K.DegreePlan(torch.from_numpy(np.asarray(rowptr, dtype=np.int32)).to(DEV), NB)
+    perm, tb, ch, over = _degree_plan_ref(rowptr, NB, K.DegreePlan.CHUNK_TILES)
+    out += [("degree_plan/qm9_b512/perm", exact(plan.perm, perm), 0),
+            ("degree_plan/qm9_b512/chunk_tab", exact(plan.chunk_tab, ch), 0),
+            ("degree_plan/qm9_b512/every_node_once",
+             exact(np.sort(plan.perm.cpu().numpy()[plan.perm.cpu().numpy() >= 0]), np.arange(len(b["x_atom"]))), 0)]
+    return out
+
+
+def _fc_merged_once(tag, n, e, Fd, seed, act, train, tol_f, tol_g):
+    """FCLayer over cat[h, A, A*amp, A*att] (models/pna.py:207-211,232) through the degree-merged weights against the
+    concatenation evaluated in fp64 torch."""
+    g = gen(seed)
+    src, dst = random_graph(seed + 1, n, e, isolated=True)
+    rowptr, _, _ = O.csr_reference(src.numpy(), dst.numpy(), n)
+    md = int(np.diff(rowptr).max())
+    st = _with_env({"I3D_PLAN_MIN_NODES": "0"}, i3d.GraphStructure, src.to(DEV), dst.to(DEV), torch.tensor([n]), n,
+                   max_in_degree=md)
+    assert st.plan is not None, "max in-degree %d does not fit the degree plan" % md
+    amp, att = st.amp.cpu().double(), st.att.cpu().double()
+    mk = lambda *shape, s=1.0: (torch.randn(*shape, generator=g) * s)
+    A, h2 = mk(n, 4 * Fd), mk(n, Fd)
+    W2, b2 = mk(Fd, 13 * Fd, s=0.05), mk(Fd, s=0.1)
+    gam, bet = 1 + 0.1 * mk(Fd), 0.1 * mk(Fd)
+    rm, rv = 0.1 * mk(Fd), 1 + 0.1 * mk(Fd).abs()
+    gout = mk(n, Fd)
+    leaf = lambda t: t.double().requires_grad_(True)
+    A64, h64, W64, b64, g64, bt64 = leaf(A), leaf(h2), leaf(W2), leaf(b2), leaf(gam), leaf(bet)
+    x = torch.cat([h64, A64, A64 * amp[:, None], A64 * att[:, None]], -1)
+    y = F.linear(x, W64, b64)
+    y = torch.relu(y) if act == "relu" else y
+    rm64, rv64 = rm.double().clone(), rv.double().clone()
+    ref = F.batch_norm(y, rm64, rv64, g64, bt64, train, 0.9, 1e-5) + h64
+    ref.backward(gout.double())
+    d = lambda t: t.detach().float().to(DEV).requires_grad_(True)
+    Ad, hd, Wd, bd, gd, btd = d(A), d(h2), d(W2), d(b2), d(gam), d(bet)
+    rmd, rvd = rm.to(DEV).clone(), rv.to(DEV).clone()
+    bn = (gd, btd, rmd, rvd, torch.zeros((), dtype=torch.long, device=DEV), 0.9, 1e-5)
+    merged = K.MergedPosttransWeights(Fd, Fd, st.plan.n_buckets, DEV)
+    got = ops.fc_post_merged(st.plan, merged, hd, Ad, Wd, bd, K.ACT[act], bn, train, residual=hd)
+    got.backward(gout.to(DEV))
+    st.check_plan()
+    out = [("%s/fwd" % tag, rel(got, ref), tol_f), ("%s/dA" % tag, rel(Ad.grad, A64.grad), tol_g),
+           ("%s/dh" % tag, rel(hd.grad, h64.grad), tol_g), ("%s/dW" % tag, rel(Wd.grad, W64.grad), tol_g),
+           # under train-mode BN without activation db is mathematically 0: measure against the column sums of |dO|
+           ("%s/db" % tag, float((bd.grad.cpu().double() - b64.grad).abs().max() / gout.abs().sum(0).max()), tol_g),
+           ("%s/dgamma" % tag, rel(gd.grad, g64.grad), tol_g), ("%s/dbeta" % tag, rel(btd.grad, bt64.grad), tol_g)]
+    if train:
+        # the batch variance inherits ~2x the relative error of the 3xTF32 GEMM output it is computed from
+        out += [("%s/running_mean" % tag, rel(rmd, rm64), 1e-5), ("%s/running_var" % tag, rel(rvd, rv64), 5e-5)]
+    # the generic 13F-wide path on the same inputs (same kernels family, different association): both within tolerance
+    Ae, he, We, be_, ge, bte = d(A), d(h2), d(W2), d(b2), d(gam), d(bet)
+    bn2 = (ge, bte, rm.to(DEV).clone(), rv.to(DEV).clone(), torch.zeros((), dtype=torch.long, device=DEV), 0.9, 1e-5)
+    gen_out = ops.fc([ops.Seg(he), ops.Seg(Ae), ops.Seg(Ae, scale=st.amp), ops.Seg(Ae, scale=st.att)], We, be_,
+                     K.ACT[act], bn2, train, residual=he)
+    out.append(("%s/generic_path_fwd" % tag, rel(gen_out, ref), tol_f))
+    return out
+
+
+def case_fc_merged():
+    out = []
+    # db under train-mode BN is mathematically zero (bias feeds a BatchNorm): compared at a looser, absolute-ish level
+    out += _fc_merged_once("fc_merged/small_train", 300, 700, 40, 50, "none", True, 2e-5, 5e-5)
+    out += _fc_merged_once("fc_merged/small_eval_relu", 300, 700, 40, 52, "relu", False, 2e-5, 5e-5)
+    out += _fc_merged_once("fc_merged/pna_width_train", 9400, 19500, 200, 54, "none", True, 3e-5, 1e-4)
+    return out
+
+
+def _with_env(env, fn, *a, **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn(*a, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def case_golden_merged():
+    """the golden vectors of the reference's own modules with the degree-merged posttrans path forced on (the
+    8-molecule cases are below the node threshold at which it switches on by itself)"""
+    res = _with_env({"I3D_PLAN_MIN_NODES": "0", "I3D_CHECK_PLAN": "1"}, case_golden, "qm9_b8")
+    res += _with_env({"I3D_PLAN_MIN_NODES": "0", "I3D_CHECK_PLAN": "1"}, case_golden, "qmugs_b6_c3")
+    return [(l.replace("golden/", "golden_merged/"), e, t) for l, e, t in res]
+
+
+def case_train_steps_merged():
+    res = _with_env({"I3D_PLAN_MIN_NODES": "0"}, case_train_steps, 16, 2, False, 23)
+    res += _with_env({"I3D_PLAN_MIN_NODES": "0"}, case_train_steps, 16, 2, True, 23)
+    return [(l.replace("train", "train_merged", 1), e, t) for l, e, t in res]
+
+
 # ------------------------------------------------------------------------------------------ whole models
 def _models(s2, s3, trained=True):
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
@@ -763,5 +901,6 @@ def case_full_size_properties():
 from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
-             case_ntxent, case_adam, case_fc, case_golden, case_golden_qmugs, case_train_steps,
-             case_train_steps_captured, case_full_size_properties, case_sharded_equals_full]
+             case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
+             case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
+             case_full_size_properties, case_sharded_equals_full]

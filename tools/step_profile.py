@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""In-situ per-kernel GPU time of the pre-training step (warm caches, real launch order) via torch.profiler (CUPTI).
+
+    python tools/step_profile.py [--batch 512] [--steps 5] [--mode eager|graph] > gpurun_out/step_profile.txt
+
+ncu serialises launches and flushes caches before each one, so its per-launch times overstate kernels whose inputs
+are L2-resident in the real step; this table is what the step actually spends.  Not a bench: no number printed here
+is a throughput claim.
+"""
+import argparse
+import importlib
+import os
+import re
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--mode", default="eager", choices=["eager", "graph"])
+    args = ap.parse_args()
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    i3d = importlib.import_module("3dinfomax_b200")
+    cfg = importlib.import_module("3dinfomax_b200.configs")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(123)
+    pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
+    graph = args.mode == "graph"
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), dev, {"lr": 8e-5}, graph_safe=graph)
+    batches = [i3d.batch_from_numpy(i3d.synthetic.make_batch(1000 + i, args.batch), dev) for i in range(2)]
+
+    def fresh(pair):
+        g2, g3 = pair
+        a = i3d.GraphBatch(*g2.edges(), g2.batch_num_nodes(), None, {"feat": g2.ndata["feat"]},
+                           {"feat": g2.edata["feat"]}, g2.number_of_nodes(), g2.max_in_degree)
+        b = i3d.GraphBatch(*g3.edges(), g3.batch_num_nodes(), None, {}, {"d": g3.edata["d"]}, g3.number_of_nodes())
+        return a, b
+
+    caps = [i3d.CapturedStep(tr, *fresh(p), warmup=2) for p in batches] if graph else None
+
+    def step(i):
+        if caps is not None:
+            return caps[i % 2].run()
+        g2, g3 = fresh(batches[i % 2])
+        return tr.process_batch(([g2], [g3]))[0]
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for i in range(args.steps):
+            step(i)
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0, 0.0])
+    t_min, t_max = None, None
+    for ev in prof.events():
+        if str(getattr(ev, "device_type", "")).endswith("CUDA") and ev.device_time_total > 0:
+            name = re.sub(r"\(.*$", "", ev.name)[:100]
+            agg[name][0] += 1
+            agg[name][1] += ev.device_time_total
+            tr_ = ev.time_range
+            t_min = tr_.start if t_min is None else min(t_min, tr_.start)
+            t_max = tr_.end if t_max is None else max(t_max, tr_.end)
+    total = sum(v[1] for v in agg.values())
+    span = (t_max - t_min) if t_min is not None else 0.0
+    print("torch.profiler (CUPTI), %s mode, batch %d, %d steps: sum of kernel time %.1f us/step, GPU span %.1f us/step"
+          % (args.mode, args.batch, args.steps, total / args.steps, span / args.steps))
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%6.2f%% %6.1f x/step %8.1f us  %9.1f us/step  %s" % (100 * us / total, n / args.steps, us / n,
+                                                                     us / args.steps, name))
+
+
+if __name__ == "__main__":
+    main()
