@@ -335,28 +335,37 @@ int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, 
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared);
 int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-                        const float* hi, const float* lo, int n_buckets, const int32_t* tile_bucket,
+                        const float* hi, const float* lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
                         const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream);
 int gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int64_t c_bucket_stride,
                     const int32_t* chunk_tab, int n_chunks, cudaStream_t stream);
 bool gemm_ws_available();
+int gemm_ws_debug_read(unsigned long long* out);
 }  // namespace i3d
 
+extern "C" int i3d_gemm_debug_counters(unsigned long long* out16) {
+  I3D_REQUIRE(out16 != nullptr, "out16 is null");
+  return gemm_ws_debug_read(out16);
+}
+
 extern "C" int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
-                                    const float* bias, const float* b_hi, const float* b_lo, int n_buckets,
-                                    const int32_t* tile_bucket, const int32_t* row_map, double* col_stats,
-                                    int stats_act, void* stream) {
+                                    const float* bias, const float* b_hi, const float* b_lo, int b_pitch,
+                                    int n_buckets, const int32_t* tile_bucket, const int32_t* row_map,
+                                    double* col_stats, int stats_act, void* stream) {
   I3D_REQUIRE(Mv > 0 && (Mv % 128) == 0 && N >= 16 && (N & 3) == 0 && n_seg >= 1 && n_seg <= 4 && segs && C &&
                   ldc >= N && b_hi && b_lo && n_buckets >= 1 && n_buckets <= 16 && tile_bucket && row_map,
               "invalid argument");
   I3D_REQUIRE(gemm_ws_available(), "cuTensorMapEncodeTiled is not available (needs a CUDA 12 driver)");
+  int ktot = 0;
+  for (int s = 0; s < n_seg; ++s) ktot += (segs[s].K + 31) / 32 * 32;
+  I3D_REQUIRE(b_pitch >= ktot && (b_pitch & 3) == 0, "b_pitch must cover the padded K extent and be a multiple of 4");
   for (int s = 0; s < n_seg; ++s)
     I3D_REQUIRE(segs[s].K > 0 && (segs[s].K & 3) == 0 && (segs[s].lda & 3) == 0 && segs[s].A && !segs[s].b_idx &&
                     !segs[s].scale && (reinterpret_cast<uintptr_t>(segs[s].A) & 15u) == 0,
                 "segments must be 16-byte aligned, unscaled, with K a multiple of 4");
   if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
-  return gemm_ws_nt_bucketed(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, n_buckets, tile_bucket, row_map, col_stats,
-                             stats_act, as_stream(stream));
+  return gemm_ws_nt_bucketed(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, b_pitch, n_buckets, tile_bucket, row_map,
+                             col_stats, stats_act, as_stream(stream));
 }
 
 extern "C" int i3d_gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg* seg, float* C, int ldc,

@@ -17,6 +17,8 @@
 // at least 4 deep to keep the tensor pipe busy (ncu: 39 % tensor-active with the 2-stage kernel this one replaces).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "i3d_tc.cuh"
@@ -26,6 +28,29 @@ namespace i3d {
 constexpr int WS_BK = 16;                 // floats per k-block = one SWIZZLE_64B row
 constexpr int WS_STAGER_THREADS = 256;    // warps 0-7
 constexpr int WS_THREADS = 320;           // + TMA warp + MMA warp
+#ifndef I3D_WS_EXP
+#define I3D_WS_EXP 0      // timing experiments only (results are wrong): 1 no proxy fence, 2 no A loads, 3 no A stores
+#endif
+#ifndef I3D_WS_DUAL_ACC
+#define I3D_WS_DUAL_ACC 0     // measured: no gain (55.7 vs 55.6 us on the K = 1000 posttrans GEMM), costs 2x TMEM columns
+#endif
+#ifndef I3D_WS_PREFETCH
+#define I3D_WS_PREFETCH 4
+#endif
+constexpr int WS_PREFETCH = I3D_WS_PREFETCH;   // k-blocks of A held in registers per stager thread
+
+// Optional cycle accounting of the pipeline roles (build with -DI3D_WS_DEBUG; tools/gemm_bench.py --debug): CTA (0,0)
+// adds the clock64() cycles each role spends blocked on each barrier.  [0] kernel total, [1] MMA waits a_full,
+// [2] MMA waits b_full, [3] MMA issue, [4] TMA producer waits mma_done, [5] stager warp 0 waits mma_done,
+// [6] stager warp 0 total main loop, [7] epilogue, [8] launches
+__device__ unsigned long long g_ws_dbg[16];
+#ifdef I3D_WS_DEBUG
+#define WS_DBG_T0() const long long dbg_t0__ = clock64()
+#define WS_DBG_ADD(slot) if (dbg_on) atomicAdd(&g_ws_dbg[slot], (unsigned long long)(clock64() - dbg_t0__))
+#else
+#define WS_DBG_T0()
+#define WS_DBG_ADD(slot)
+#endif
 
 struct WsParams {
   CUtensorMap map_hi, map_lo;       // [N rows, Kpad_total cols] fp32, box = [BN rows x 16 cols], SWIZZLE_64B
@@ -50,6 +75,7 @@ struct WsParams {
   const int32_t* tile_bucket;
   const int32_t* row_map;
   int b_rows_total;                 // rows of the prepared B (n_buckets * N); 0 = plain mode (N rows)
+  int b_pitch;                      // row pitch (floats) of the prepared B; 0 = the padded K extent
 };
 
 // OCC = CTAs resident per SM.  OCC 1: deepest ring (5 stages at BN = 208).  OCC 2: two CTAs share an SM (2-3 stages
@@ -66,7 +92,13 @@ struct WsLayout {
   static constexpr int CTILE_BYTES = TC_BM * (BN + 4) * 4;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES > CTILE_BYTES ? STAGES * STAGE_BYTES : CTILE_BYTES;
   static constexpr size_t BYTES = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // Optional second accumulator (-DI3D_WS_DUAL_ACC=1): hi*hi goes to the first, the two cross terms (lo*hi, hi*lo) to
+  // the second, the epilogue adds them.  Written to test whether the ~160 cycles per 128 x N x 8 tf32 instruction seen
+  // with the I3D_WS_DEBUG counters (same for N = 112 and 208) come from the accumulate dependency: they do not — two
+  // independent chains run at the same pace, so the default stays one accumulator.
+  static constexpr bool DUAL = (I3D_WS_DUAL_ACC != 0) && (2 * ACC_COLS * OCC <= 512);
+  static constexpr int TMEM_COLS = DUAL ? 2 * ACC_COLS : ACC_COLS;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -93,6 +125,7 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
   pdl_grid_sync();
   using L = WsLayout<BN, OCC>;
   constexpr int S = L::STAGES;
+  constexpr int PF = WS_PREFETCH;
   extern __shared__ uint8_t smem_raw[];
   float* tiles = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tiles) + L::RING_BYTES);
@@ -114,6 +147,10 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
     b_row0 += bucket * N;
   }
   const int32_t* __restrict__ row_map = p.row_map;
+#ifdef I3D_WS_DEBUG
+  const bool dbg_on = blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  const long long dbg_kernel_t0 = clock64();
+#endif
 
   if (warp == 9) tmem_alloc(tmem_slot, L::TMEM_COLS);
   if (tid == 256) {
@@ -164,7 +201,9 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#if I3D_WS_EXP != 2
         if (a_row[i] >= 0 && kc < K) v = __ldg(reinterpret_cast<const float4*>(A + a_row[i] * lda + kc));
+#endif
         va[i] = v;
         vs[i] = a_sc[i];
       }
@@ -180,27 +219,47 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
       const int use = it / S;
       float* a_hi = tiles + (size_t)st * L::STAGE;
       float* a_lo = a_hi + L::A_TILE;
-      if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+      if (use > 0) {
+        WS_DBG_T0();
+        mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+#ifdef I3D_WS_DEBUG
+        if (warp == 0) { WS_DBG_ADD(5); }
+#endif
+      }
       const int j = tid & 3;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         float4 v = va[i];
         const float sc = vs[i];
         v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+#if I3D_WS_EXP != 3
         split_store4(a_hi, a_lo, sw64_off((tid >> 2) + 64 * i, j), v);
+#endif
       }
+#if I3D_WS_EXP != 1
       fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
-      if (it + 2 < total) prefetch(va, vs);      // refill with the k-block two iterations ahead
+#endif
+      if (it + PF < total) prefetch(va, vs);     // refill with the k-block PF iterations ahead
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[st]);
     };
-    float4 va0[2], va1[2];
-    float vs0[2], vs1[2];
-    if (total > 0) prefetch(va0, vs0);
-    if (total > 1) prefetch(va1, vs1);
-    for (int it = 0; it < total; it += 2) {
-      body(it, va0, vs0);
-      if (it + 1 < total) body(it + 1, va1, vs1);
+    // PF k-blocks of A are in flight per thread (registers): the stagers are a latency chain LDG -> STS, and with one
+    // CTA per SM only PF x 8 KB per SM are outstanding (ncu: long_scoreboard is the top stall of this kernel)
+    float4 va[PF][2];
+    float vs[PF][2];
+#pragma unroll
+    for (int q = 0; q < PF; ++q)
+      if (total > q) prefetch(va[q], vs[q]);
+    {
+      WS_DBG_T0();
+      for (int it = 0; it < total; it += PF) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q)
+          if (it + q < total) body(it + q, va[q], vs[q]);
+      }
+#ifdef I3D_WS_DEBUG
+      if (warp == 0) { WS_DBG_ADD(6); }
+#endif
     }
   } else if (warp == 8) {
     // ======================================= B producer (TMA) ================================================
@@ -211,7 +270,11 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
         const int use = it / S;
         float* b_hi = tiles + (size_t)st * L::STAGE + 2 * L::A_TILE;
         float* b_lo = b_hi + L::B_TILE;
-        if (use > 0) mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+        if (use > 0) {
+          WS_DBG_T0();
+          mbar_wait(&mma_done[st], (uint32_t)((use - 1) & 1));
+          WS_DBG_ADD(4);
+        }
         const int kcol = p.kcol0[seg] + k0;
         mbar_expect_tx(&b_full[st], 2u * BN * WS_BK * 4u);
         tma_load_2d(b_hi, &p.map_hi, kcol, b_row0, &b_full[st]);
@@ -234,19 +297,36 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
         float* a_lo = a_hi + L::A_TILE;
         float* b_hi = a_lo + L::A_TILE;
         float* b_lo = b_hi + L::B_TILE;
-        mbar_wait(&a_full[st], par);
-        mbar_wait(&b_full[st], par);
+        {
+          WS_DBG_T0();
+          mbar_wait(&a_full[st], par);
+          WS_DBG_ADD(1);
+        }
+        {
+          WS_DBG_T0();
+          mbar_wait(&b_full[st], par);
+          WS_DBG_ADD(2);
+        }
+        WS_DBG_T0();
         tc_fence_after();
         const uint64_t dah = make_smem_desc_sw64(smem_u32(a_hi)), dal = make_smem_desc_sw64(smem_u32(a_lo));
         const uint64_t dbh = make_smem_desc_sw64(smem_u32(b_hi)), dbl = make_smem_desc_sw64(smem_u32(b_lo));
 #pragma unroll
         for (int ks = 0; ks < WS_BK / 8; ++ks) {
           const uint64_t koff = (uint64_t)(ks * 32 >> 4);      // 8 tf32 = 32 bytes along K inside the 64-byte row
-          umma_tf32(tmem, dah + koff, dbh + koff, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem, dal + koff, dbh + koff, idesc, 1u);
-          umma_tf32(tmem, dah + koff, dbl + koff, idesc, 1u);
+          const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+          if constexpr (L::DUAL) {
+            umma_tf32(tmem, dah + koff, dbh + koff, idesc, acc);
+            umma_tf32(tmem + L::ACC_COLS, dal + koff, dbh + koff, idesc, acc);
+            umma_tf32(tmem + L::ACC_COLS, dah + koff, dbl + koff, idesc, 1u);
+          } else {
+            umma_tf32(tmem, dah + koff, dbh + koff, idesc, acc);
+            umma_tf32(tmem, dal + koff, dbh + koff, idesc, 1u);
+            umma_tf32(tmem, dah + koff, dbl + koff, idesc, 1u);
+          }
         }
         umma_commit(&mma_done[st]);
+        WS_DBG_ADD(3);
       }
       if (total > 0) umma_commit(acc_done);
     }
@@ -258,11 +338,21 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
     tc_fence_after();
   }
   __syncthreads();      // every role has left the operand ring before it is reused as the output tile
+#ifdef I3D_WS_DEBUG
+  const long long dbg_epi_t0 = clock64();
+#endif
   tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false,
-                                     p.stats, p.stats_act, row_map);
+                                     p.stats, p.stats_act, row_map, L::DUAL ? tmem + L::ACC_COLS : 0xffffffffu);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, L::TMEM_COLS);
+#ifdef I3D_WS_DEBUG
+  if (dbg_on && warp == 0) {
+    atomicAdd(&g_ws_dbg[0], (unsigned long long)(clock64() - dbg_kernel_t0));
+    atomicAdd(&g_ws_dbg[7], (unsigned long long)(clock64() - dbg_epi_t0));
+    atomicAdd(&g_ws_dbg[8], 1ull);
+  }
+#endif
 }
 
 // hi[n, kcol0_s + c] = tf32(B_s[n, c]),  lo = B_s - hi  for c < K_s;  zeros for K_s <= c < Kpad_s  (blockIdx.y = s)
@@ -312,11 +402,19 @@ static WsEncodeTiledFn ws_encode_tiled() {
 
 bool gemm_ws_available() { return ws_encode_tiled() != nullptr; }
 
-static bool ws_make_b_map(CUtensorMap* map, float* base, int N, int ktot, int bn) {
+// copies the 16 debug counters to `out` and clears them (all zero unless built with -DI3D_WS_DEBUG)
+int gemm_ws_debug_read(unsigned long long* out) {
+  if (cudaMemcpyFromSymbol(out, g_ws_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return I3D_ERR_CUDA;
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyToSymbol(g_ws_dbg, z, sizeof(z)) != cudaSuccess) return I3D_ERR_CUDA;
+  return I3D_OK;
+}
+
+static bool ws_make_b_map(CUtensorMap* map, float* base, int N, int ktot, int bn, int pitch = 0) {
   WsEncodeTiledFn enc = ws_encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
-  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+  const cuuint64_t strides[1] = {(cuuint64_t)(pitch > 0 ? pitch : ktot) * 4};
   const cuuint32_t box[2] = {(cuuint32_t)WS_BK, (cuuint32_t)bn};
   const cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -346,7 +444,8 @@ static int launch_ws(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t s
     configured = true;
   }
   const int b_rows = p.b_rows_total > 0 ? p.b_rows_total : p.N;
-  if (!ws_make_b_map(&p.map_hi, hi, b_rows, ktot, BN) || !ws_make_b_map(&p.map_lo, lo, b_rows, ktot, BN)) {
+  if (!ws_make_b_map(&p.map_hi, hi, b_rows, ktot, BN, p.b_pitch) ||
+      !ws_make_b_map(&p.map_lo, lo, b_rows, ktot, BN, p.b_pitch)) {
     set_error("i3d_gemm(ws): cuTensorMapEncodeTiled failed");
     return I3D_ERR_CUDA;
   }
@@ -446,6 +545,17 @@ static int ws_dispatch(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t
   const int N = p.N;
   const int64_t gx = (M + TC_BM - 1) / TC_BM;
   const int sms = sm_count();
+  // tuning override for tools/gemm_bench.py: I3D_WS_FORCE="<BN>,<OCC>" (only shapes with N <= 208)
+  static int force_bn = -1, force_occ = 1;
+  if (force_bn < 0) {
+    const char* e = getenv("I3D_WS_FORCE");
+    force_bn = 0;
+    if (e && sscanf(e, "%d,%d", &force_bn, &force_occ) < 1) force_bn = 0;
+  }
+  if (force_bn > 0 && N > 64 && N <= 208) {
+    if (force_bn == 112) return force_occ == 2 ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
+    if (force_bn == 208) return force_occ == 2 ? launch_ws<208, 2>(p, hi, lo, ktot, stream) : launch_ws<208>(p, hi, lo, ktot, stream);
+  }
   if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
   if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
   if (N <= 112) return gx > sms ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
@@ -503,7 +613,7 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
 // Degree-bucketed NT GEMM (see i3d_degree_plan / i3d_posttrans_merge): M = virtual rows (multiple of 128), B = the
 // prepared [n_buckets * N, ktot] hi/lo operands, output rows scattered through row_map.
 int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-                        const float* hi, const float* lo, int n_buckets, const int32_t* tile_bucket,
+                        const float* hi, const float* lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
                         const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream) {
   WsParams p;
   memset(&p, 0, sizeof(p));
@@ -515,7 +625,7 @@ int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, f
   }
   p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = 0;
   p.stats = stats, p.stats_act = stats_act;
-  p.tile_bucket = tile_bucket, p.row_map = row_map, p.b_rows_total = n_buckets * N;
+  p.tile_bucket = tile_bucket, p.row_map = row_map, p.b_rows_total = n_buckets * N, p.b_pitch = b_pitch;
   return ws_dispatch(p, const_cast<float*>(hi), const_cast<float*>(lo), ktot, stream);
 }
 

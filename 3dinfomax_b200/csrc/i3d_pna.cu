@@ -422,36 +422,54 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// one CTA = one 32 x 32 tile of (output row n, merged column j) of one bucket: both operand layouts are written with
+// coalesced rows (the backward operand is the transpose, staged through shared memory)
 __global__ void __launch_bounds__(256)
     posttrans_merge_kernel(const float* __restrict__ W, int ldw, int Fout, int F, int NB, float* __restrict__ fwd_hi,
-                           float* __restrict__ fwd_lo, float* __restrict__ bwd_hi, float* __restrict__ bwd_lo) {
+                           float* __restrict__ fwd_lo, int ktf, float* __restrict__ bwd_hi, float* __restrict__ bwd_lo,
+                           int ktb) {
   pdl_grid_sync();
+  __shared__ float th[32][33], tl[32][33];
   const int F4 = 4 * F, K5 = 5 * F;
-  const int ktf = kpad32(F) + kpad32(F4), ktb = kpad32(Fout);
-  const int64_t total = (int64_t)NB * Fout * K5;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(t % K5);
-    const int n = (int)((t / K5) % Fout);
-    const int b = (int)(t / ((int64_t)K5 * Fout));
-    const float* w = W + (int64_t)n * ldw;
-    float m;
-    int col;
-    if (j < F) {
-      m = __ldg(w + j);
-      col = j;
-    } else {
-      float a, tt;
-      bucket_scalers(b, &a, &tt);
-      const int c = j - F;
-      m = __ldg(w + F + c) + a * __ldg(w + F + F4 + c) + tt * __ldg(w + F + 2 * F4 + c);
-      col = kpad32(F) + c;
+  const int tiles_j = (K5 + 31) / 32, tiles_n = (Fout + 31) / 32;
+  const int t = blockIdx.x;
+  const int b = t / (tiles_j * tiles_n);
+  const int r = t - b * (tiles_j * tiles_n);
+  const int n0 = (r / tiles_j) * 32, j0 = (r % tiles_j) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float a, tt;
+  bucket_scalers(b, &a, &tt);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty + 8 * i, j = j0 + tx;
+    float h = 0.f, l = 0.f;
+    if (n < Fout && j < K5) {
+      const float* w = W + (int64_t)n * ldw;
+      float m;
+      int col;
+      if (j < F) {
+        m = __ldg(w + j);
+        col = j;
+      } else {
+        const int c = j - F;
+        m = __ldg(w + F + c) + a * __ldg(w + F + F4 + c) + tt * __ldg(w + F + 2 * F4 + c);
+        col = kpad32(F) + c;
+      }
+      h = to_tf32_rna(m);
+      l = m - h;
+      const int64_t of = ((int64_t)b * Fout + n) * ktf + col;
+      fwd_hi[of] = h, fwd_lo[of] = l;
     }
-    const float h = to_tf32_rna(m);
-    const float l = m - h;
-    const int64_t of = ((int64_t)b * Fout + n) * ktf + col;
-    fwd_hi[of] = h, fwd_lo[of] = l;
-    const int64_t ob = ((int64_t)b * K5 + j) * ktb + n;
-    bwd_hi[ob] = h, bwd_lo[ob] = l;
+    th[ty + 8 * i][tx] = h, tl[ty + 8 * i][tx] = l;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + ty + 8 * i, n = n0 + tx;
+    if (n < Fout && j < K5) {
+      const int64_t ob = ((int64_t)b * K5 + j) * ktb + n;
+      bwd_hi[ob] = th[tx][ty + 8 * i], bwd_lo[ob] = tl[tx][ty + 8 * i];
+    }
   }
 }
 
@@ -711,11 +729,13 @@ int i3d_pna_aggregate_fwd(const float* msg, const int32_t* rowptr, int64_t N, in
   const bool v4 = can_vec4({msg, out}, {F, ldo});
   const int64_t work = N * (F / (v4 ? 4 : 1));
   cudaStream_t st = as_stream(stream);
-  // default: bulk-copy (TMA 1-D) staged kernel; I3D_AGG_FWD=ldg selects the register-staged variant
+  // default: register-staged LDG kernel.  I3D_AGG_FWD=tma selects the bulk-copy (TMA 1-D) staged variant, measured
+  // SLOWER on B200 at the target sizes (batch 512: 9.8 vs 7.9 us warm, 11.3 vs 9.4 us cold; batch 2048: 37.2 vs 36.2 us,
+  // tests/gpu_agg_bench.py): at <= 2 blocks per CTA its copy -> reduce -> store phases barely overlap.
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("I3D_AGG_FWD");
-    variant = (e && e[0] == 'l') ? 0 : 1;
+    variant = (e && e[0] == 't') ? 1 : 0;
   }
   if (variant == 1 && v4 && N >= kAggNodes) {
     // two stages per CTA, two CTAs per SM: a stage holds a block of kAggNodes nodes of in-degree <= 4 (64 rows),
@@ -819,12 +839,14 @@ int i3d_segment_sum_bwd(const float* g, const int32_t* rowptr, const int32_t* ro
 }
 
 int i3d_posttrans_merge(const float* W, int ldw, int Fout, int F, int n_buckets, float* fwd_hi, float* fwd_lo,
-                        float* bwd_hi, float* bwd_lo, void* stream) {
+                        int fwd_pitch, float* bwd_hi, float* bwd_lo, int bwd_pitch, void* stream) {
   I3D_REQUIRE(W && Fout > 0 && F > 0 && ldw >= 13 * F && n_buckets >= 1 && n_buckets <= 16 && fwd_hi && fwd_lo &&
                   bwd_hi && bwd_lo, "invalid argument");
-  const int64_t work = (int64_t)n_buckets * Fout * 5 * F;
-  launch(posttrans_merge_kernel, grid_for(work, 256), 256, 0, as_stream(stream), W, ldw, Fout, F, n_buckets, fwd_hi,
-         fwd_lo, bwd_hi, bwd_lo);
+  I3D_REQUIRE(fwd_pitch >= (F + 31) / 32 * 32 + (4 * F + 31) / 32 * 32 && bwd_pitch >= (Fout + 31) / 32 * 32,
+              "operand pitch smaller than the padded K extent");
+  const int tiles = n_buckets * ((Fout + 31) / 32) * ((5 * F + 31) / 32);
+  launch(posttrans_merge_kernel, tiles, 256, 0, as_stream(stream), W, ldw, Fout, F, n_buckets, fwd_hi, fwd_lo,
+         fwd_pitch, bwd_hi, bwd_lo, bwd_pitch);
   I3D_LAUNCHED();
   return I3D_OK;
 }

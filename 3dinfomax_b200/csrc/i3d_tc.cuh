@@ -153,7 +153,9 @@ template <int BN, int NTHR = TC_THREADS>
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N, int64_t m0,
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
                                             int accumulate, bool atomic, double* __restrict__ stats = nullptr,
-                                            int stats_act = 0, const int32_t* __restrict__ row_map = nullptr) {
+                                            int stats_act = 0, const int32_t* __restrict__ row_map = nullptr,
+                                            uint32_t tmem2 = 0xffffffffu) {
+  // tmem2: optional second accumulator (same shape) that is added to the first while the tile is drained
   // row_map (degree-bucketed GEMMs): tile row r is written to output row row_map[m0 + r]; negative = padding row that
   // is neither stored nor counted in the statistics
   __shared__ int32_t s_row[TC_BM];
@@ -170,6 +172,12 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
     float v[16];
     if (has_acc) {
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);    // warp-collective: no divergence around it
+      if (tmem2 != 0xffffffffu) {
+        float w[16];
+        tmem_ld16(tmem2 + ((uint32_t)(q * 32) << 16) + (uint32_t)c, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;

@@ -4,6 +4,7 @@ torch is used here for what the task calls plumbing only: device allocations (``
 the current CUDA stream and raw ``data_ptr()``s.  No wrapper computes anything with torch ops.
 """
 import ctypes
+import os
 
 import torch
 
@@ -89,13 +90,17 @@ def degree_scalers(rowptr):
 
 class DegreePlan:
     """Device arrays of i3d_degree_plan (include/i3d.h): nodes grouped by in-degree into whole 128-row tiles."""
-    CHUNK_TILES = 4        # split-K chunk of the weight-gradient GEMM: at most 512 virtual rows
+    CHUNK_TILES = 4        # smallest split-K chunk of the weight-gradient GEMM (4 tiles = 512 virtual rows)
 
-    def __init__(self, rowptr, n_buckets):
+    def __init__(self, rowptr, n_buckets, ctas_per_chunk=8, sms=148):
         N = rowptr.numel() - 1
         dev = rowptr.device
         tiles = (N + 127) // 128
         self.n_buckets = int(n_buckets)
+        # the chunked dW GEMM launches ctas_per_chunk CTAs (output tiles of the [Fout, 4F] block) per chunk: size the
+        # chunks so that all of them fit one wave of the machine
+        room = max(1, sms // ctas_per_chunk - self.n_buckets)
+        self.CHUNK_TILES = max(DegreePlan.CHUNK_TILES, -(-tiles // room))
         self.N = N
         self.T = tiles + self.n_buckets
         self.Mv = 128 * self.T
@@ -118,7 +123,10 @@ class MergedPosttransWeights:
 
     def __init__(self, Fout, F, n_buckets, device):
         self.Fout, self.F, self.n_buckets = int(Fout), int(F), int(n_buckets)
-        self.ktf = kpad32(F) + kpad32(4 * F)
+        # row pitch of the operands: the padded K extent, bumped off multiples of 2 KB (e.g. 1024 floats at F = 200)
+        # so that the 200-odd rows of a TMA box do not all map to the same L2 slice
+        unpow2 = lambda k: k + 32 if (k * 4) % 2048 == 0 else k
+        self.ktf = unpow2(kpad32(F) + kpad32(4 * F)) if os.environ.get("I3D_MERGED_PITCH", "pad") == "pad" else kpad32(F) + kpad32(4 * F)
         self.ktb = kpad32(Fout)
         z = lambda r, c: torch.zeros(r, c, dtype=torch.float32, device=device)     # pad columns stay zero for good
         self.fwd_hi, self.fwd_lo = z(n_buckets * Fout, self.ktf), z(n_buckets * Fout, self.ktf)
@@ -129,17 +137,18 @@ class MergedPosttransWeights:
         if W.shape != (self.Fout, 13 * self.F):
             raise ValueError("posttrans weight must be [Fout, 13F]")
         _lib.check(_L().i3d_posttrans_merge(pw, ldw, self.Fout, self.F, self.n_buckets, _p(self.fwd_hi),
-                                            _p(self.fwd_lo), _p(self.bwd_hi), _p(self.bwd_lo), _s()),
+                                            _p(self.fwd_lo), self.ktf, _p(self.bwd_hi), _p(self.bwd_lo), self.ktb, _s()),
                    "i3d_posttrans_merge")
 
 
 def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None):
+    b_pitch = b_hi.shape[1]
     """C[plan.perm[m], :] = bias + sum_s A_s[a_idx_s[m] or m, :] @ B[bucket(m)]^T over the plan's virtual rows."""
     pc, ldc = _mat(C, "C")
     arr = _seg_array(segs, need_b=False)
     stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
     _lib.check(_L().i3d_gemm_nt_bucketed(plan.Mv, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                                         _p(b_hi), _p(b_lo), plan.n_buckets, _p(plan.tile_bucket), _p(plan.perm),
+                                         _p(b_hi), _p(b_lo), b_pitch, plan.n_buckets, _p(plan.tile_bucket), _p(plan.perm),
                                          _p(stats), 0 if stats_act is None else stats_act, _s()),
                "i3d_gemm_nt_bucketed")
     return C if stats_act is None else (C, stats)

@@ -52,9 +52,11 @@ SIGNATURES = {
     "i3d_segment_ptr": (_I, [_P, _L, _P, _P]),
     "i3d_degree_scalers": (_I, [_P, _L, _P, _P, _P]),
     "i3d_degree_plan": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P]),
-    "i3d_posttrans_merge": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "i3d_gemm_nt_bucketed": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
+    "i3d_posttrans_merge": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "i3d_gemm_nt_bucketed": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I,
+                                  _P]),
     "i3d_gemm_tn_chunked": (_I, [_L, _I, ctypes.POINTER(gemm_seg), _P, _I, _L, _P, _I, _P]),
+    "i3d_gemm_debug_counters": (_I, [_P]),
     "i3d_posttrans_unmerge": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
@@ -118,7 +120,8 @@ def build(force=False, verbose=False):
         if not force and not _needs_build():
             return SO_PATH
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        extra = os.environ.get("I3D_NVCC_EXTRA", "").split()          # tuning builds, e.g. -DI3D_WS_PREFETCH=6
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-shared", "-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
         if verbose:
             print(" ".join(cmd))
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

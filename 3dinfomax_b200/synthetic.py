@@ -182,3 +182,37 @@ def slice_batch(b, lo, hi):
         "src3": b["src3"][f0:f1] - m0, "dst3": b["dst3"][f0:f1] - m0, "d3": b["d3"][f0:f1],
         "num_nodes3": nn3[lo * C:hi * C], "num_edges3": ne3[lo * C:hi * C], "xyz3": b["xyz3"][m0:m1],
     }
+
+
+def make_store(seed, n_molecules, shape="qm9"):
+    """A packed molecule store with the fields of the reference's processed file (datasets/qm9_dataset.py:454-467):
+    n_atoms [M], atom_slices / edge_slices [M+1] (leading 0), edge_indices [2, Etot] with molecule-LOCAL node ids,
+    atom_features int64 [Ntot, 9], edge_features int64 [Etot, 3], coordinates fp32 [Ntot, 3]."""
+    rng = np.random.default_rng(seed)
+    counts = _sample_atom_counts(rng, n_molecules, shape)
+    heavy_z = np.array([5, 6, 7, 8])
+    ei_l, ef_l, xf_l, xyz_l = [], [], [], []
+    atom_slices, edge_slices = [0], [0]
+    for n in counts.tolist():
+        bonds, pos, heavy = make_molecule(rng, n)
+        nb = len(bonds)
+        b = np.array(bonds, dtype=np.int64).reshape(nb, 2)
+        s = np.empty(2 * nb, dtype=np.int64)
+        t = np.empty(2 * nb, dtype=np.int64)
+        s[0::2], t[0::2] = b[:, 0], b[:, 1]
+        s[1::2], t[1::2] = b[:, 1], b[:, 0]
+        bf = np.stack([rng.integers(0, 4, size=nb), np.zeros(nb, dtype=np.int64), rng.integers(0, 2, size=nb)], 1)
+        xf = np.stack([rng.integers(0, d, size=n) for d in ATOM_FEATURE_DIMS], 1)
+        xf[:, 0] = np.where(heavy, rng.choice(heavy_z, size=n), 0)
+        ei_l.append(np.stack([s, t]))
+        ef_l.append(np.repeat(bf, 2, axis=0))
+        xf_l.append(xf)
+        xyz_l.append(pos)
+        atom_slices.append(atom_slices[-1] + n)
+        edge_slices.append(edge_slices[-1] + 2 * nb)
+    return {"n_atoms": counts.astype(np.int64), "atom_slices": np.array(atom_slices, dtype=np.int64),
+            "edge_slices": np.array(edge_slices, dtype=np.int64),
+            "edge_indices": np.concatenate(ei_l, axis=1).astype(np.int64),
+            "atom_features": np.concatenate(xf_l).astype(np.int64),
+            "edge_features": np.concatenate(ef_l).astype(np.int64).reshape(-1, 3),
+            "coordinates": np.concatenate(xyz_l).astype(np.float32)}

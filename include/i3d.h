@@ -166,7 +166,9 @@ int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, 
  *                          Wm_b = [Wh | W_id + a_b W_amp + t_b W_att], a_b = (float)ln(b+1), t_b = (float)(1/ln(b+1)):
  *                          fwd_hi/lo [n_buckets*Fout, kpad(F)+kpad(4F)]  (B of y = [h|A] Wm_b^T; kpad = round up to 32)
  *                          bwd_hi/lo [n_buckets*5F, kpad(Fout)]          (B of d[h|A] = dy Wm_b)
- *                          pad columns are not written: zero-fill the buffers once when allocating them.
+ *                          rows are fwd_pitch / bwd_pitch floats apart (>= the padded K extent; a pitch that is not
+ *                          a power of two keeps the TMA row fetches spread over the L2 slices); pad columns are
+ *                          not written: zero-fill the buffers once when allocating them.
  *   i3d_gemm_nt_bucketed   C[row_map[m], n] = bias[n] + sum_s sum_k A_s[a_idx_s[m] or m, k] * B[bucket(m)*N + n, k]
  *                          for the Mv = 128*(tiles+n_buckets) virtual rows; rows with row_map[m] < 0 are skipped (and
  *                          excluded from col_stats).  Segments: unscaled, K % 4 == 0; a_idx entries < 0 read zeros.
@@ -175,12 +177,15 @@ int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, 
  *   i3d_posttrans_unmerge  dW[:, F:5F] += sum_b dWb[b]; dW[:, 5F:9F] += sum_b a_b dWb[b]; dW[:, 9F:13F] += sum_b t_b dWb[b]
  *                          with dWb [n_buckets, Fout, 4F] dense.                                                  */
 int i3d_posttrans_merge(const float* W, int ldw, int Fout, int F, int n_buckets, float* fwd_hi, float* fwd_lo,
-                        float* bwd_hi, float* bwd_lo, void* stream);
+                        int fwd_pitch, float* bwd_hi, float* bwd_lo, int bwd_pitch, void* stream);
 int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-                         const float* b_hi, const float* b_lo, int n_buckets, const int32_t* tile_bucket,
+                         const float* b_hi, const float* b_lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
                          const int32_t* row_map, double* col_stats, int stats_act, void* stream);
 int i3d_gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg* seg, float* C, int ldc, int64_t c_bucket_stride,
                         const int32_t* chunk_tab, int n_chunks, void* stream);
+/* Tuning aid: per-role blocked-cycle counters of the warp-specialised NT kernel (16 HOST uint64; read-and-clear).
+ * All zero unless the library was built with -DI3D_WS_DEBUG (see i3d_gemm_tc_ws.cu). */
+int i3d_gemm_debug_counters(unsigned long long* out16);
 int i3d_posttrans_unmerge(const float* dWb, int n_buckets, int Fout, int F, float* dW, int ldw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

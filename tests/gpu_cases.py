@@ -640,7 +640,7 @@ def case_degree_plan():
         rowptr, _, _ = O.csr_reference(src.numpy(), dst.numpy(), n)
         NB = nb if nb is not None else int(np.diff(rowptr).max()) + 1
         plan = K.DegreePlan(torch.from_numpy(np.asarray(rowptr, dtype=np.int32)).to(DEV), NB)
-        perm, tb, ch, over = _degree_plan_ref(rowptr, NB, K.DegreePlan.CHUNK_TILES)
+        perm, tb, ch, over = _degree_plan_ref(rowptr, NB, plan.CHUNK_TILES)
         out += [("degree_plan/%s/perm" % tag, exact(plan.perm, perm), 0),
                 ("degree_plan/%s/tile_bucket" % tag, exact(plan.tile_bucket, tb), 0),
                 ("degree_plan/%s/chunk_tab" % tag, exact(plan.chunk_tab, ch), 0),
@@ -649,7 +649,7 @@ def case_degree_plan():
     rowptr, _, _ = O.csr_reference(b["src"], b["dst"], len(b["x_atom"]))
     NB = int(np.diff(rowptr).max()) + 1
     plan = K.DegreePlan(torch.from_numpy(np.asarray(rowptr, dtype=np.int32)).to(DEV), NB)
-    perm, tb, ch, over = _degree_plan_ref(rowptr, NB, K.DegreePlan.CHUNK_TILES)
+    perm, tb, ch, over = _degree_plan_ref(rowptr, NB, plan.CHUNK_TILES)
     out += [("degree_plan/qm9_b512/perm", exact(plan.perm, perm), 0),
             ("degree_plan/qm9_b512/chunk_tab", exact(plan.chunk_tab, ch), 0),
             ("degree_plan/qm9_b512/every_node_once",
