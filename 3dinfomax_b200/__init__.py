@@ -10,7 +10,8 @@ Public surface = the reference's plugin names (train.py:167-208 looks classes up
 Everything computes through lib3dinfomax_b200.so (hand-written sm_100a kernels, C ABI in include/i3d.h).
 There is no CPU fallback: constructing modules works anywhere, running them needs a CUDA device.
 """
-from .graph import GraphBatch, GraphStructure, batch_from_numpy, graph_structure  # noqa: F401
+from .collate import PackedMoleculeStore  # noqa: F401
+from .graph import GraphBatch, GraphStructure, annotate_max_in_degree, batch_from_numpy, graph_structure  # noqa: F401
 from .losses import NTXent, NTXentMultiplePositives  # noqa: F401
 from .net3d import Net3D  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
@@ -19,4 +20,5 @@ from .trainer import CapturedStep, SelfSupervisedTrainer  # noqa: F401
 from . import lib, synthetic  # noqa: F401
 
 __all__ = ["PNA", "Net3D", "NTXent", "NTXentMultiplePositives", "SelfSupervisedTrainer", "CapturedStep", "FusedAdam",
-           "GraphBatch", "GraphStructure", "batch_from_numpy", "graph_structure", "lib", "synthetic"]
+           "GraphBatch", "GraphStructure", "PackedMoleculeStore", "annotate_max_in_degree", "batch_from_numpy",
+           "graph_structure", "lib", "synthetic"]

@@ -58,6 +58,8 @@ SIGNATURES = {
     "i3d_gemm_tn_chunked": (_I, [_L, _I, ctypes.POINTER(gemm_seg), _P, _I, _L, _P, _I, _P]),
     "i3d_gemm_debug_counters": (_I, [_P]),
     "i3d_posttrans_unmerge": (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    "i3d_collate_2d": (_I, [_P, _L, _P, _P, _P, _L, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "i3d_collate_3d": (_I, [_P, _L, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "i3d_gemm_backend": (_I, [_I]),

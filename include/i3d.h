@@ -87,6 +87,26 @@ int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att,
 int i3d_degree_plan(const int32_t* rowptr, int64_t N, int n_buckets, int chunk_tiles, int32_t* perm,
                     int32_t* tile_bucket, int32_t* chunk_tab, int32_t* overflow, void* stream);
 
+/* Device-side batch construction from a packed molecule store in HBM (replaces B x QM9Dataset.__getitem__
+ * [datasets/qm9_dataset.py:189-244: get_graph :219-229, get_complete_graph :231-244, get_pairwise :207-217] +
+ * dgl.batch [datasets/custom_collate.py:105-114] + the host->device copy of the collated graphs).
+ * Store (device, layout of the reference's processed file, qm9_dataset.py:454-467): atom_slices / edge_slices [M+1]
+ * with leading 0, edge_indices [2, Etot] molecule-local ids, atom_features [Ntot, n_atom_feat] int64,
+ * edge_features [Etot, n_edge_feat] int64, coordinates [Ntot, 3] fp32.
+ * Per batch (device): idx[B] molecule ids; node_ptr / edge_ptr / edge3_ptr [B+1] exclusive prefix sums of the
+ * batch's atom counts n_k, bond-edge counts and n_k (n_k - 1).
+ *   i3d_collate_2d: src/dst [E] = molecule-local ids + node_ptr[k]; x_atom [N, n_atom_feat]; e_attr [E, n_edge_feat]
+ *   i3d_collate_3d: complete digraph without self loops in the reference's order (src = repeat_interleave(arange(n),
+ *                   n-1), dst ascending), d3 [E3] = ||x_src - x_dst||_2 as torch.norm evaluates it in fp32
+ *                   (x*x, fma(y,y,.), fma(z,z,.), sqrt: bit-equal to the CPU reference on the pinned vectors)   */
+int i3d_collate_2d(const int64_t* idx, int64_t B, const int64_t* atom_slices, const int64_t* edge_slices,
+                   const int64_t* edge_indices, int64_t Etot, const int64_t* atom_features, int n_atom_feat,
+                   const int64_t* edge_features, int n_edge_feat, const int64_t* node_ptr, const int64_t* edge_ptr,
+                   int64_t N, int64_t E, int64_t* src, int64_t* dst, int64_t* x_atom, int64_t* e_attr, void* stream);
+int i3d_collate_3d(const int64_t* idx, int64_t B, const int64_t* atom_slices, const float* coordinates,
+                   const int64_t* node_ptr, const int64_t* edge3_ptr, int64_t E3, int64_t* src3, int64_t* dst3,
+                   float* d3, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * AtomEncoder / BondEncoder  [commons/mol_encoder.py:34-42,65-73; models/pna.py:162-163]
  *   out[r,:] = sum_c table[col_off[c] + idx[perm ? perm[r] : r, c], :]

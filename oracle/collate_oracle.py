@@ -35,6 +35,18 @@ def pairwise_edges(n):
     return src, dst
 
 
+def norm3_fp32(diff):
+    """torch.norm(diff, p=2, dim=-1) for fp32 [.., 3] as torch evaluates it (probe in oracle/pin_collate.py: bit-equal
+    on 200k random vectors): a fused-multiply-add chain acc = x*x; acc = fma(y, y, acc); acc = fma(z, z, acc) rounded
+    to fp32 after every step, then an fp32 square root.  The fma is emulated in fp64 (products of fp32 are exact)."""
+    d = diff.astype(np.float64)
+    r32 = lambda v: v.astype(np.float32).astype(np.float64)
+    acc = r32(d[..., 0] * d[..., 0])
+    acc = r32(d[..., 1] * d[..., 1] + acc)
+    acc = r32(d[..., 2] * d[..., 2] + acc)
+    return np.sqrt(acc.astype(np.float32))
+
+
 def collate_reference(store, idx):
     """numpy dict in the layout of 3dinfomax_b200.synthetic.make_batch for molecules ``idx`` of ``store``."""
     idx = np.asarray(idx, dtype=np.int64)
@@ -52,9 +64,7 @@ def collate_reference(store, idx):
         e_attr.append(store["edge_features"][e0[k]:e1[k]])
         s3, t3 = pairwise_edges(n)
         x = store["coordinates"][a0[k]:a0[k] + n].astype(np.float32)
-        diff = x[s3] - x[t3]
-        # torch.norm(p=2, dim=-1) in fp32: sqrt of the sum of squares
-        d3.append(np.sqrt((diff * diff).sum(-1, dtype=np.float32)).astype(np.float32)[:, None])
+        d3.append(norm3_fp32(x[s3] - x[t3])[:, None])
         src3.append(s3 + off[k])
         dst3.append(t3 + off[k])
     cat = lambda xs, dt, tail=(): (np.concatenate(xs).astype(dt) if xs else np.zeros((0,) + tail, dt))

@@ -111,7 +111,7 @@ def reference_batch(store, idx):
     ds = object.__new__(QM9Dataset)               # __init__ builds the store with rdkit; the store is given here
     t = torch.from_numpy
     ds.device = "cpu"
-    ds.return_types = ["dgl_graph", "complete_graph"]
+    ds.return_types = ["dgl_graph", "complete_graph3d"]      # configs_clean/pre-train_QM9.yml:12-14
     ds.features_tensor = t(store["atom_features"])
     ds.e_features_tensor = t(store["edge_features"])
     ds.coordinates = t(store["coordinates"])

@@ -743,6 +743,57 @@ def case_train_steps_merged():
     return [(l.replace("train", "train_merged", 1), e, t) for l, e, t in res]
 
 
+# ------------------------------------------------------------------------------------ device collate (N1)
+def case_collate():
+    """i3d_collate_2d / i3d_collate_3d against the numpy restatement of QM9Dataset.__getitem__ + contrastive_collate
+    (oracle/collate_oracle.py, pinned on the reference's code) and against the committed reference vectors."""
+    from oracle import collate_oracle as CO
+    out = []
+    keys = ("src", "dst", "x_atom", "e_attr", "num_nodes", "num_edges", "src3", "dst3", "num_nodes3", "num_edges3")
+
+    def compare(tag, g2, g3, ref):
+        got = {"src": g2.edges()[0], "dst": g2.edges()[1], "x_atom": g2.ndata["feat"], "e_attr": g2.edata["feat"],
+               "num_nodes": g2.batch_num_nodes(), "num_edges": g2.batch_num_edges(), "src3": g3.edges()[0],
+               "dst3": g3.edges()[1], "num_nodes3": g3.batch_num_nodes(), "num_edges3": g3.batch_num_edges()}
+        res = [("collate/%s/%s" % (tag, k), exact(got[k], ref[k]), 0) for k in keys]
+        # fp32 distance: same fma chain + sqrt as torch.norm on the CPU; bit-equal expected, 1 ulp allowed
+        res.append(("collate/%s/d3" % tag, rel(g3.edata["d"], ref["d3"]), 1.2e-7))
+        res.append(("collate/%s/d3_bit_equal_fraction_missing" % tag,
+                    float((g3.edata["d"].cpu().numpy() != ref["d3"]).mean()), 0.0))
+        return res
+
+    for name, shape in (("collate_qm9", "qm9"), ("collate_qmugs", "qmugs")):
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        store = CO.make_store(int(g["seed"]), int(g["n_molecules"]), shape)
+        ps = i3d.PackedMoleculeStore(store, DEV)
+        out += compare("golden_" + name, *ps.collate(g["idx"]), g)
+    # BASELINE config-2 size: 512 random molecules out of a 2000-molecule store, with repeats and a 1-atom... (n>=3 in QM9)
+    store = CO.make_store(91, 2000, "qm9")
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    idx = np.random.default_rng(3).integers(0, 2000, size=512)
+    g2, g3 = ps.collate(idx)
+    ref = CO.collate_reference(store, idx)
+    out += compare("qm9_b512", g2, g3, ref)
+    out.append(("collate/qm9_b512/max_in_degree_hint", abs(g2.max_in_degree - int(np.bincount(ref["dst"]).max())), 0))
+    # the collated batch drives the encoders exactly like a batch built on the host
+    c2, c3, st2, st3, pna, n3 = _models(61, 62)
+    pna.eval(), n3.eval()
+    with torch.no_grad():
+        z2, z3 = pna(g2), n3(g3)
+        h2, h3 = i3d.batch_from_numpy(dict(ref, batch_size=512, conformers=1), DEV)
+        y2, y3 = pna(h2), n3(h3)
+    out += [("collate/qm9_b512/pna_on_device_batch_equals_host_batch", rel(z2, y2), 1e-6),
+            ("collate/qm9_b512/net3d_on_device_batch_equals_host_batch", rel(z3, y3), 1e-6)]
+    # a second batch of the same size reuses the staging buffer: the first batch's graphs must stay intact
+    src_before = g2.edges()[0].clone()
+    bnn_before = g2.batch_num_nodes().clone()
+    ps.collate(np.random.default_rng(4).integers(0, 2000, size=512))
+    torch.cuda.synchronize()
+    out += [("collate/staging_reuse_keeps_previous_batch", exact(g2.edges()[0], src_before) +
+             exact(g2.batch_num_nodes(), bnn_before), 0)]
+    return out
+
+
 # ------------------------------------------------------------------------------------------ whole models
 def _models(s2, s3, trained=True):
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
@@ -903,4 +954,4 @@ from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
-             case_full_size_properties, case_sharded_equals_full]
+             case_full_size_properties, case_collate, case_sharded_equals_full]
