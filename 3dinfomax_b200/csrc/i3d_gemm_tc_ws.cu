@@ -556,8 +556,9 @@ static int ws_dispatch(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t
     if (force_bn == 112) return force_occ == 2 ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
     if (force_bn == 208) return force_occ == 2 ? launch_ws<208, 2>(p, hi, lo, ktot, stream) : launch_ws<208>(p, hi, lo, ktot, stream);
   }
-  if (N <= 32) return launch_ws<32>(p, hi, lo, ktot, stream);
-  if (N <= 64) return launch_ws<64>(p, hi, lo, ktot, stream);
+  // narrow outputs (Net3D: 20 columns over ~160k edge rows = ~1260 row tiles): two CTAs per SM halve the waves
+  if (N <= 32) return gx > sms ? launch_ws<32, 2>(p, hi, lo, ktot, stream) : launch_ws<32>(p, hi, lo, ktot, stream);
+  if (N <= 64) return gx > sms ? launch_ws<64, 2>(p, hi, lo, ktot, stream) : launch_ws<64>(p, hi, lo, ktot, stream);
   if (N <= 112) return gx > sms ? launch_ws<112, 2>(p, hi, lo, ktot, stream) : launch_ws<112>(p, hi, lo, ktot, stream);
   if (N <= 128) return launch_ws<128>(p, hi, lo, ktot, stream);
   if (N <= 208) {

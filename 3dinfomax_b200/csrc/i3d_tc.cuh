@@ -195,15 +195,26 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
     for (int c = tid; tid < NTHR && c < BN; c += NTHR) {
       if (n0 + c >= N) continue;
       const float b = bias ? __ldg(bias + n0 + c) : 0.f;
-      double s1 = 0.0, s2 = 0.0;
-      for (int r = 0; r < rows; ++r) {
+      // four independent fp64 chains (the loop is bound by the DADD/DFMA dependency, not by the shared-memory reads)
+      double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+      int r = 0;
+      for (; r + 4 <= rows; r += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool valid = !row_map || s_row[r + u] >= 0;
+          const double h = valid ? (double)act_apply(ctile[(r + u) * LDT + c] + b, stats_act) : 0.0;
+          s1[u] += h;
+          s2[u] = fma(h, h, s2[u]);
+        }
+      }
+      for (; r < rows; ++r) {
         if (row_map && s_row[r] < 0) continue;
         const double h = (double)act_apply(ctile[r * LDT + c] + b, stats_act);
-        s1 += h;
-        s2 += h * h;
+        s1[0] += h;
+        s2[0] = fma(h, h, s2[0]);
       }
-      atomicAdd(stats + n0 + c, s1);
-      atomicAdd(stats + N + n0 + c, s2);
+      atomicAdd(stats + n0 + c, (s1[0] + s1[1]) + (s1[2] + s1[3]));
+      atomicAdd(stats + N + n0 + c, (s2[0] + s2[1]) + (s2[2] + s2[3]));
     }
   }
   const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);
