@@ -6,9 +6,55 @@ concatenation of K-segments, each optionally row-gathered and row-scaled, so tha
 ``cat([h[src], h[dst], e])`` (models/pna.py:249) and ``cat([h, agg, agg*amp, agg*att])``
 (models/pna.py:207,232) are never materialised.
 """
+import os
+import threading
+
 import torch
 
 from . import kernels as K
+
+# ---------------------------------------------------------------------------------------------------------------
+# Weight-gradient side stream.  dW = dY^T x of the big FC layers is a leaf of the backward graph: nothing downstream
+# of it runs before the optimizer.  Its split-K tensor-core kernels occupy one CTA per SM with most of the shared
+# memory but few warps, while the BatchNorm / aggregation / segment-sum backward kernels of the next layers are
+# bandwidth-bound and light on shared memory — so the dW GEMMs are issued on a second stream (a parallel branch of
+# the captured step graph) and joined once, when backward() ends.  Only taken when the gradient accumulates straight
+# into FusedAdam's flat buffer (nothing is handed back to autograd).  I3D_DW_STREAM=0 keeps everything on one stream.
+# ---------------------------------------------------------------------------------------------------------------
+_dw_lock = threading.Lock()
+_dw_streams = {}          # device index -> side stream
+_dw_join_pending = {}     # device index -> a join callback is queued for the running backward()
+DW_MIN_ROWS = int(os.environ.get("I3D_DW_MIN_ROWS", "2048"))     # smaller GEMMs stay on the main stream
+
+
+def _dw_min_rows():
+    return int(os.environ.get("I3D_DW_MIN_ROWS", DW_MIN_ROWS))
+
+
+def _dw_fork(device, main, used):
+    """Side stream ordered after everything enqueued on ``main`` so far, or None.  ``used``: tensors the side work
+    reads that may be freed while it still runs (caching-allocator bookkeeping).  Backward nodes run on autograd's
+    worker thread, the end-of-backward callback on the thread that called backward(): state is global, not thread-local."""
+    if os.environ.get("I3D_DW_STREAM", "1") == "0":
+        return None
+    with _dw_lock:
+        side = _dw_streams.get(device.index)
+        if side is None:
+            side = _dw_streams[device.index] = torch.cuda.Stream(device=device)
+        queue = not _dw_join_pending.get(device.index, False)
+        _dw_join_pending[device.index] = True
+    side.wait_stream(main)
+    for t in used:
+        if t is not None:
+            t.record_stream(side)
+    if queue:
+        def join():
+            with _dw_lock:
+                _dw_join_pending[device.index] = False
+            torch.cuda.current_stream(device).wait_stream(side)
+
+        torch.autograd.Variable._execution_engine.queue_callback(join)      # runs when this backward() finishes
+    return side
 
 
 class Seg:
@@ -38,6 +84,14 @@ class FCConfig:
         self.segs, self.act, self.has_bn, self.training = segs, act, has_bn, training
         self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
         self.momentum, self.eps = momentum, eps
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 class _FC(torch.autograd.Function):
@@ -115,18 +169,24 @@ class _FC(torch.autograd.Function):
             # and hand autograd nothing; otherwise one memset and the split-K column-block GEMMs accumulate into dW
             direct = getattr(ctx.w_param, "_i3d_grad_view", None)
             acc = direct if direct is not None else torch.zeros_like(W)
-            off = 0
-            for i, (s, x) in enumerate(zip(segs, xs)):
-                k = x.shape[1]
-                if s.idx is not None and x.shape[0] < M:
-                    # dY^T x[idx] == (sum of the dY rows that read each x row)^T x: reduce over the gather first (the
-                    # same row sums feed dx below), then a GEMM over the R source rows instead of the M gathered ones
-                    K.gemm(K.TN, Fout, k, [{"A": row_sums(i, s), "B": x, "K": x.shape[0]}], acc[:, off:off + k],
-                           accumulate=True)
-                else:
-                    K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
-                           acc[:, off:off + k], accumulate=True)
-                off += k
+            # dY^T x[idx] == (sum of the dY rows that read each x row)^T x: reduce over the gather first (the same row
+            # sums feed dx below), then a GEMM over the R source rows instead of the M gathered ones
+            via_sums = [s.idx is not None and x.shape[0] < M for s, x in zip(segs, xs)]
+            a_ops = [row_sums(i, s) if v else dY for i, (v, s) in enumerate(zip(via_sums, segs))]
+            side = None
+            if direct is not None and M >= _dw_min_rows() and Fout >= 64:
+                side = _dw_fork(W.device, torch.cuda.current_stream(W.device), [dY] + a_ops + list(xs))
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                off = 0
+                for i, (s, x) in enumerate(zip(segs, xs)):
+                    k = x.shape[1]
+                    if via_sums[i]:
+                        K.gemm(K.TN, Fout, k, [{"A": a_ops[i], "B": x, "K": x.shape[0]}], acc[:, off:off + k],
+                               accumulate=True)
+                    else:
+                        K.gemm(K.TN, Fout, k, [{"A": dY, "B": x, "K": M, "b_idx": s.idx, "scale": s.scale}],
+                               acc[:, off:off + k], accumulate=True)
+                    off += k
             dW = None if direct is not None else acc
         # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
         dxs = [None] * len(xs)
@@ -230,10 +290,14 @@ class _FCPostMerged(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             direct = getattr(ctx.w_param, "_i3d_grad_view", None)
             acc = direct if direct is not None else torch.zeros_like(W)
-            K.gemm(K.TN, Fout, F, [{"A": dY, "B": h, "K": N}], acc[:, :F], accumulate=True)
-            dWb = torch.zeros(plan.n_buckets, Fout, 4 * F, dtype=torch.float32, device=W.device)
-            K.gemm_tn_chunked(plan, dY, agg, dWb)
-            K.posttrans_unmerge(dWb, acc, F)
+            side = None
+            if direct is not None and N >= _dw_min_rows() and Fout >= 64:
+                side = _dw_fork(W.device, torch.cuda.current_stream(W.device), [dY, h, agg])
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                K.gemm(K.TN, Fout, F, [{"A": dY, "B": h, "K": N}], acc[:, :F], accumulate=True)
+                dWb = torch.zeros(plan.n_buckets, Fout, 4 * F, dtype=torch.float32, device=W.device)
+                K.gemm_tn_chunked(plan, dY, agg, dWb)
+                K.posttrans_unmerge(dWb, acc, F)
             dW = None if direct is not None else acc
         dh = dagg = None
         if ctx.needs_input_grad[8] or ctx.needs_input_grad[9]:

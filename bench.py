@@ -320,6 +320,29 @@ def run_b200(args):
                        "one buffer set; algorithmic bytes = 4F*E + 4E + 4(N+1) + 16F*N (fwd), 32F*N + 8F*E + 4(N+1) "
                        "(bwd), SURVEY 8d" % (N, E, F)}
 
+    # ---- device-side batch construction: time of PackedMoleculeStore.collate per batch ----------------
+    collate_info = None
+    if rank == 0:
+        store = i3d.PackedMoleculeStore(i3d.synthetic.make_store(7, 4 * args.batch), dev)
+        rng = __import__("numpy").random.default_rng(11)
+        idxs = [rng.integers(0, len(store), size=args.batch) for _ in range(12)]
+        for ix in idxs[:2]:
+            store.collate(ix)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for ix in idxs[2:]:
+            cg2, cg3 = store.collate(ix)
+        c1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 10
+        collate_info = {"us_per_batch_device": c0.elapsed_time(c1) * 1e3 / 10, "us_per_batch_wall": wall * 1e6,
+                        "h2d_bytes_per_batch": 8 * (7 * args.batch + 3),
+                        "what": "PackedMoleculeStore.collate: molecule indices -> batched 2-D + 3-D graphs on the "
+                                "device (replaces B x Dataset.__getitem__ + dgl.batch + graph H2D copy)"}
+        del store, cg2, cg3
+
     if rank == 0:
         mols = args.batch * world * args.steps
         line = {"metric": METRIC, "value": mols / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -332,7 +355,7 @@ def run_b200(args):
                            "bn": "local per-rank batch statistics", "note": note, "last_loss": float(last_loss)},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roof}
+                "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roof, "collate": collate_info}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             val, per, threads = cpu_oracle_throughput(min(args.batch, 256), 3, 1, cores)

@@ -738,9 +738,35 @@ def case_golden_merged():
 
 
 def case_train_steps_merged():
-    res = _with_env({"I3D_PLAN_MIN_NODES": "0"}, case_train_steps, 16, 2, False, 23)
-    res += _with_env({"I3D_PLAN_MIN_NODES": "0"}, case_train_steps, 16, 2, True, 23)
+    """training steps against the oracle with the degree-merged posttrans AND the weight-gradient side stream forced
+    on (both switch on by themselves only above a size threshold that a 16-molecule batch does not reach)"""
+    env = {"I3D_PLAN_MIN_NODES": "0", "I3D_DW_MIN_ROWS": "0"}
+    res = _with_env(env, case_train_steps, 16, 2, False, 23)
+    res += _with_env(env, case_train_steps, 16, 2, True, 23)
     return [(l.replace("train", "train_merged", 1), e, t) for l, e, t in res]
+
+
+def case_dw_side_stream():
+    """BASELINE config-2 size: parameter gradients of one backward pass with the weight-gradient GEMMs on the side
+    stream equal the single-stream ones (split-K atomics make both runs differ at rounding level only)."""
+    b = syn.make_batch(9, 512)
+    grads = {}
+    for mode in ("1", "0"):
+        def run():
+            c2, c3, st2, st3, pna, n3 = _models(71, 72)
+            tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), DEV, {"lr": 8e-5})
+            g2, g3 = i3d.batch_from_numpy(b, DEV)
+            loss, _, _ = tr.forward_pass(([g2], [g3]))
+            loss.backward()
+            torch.cuda.synchronize()
+            return loss.item(), {k: p.grad.detach().clone() for k, p in list(pna.named_parameters()) + list(n3.named_parameters())}
+        grads[mode] = _with_env({"I3D_DW_STREAM": mode}, run)
+    (l1, g1), (l0, g0) = grads["1"], grads["0"]
+    scale = max(float(v.abs().max()) for v in g0.values())
+    worst = max(float((g1[k] - g0[k]).abs().max()) for k in g0) / scale
+    nonzero = min(float(g1[k].abs().max() > 0) for k in g1 if "linear.weight" in k)
+    return [("dw_side_stream/loss", abs(l1 - l0), 1e-6), ("dw_side_stream/param_grads_vs_single_stream", worst, 2e-5),
+            ("dw_side_stream/every_weight_gradient_written", 1.0 - nonzero, 0)]
 
 
 # ------------------------------------------------------------------------------------ device collate (N1)
@@ -954,4 +980,4 @@ from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
-             case_full_size_properties, case_collate, case_sharded_equals_full]
+             case_dw_side_stream, case_full_size_properties, case_collate, case_sharded_equals_full]
