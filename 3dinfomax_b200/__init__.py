@@ -13,12 +13,15 @@ There is no CPU fallback: constructing modules works anywhere, running them need
 from .collate import PackedMoleculeStore  # noqa: F401
 from .graph import GraphBatch, GraphStructure, annotate_max_in_degree, batch_from_numpy, graph_structure  # noqa: F401
 from .losses import NTXent, NTXentMultiplePositives  # noqa: F401
+from .metrics import (ContrastiveAccuracy, NegativeSimilarity, PositiveSimilarity, TrueNegativeRate,  # noqa: F401
+                      TruePositiveRate, contrastive_metrics)
 from .net3d import Net3D  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .pna import PNA  # noqa: F401
 from .trainer import CapturedStep, SelfSupervisedTrainer  # noqa: F401
 from . import lib, synthetic  # noqa: F401
 
-__all__ = ["PNA", "Net3D", "NTXent", "NTXentMultiplePositives", "SelfSupervisedTrainer", "CapturedStep", "FusedAdam",
+__all__ = ["PNA", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
+           "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "SelfSupervisedTrainer", "CapturedStep", "FusedAdam",
            "GraphBatch", "GraphStructure", "PackedMoleculeStore", "annotate_max_in_degree", "batch_from_numpy",
            "graph_structure", "lib", "synthetic"]

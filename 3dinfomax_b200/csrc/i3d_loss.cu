@@ -184,6 +184,81 @@ __global__ void multi_copy_kernel(const uint64_t* __restrict__ ptrs, const int64
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Contrastive metrics of the pre-training configs (trainer/metrics.py:240-334,444-463, pos_mask == None):
+// all five read the same cosine-similarity matrix S = z1 z2^T / (|z1_i| |z2_j|); the reference rebuilds it once per
+// metric (five einsums + masks over [B, B]), here one pass over the dot-product matrix produces per-row partials:
+//   part[i] = (S_ii, sum_j S_ij, [pred_ii], #{j != i : !pred_ij})     pred_ij = ((S_ij + 1) / 2 > threshold)
+// and a deterministic single-block reduction turns them into
+//   out[0] positive_similarity = mean_i (S_ii + 1)/2                 out[1] negative_similarity = mean_i ((rowsum_i - S_ii)/(B-1) + 1)/2
+//   out[2] true_positive_rate  = #pred_ii / B                        out[3] true_negative_rate  = #(!pred_ij, i != j) / (B (B-1))
+//   out[4] contrastive_accuracy = (out[2] + out[3]) / 2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    contrastive_metric_rows_kernel(const float* __restrict__ dot, int64_t B, const float* __restrict__ n1,
+                                   const float* __restrict__ n2, float threshold, float* __restrict__ part) {
+  pdl_grid_sync();
+  __shared__ float sh[32];
+  for (int64_t i = blockIdx.x; i < B; i += gridDim.x) {
+    const float* row = dot + i * B;
+    const float a = n1[i];
+    float rowsum = 0.f, diag = 0.f, tn = 0.f, tp = 0.f;
+    for (int64_t j = threadIdx.x; j < B; j += blockDim.x) {
+      const float s = __fdiv_rn(row[j], __fmul_rn(a, __ldg(n2 + j)));
+      const bool pred = __fdiv_rn(__fadd_rn(s, 1.f), 2.f) > threshold;
+      rowsum += s;
+      if (j == i) {
+        diag = s;
+        tp = pred ? 1.f : 0.f;
+      } else if (!pred) {
+        tn += 1.f;
+      }
+    }
+    rowsum = block_sum(rowsum, sh);
+    diag = block_sum(diag, sh);
+    tn = block_sum(tn, sh);
+    tp = block_sum(tp, sh);
+    if (threadIdx.x == 0) {
+      part[4 * i] = diag, part[4 * i + 1] = rowsum, part[4 * i + 2] = tp, part[4 * i + 3] = tn;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+    contrastive_metric_final_kernel(const float* __restrict__ part, int64_t B, float* __restrict__ out) {
+  pdl_grid_sync();
+  __shared__ double shd[32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+    const double d = part[4 * i], rs = part[4 * i + 1];
+    acc[0] += (d + 1.0) * 0.5;
+    acc[1] += B > 1 ? ((rs - d) / (double)(B - 1) + 1.0) * 0.5 : 0.0;
+    acc[2] += part[4 * i + 2];
+    acc[3] += part[4 * i + 3];
+  }
+  double tot[4];
+  for (int k = 0; k < 4; ++k) {
+    double v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = 0.0;
+    if (threadIdx.x < 32) {
+      v = threadIdx.x < (blockDim.x >> 5) ? shd[threadIdx.x] : 0.0;
+      v = warp_sum(v);
+    }
+    if (threadIdx.x == 0) tot[k] = v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double b = (double)B;
+    out[0] = (float)(tot[0] / b);
+    out[1] = (float)(tot[1] / b);
+    out[2] = (float)(tot[2] / b);
+    out[3] = B > 1 ? (float)(tot[3] / (b * (b - 1.0))) : 0.f;
+    out[4] = 0.5f * (out[2] + out[3]);
+  }
+}
+
 }  // namespace i3d
 
 using namespace i3d;
@@ -264,6 +339,17 @@ int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len,
   I3D_REQUIRE(T >= 0 && T <= 65535 && (T == 0 || (ptrs && off && len && flat)), "invalid argument");
   if (T == 0) return I3D_OK;
   launch(multi_copy_kernel, dim3(16, T, 1), 256, 0, as_stream(stream), ptrs, off, len, flat, to_flat);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_contrastive_metrics(const float* dot, int64_t B, const float* n1, const float* n2, float threshold,
+                            float* part, float* out5, void* stream) {
+  I3D_REQUIRE(B >= 1 && dot && n1 && n2 && part && out5, "invalid argument");
+  const int grid = (int)(B < 65535 ? B : 65535);
+  launch(contrastive_metric_rows_kernel, grid, 256, 0, as_stream(stream), dot, B, n1, n2, threshold, part);
+  I3D_LAUNCHED();
+  launch(contrastive_metric_final_kernel, 1, 1024, 0, as_stream(stream), part, B, out5);
   I3D_LAUNCHED();
   return I3D_OK;
 }

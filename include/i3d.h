@@ -294,6 +294,13 @@ int i3d_row_norms(const float* z, int64_t R, int D, float* norms, void* stream);
 /* P[B, BcC] in: dot, out: p = exp(s/tau).  rowstats[B,2] = (pos, rowsum-pos).  loss_rows[B] = l_i   */
 int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1, const float* n2, int norm,
                         float eps, float tau, int64_t row_offset, float* rowstats, float* loss_rows, void* stream);
+/* Contrastive metrics logged by the pre-training configs (configs_clean/pre-train_QM9.yml:15-20): PositiveSimilarity,
+ * NegativeSimilarity, TruePositiveRate, TrueNegativeRate, ContrastiveAccuracy [trainer/metrics.py:240-334,444-463],
+ * global-vs-global case (pos_mask == None).  dot[B,B] = z1 z2^T (i3d_gemm NT), n1/n2 = row norms, S = dot/(n1 n2),
+ * pred = ((S+1)/2 > threshold).  part: [B,4] scratch.  out5 = (positive_similarity, negative_similarity,
+ * true_positive_rate, true_negative_rate, contrastive_accuracy).  One pass instead of five [B,B] einsums.      */
+int i3d_contrastive_metrics(const float* dot, int64_t B, const float* n1, const float* n2, float threshold,
+                            float* part, float* out5, void* stream);
 /* out[0] = scale * sum_i x[i]  (deterministic single-block reduction) */
 int i3d_sum_scaled(const float* x, int64_t n, float scale, float* out, void* stream);
 /* in: P (= p), dot recomputed as tau*log(p)*(n1n2+eps); out: P <- d loss / d dot; dn1[B], dn2[BcC] (caller-zeroed)

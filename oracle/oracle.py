@@ -522,3 +522,27 @@ def csr_reference(src, dst, n):
     rowptr = np.zeros(n + 1, dtype=np.int32)
     np.cumsum(np.bincount(dst, minlength=n), out=rowptr[1:])
     return rowptr, src[eid].astype(np.int32), eid
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Contrastive metrics (trainer/metrics.py:240-334, 444-463; pos_mask == None).  Pinned on the reference's own classes
+# by oracle/pin_metrics.py (bit-equal on the committed vectors).
+# ---------------------------------------------------------------------------------------------------------------
+def contrastive_metrics(x1, x2, threshold=0.5):
+    """(positive_similarity, negative_similarity, true_positive_rate, true_negative_rate, contrastive_accuracy)"""
+    B = x1.shape[0]
+    if x1.shape != x2.shape:
+        x2 = x2[:B]                                                              # metrics.py:243-244
+    sim = torch.einsum("ik,jk->ij", x1, x2)
+    sim = sim / torch.einsum("i,j->ij", x1.norm(dim=1), x2.norm(dim=1))          # metrics.py:246-250
+    pos = torch.nn.functional.cosine_similarity(x1, x2)                         # metrics.py:331 (global vs global)
+    positive_similarity = ((pos + 1) / 2).mean(dim=0)
+    diag = sim[range(B), range(B)]
+    negative_similarity = (((sim.sum(dim=1) - diag) / (B - 1) + 1) / 2).mean(dim=0)   # metrics.py:459-462
+    preds = (sim + 1) / 2 > threshold
+    pos_mask = torch.eye(B)
+    neg_mask = 1 - pos_mask
+    tp = B - ((preds.long() - pos_mask) * pos_mask).count_nonzero()             # metrics.py:256-257
+    tn = B * (B - 1) - (((~preds).long() - neg_mask) * neg_mask).count_nonzero()  # metrics.py:279-280
+    tpr, tnr = tp / B, tn / (B * (B - 1))
+    return torch.stack([positive_similarity, negative_similarity, tpr, tnr, (tpr + tnr) / 2])

@@ -820,6 +820,38 @@ def case_collate():
     return out
 
 
+# ------------------------------------------------------------------------------------ contrastive metrics (N3)
+def case_contrastive_metrics():
+    """i3d_contrastive_metrics against the oracle (pinned on trainer/metrics.py) and the committed reference vectors.
+    Similarities: 1e-5 absolute (3xTF32 GEMM vs fp32 einsum).  Rates are counts of threshold decisions: a similarity
+    within rounding distance of the threshold may flip, so they are compared to within 3 decisions."""
+    from oracle.pin_metrics import CASES, embeddings
+    g = np.load(os.path.join(ROOT, "tests", "golden", "metrics.npz"))
+    thr = float(g["threshold"])
+    out = []
+    for name, (seed, B, D, noisy) in CASES.items():
+        x1, x2 = embeddings(seed, B, D, noisy)
+        ref = torch.from_numpy(g[name + "/ref"]).double()
+        got = i3d.contrastive_metrics(x1.to(DEV), x2.to(DEV), thr).double().cpu()
+        flip = 3.0 / (B * (B - 1))
+        out += [("metrics/%s/positive_similarity" % name, abs(float(got[0] - ref[0])), 1e-5),
+                ("metrics/%s/negative_similarity" % name, abs(float(got[1] - ref[1])), 1e-5),
+                ("metrics/%s/true_positive_rate" % name, abs(float(got[2] - ref[2])), 3.0 / B),
+                ("metrics/%s/true_negative_rate" % name, abs(float(got[3] - ref[3])), flip),
+                ("metrics/%s/contrastive_accuracy" % name, abs(float(got[4] - ref[4])), 0.5 * (3.0 / B + flip))]
+    # module surface of trainer/metrics.py: five metric objects share one fused evaluation
+    x1, x2 = embeddings(9, 256, 64, 0)
+    a, b = x1.to(DEV), x2.to(DEV)
+    n0 = i3d.lib.launch_count()
+    vals = [i3d.PositiveSimilarity()(a, b), i3d.NegativeSimilarity()(a, b), i3d.TruePositiveRate(thr)(a, b),
+            i3d.TrueNegativeRate(thr)(a, b), i3d.ContrastiveAccuracy(thr)(a, b)]
+    launches = i3d.lib.launch_count() - n0
+    ref = O.contrastive_metrics(x1, x2, thr)
+    out.append(("metrics/modules_vs_oracle", float((torch.stack(vals).cpu() - ref).abs().max()), 1e-4))
+    out.append(("metrics/five_metrics_one_evaluation(launches<=8)", float(max(0, launches - 8)), 0))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ whole models
 def _models(s2, s3, trained=True):
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
@@ -980,4 +1012,4 @@ from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
-             case_dw_side_stream, case_full_size_properties, case_collate, case_sharded_equals_full]
+             case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_sharded_equals_full]

@@ -99,3 +99,18 @@ def test_readout_first_extremum_gradient():
     x = torch.tensor([[1.0], [5.0], [5.0], [2.0], [2.0]], requires_grad=True)
     O.segment_readout(x, g, "max").sum().backward()
     assert x.grad.flatten().tolist() == [0, 1, 0, 1, 0]
+
+
+def test_contrastive_metrics_oracle_matches_reference_vectors(golden_dir):
+    """oracle.contrastive_metrics against the values produced by the reference's own trainer/metrics.py classes
+    (oracle/pin_metrics.py)."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    from oracle.pin_metrics import CASES as MCASES, embeddings
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    thr = float(g["threshold"])
+    for name, (seed, B, D, noisy) in MCASES.items():
+        x1, x2 = embeddings(seed, B, D, noisy)
+        got = O.contrastive_metrics(x1, x2, thr).numpy()
+        assert np.array_equal(got, g[name + "/ref"]), name
