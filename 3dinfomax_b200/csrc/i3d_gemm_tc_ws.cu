@@ -35,7 +35,7 @@ constexpr int WS_THREADS = 320;           // + TMA warp + MMA warp
 #define I3D_WS_DUAL_ACC 0     // measured: no gain (55.7 vs 55.6 us on the K = 1000 posttrans GEMM), costs 2x TMEM columns
 #endif
 #ifndef I3D_WS_PREFETCH
-#define I3D_WS_PREFETCH 4
+#define I3D_WS_PREFETCH 2     // measured 2..8: no difference (the loop is MMA-issue bound), 2 keeps registers low
 #endif
 constexpr int WS_PREFETCH = I3D_WS_PREFETCH;   // k-blocks of A held in registers per stager thread
 
@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[st]);
     };
-    // PF k-blocks of A are in flight per thread (registers): the stagers are a latency chain LDG -> STS, and with one
-    // CTA per SM only PF x 8 KB per SM are outstanding (ncu: long_scoreboard is the top stall of this kernel)
+    // PF k-blocks of A are in flight per thread (registers).  ncu shows long_scoreboard as the top stall of the stager
+    // warps, but they are not the bottleneck: with their loads removed they simply wait on mma_done instead
+    // (-DI3D_WS_EXP=2), and PF = 2..8 gives the same kernel time
     float4 va[PF][2];
     float vs[PF][2];
 #pragma unroll

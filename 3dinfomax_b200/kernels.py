@@ -92,9 +92,11 @@ class DegreePlan:
     """Device arrays of i3d_degree_plan (include/i3d.h): nodes grouped by in-degree into whole 128-row tiles."""
     CHUNK_TILES = 4        # smallest split-K chunk of the weight-gradient GEMM (4 tiles = 512 virtual rows)
 
-    def __init__(self, rowptr, n_buckets, ctas_per_chunk=8, sms=148):
+    def __init__(self, rowptr, n_buckets, ctas_per_chunk=8, sms=None):
         N = rowptr.numel() - 1
         dev = rowptr.device
+        if sms is None:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
         tiles = (N + 127) // 128
         self.n_buckets = int(n_buckets)
         # the chunked dW GEMM launches ctas_per_chunk CTAs (output tiles of the [Fout, 4F] block) per chunk: size the
