@@ -4,6 +4,7 @@ The directory name starts with a digit, so import it with ``importlib.import_mod
 Public surface = the reference's plugin names (train.py:167-208 looks classes up by name):
 
     PNA, Net3D                              model_type / model3d_type      (models/pna.py, models/net3d.py)
+    PNAOriginal                             model_type (tower PNA)         (models/pna_original.py)
     NTXent, NTXentMultiplePositives         loss_func                      (commons/losses.py)
     SelfSupervisedTrainer                   trainer: 'contrastive'         (trainer/self_supervised_trainer.py)
 
@@ -18,10 +19,11 @@ from .metrics import (ContrastiveAccuracy, NegativeSimilarity, PositiveSimilarit
 from .net3d import Net3D  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .pna import PNA  # noqa: F401
+from .pna_original import PNAOriginal  # noqa: F401
 from .trainer import CapturedStep, SelfSupervisedTrainer  # noqa: F401
 from . import lib, synthetic  # noqa: F401
 
-__all__ = ["PNA", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
+__all__ = ["PNA", "PNAOriginal", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
            "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "SelfSupervisedTrainer", "CapturedStep", "FusedAdam",
            "GraphBatch", "GraphStructure", "PackedMoleculeStore", "annotate_max_in_degree", "batch_from_numpy",
            "graph_structure", "lib", "synthetic"]

@@ -15,7 +15,7 @@ from torch import nn
 from . import ops
 from .kernels import ACT
 
-SUPPORTED_ACTIVATIONS = ("relu", "silu", "none")
+SUPPORTED_ACTIVATIONS = ("relu", "silu", "none", "leakyrelu")
 
 
 def activation_code(name):

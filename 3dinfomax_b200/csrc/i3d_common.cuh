@@ -81,6 +81,7 @@ static inline int grid_for(int64_t work, int threads, int ctas_per_sm = 8) {
 __device__ __forceinline__ float act_apply(float y, int act) {
   if (act == I3D_ACT_RELU) return y > 0.f ? y : 0.f;
   if (act == I3D_ACT_SILU) return y / (1.f + expf(-y));
+  if (act == I3D_ACT_LEAKY_RELU) return y > 0.f ? y : 0.01f * y;
   return y;
 }
 // d act(y) / dy
@@ -90,6 +91,7 @@ __device__ __forceinline__ float act_grad(float y, int act) {
     float s = 1.f / (1.f + expf(-y));
     return s * (1.f + y * (1.f - s));
   }
+  if (act == I3D_ACT_LEAKY_RELU) return y > 0.f ? 1.f : 0.01f;
   return 1.f;
 }
 

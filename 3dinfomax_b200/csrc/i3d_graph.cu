@@ -151,6 +151,32 @@ __global__ void degree_scalers_kernel(const int32_t* __restrict__ rowptr, int64_
 }
 
 
+__global__ void degree_scalers_avg_kernel(const int32_t* __restrict__ rowptr, int64_t N, double avg_d,
+                                          float* __restrict__ amp, float* __restrict__ att) {
+  pdl_grid_sync();
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < N; v += (int64_t)gridDim.x * blockDim.x) {
+    const int d = rowptr[v + 1] - rowptr[v];
+    if (d <= 0) {
+      amp[v] = 0.f, att[v] = 0.f;
+    } else {
+      const double l = log((double)d + 1.0);        // np.log(D + 1) in float64, applied as an fp32 scalar
+      amp[v] = (float)(l / avg_d);
+      att[v] = (float)(avg_d / l);
+    }
+  }
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ s, int64_t M, int F,
+                                  float* __restrict__ y, int ldy) {
+  pdl_grid_sync();
+  const int64_t total = M * F;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / F;
+    const int c = (int)(t - m * F);
+    y[m * ldy + c] = x[m * ldx + c] * __ldg(s + m);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Degree plan (models/pna.py:57-68,232): the three degree scalers of a node are functions of its in-degree D only,
 // so cat[A, A*amp_D, A*att_D] W^T == A (W_id + amp_D W_amp + att_D W_att)^T.  Grouping the nodes of a batch by D lets
@@ -293,6 +319,23 @@ int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att,
   I3D_REQUIRE(N >= 0 && rowptr && (N == 0 || (amp && att)), "invalid argument");
   if (N == 0) return I3D_OK;
   i3d::launch(i3d::degree_scalers_kernel, i3d::grid_for(N, 256), 256, 0, i3d::as_stream(stream), rowptr, N, amp, att);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_degree_scalers_avg(const int32_t* rowptr, int64_t N, double avg_d, float* amp, float* att, void* stream) {
+  I3D_REQUIRE(N >= 0 && rowptr && avg_d > 0.0 && (N == 0 || (amp && att)), "invalid argument");
+  if (N == 0) return I3D_OK;
+  i3d::launch(i3d::degree_scalers_avg_kernel, i3d::grid_for(N, 256), 256, 0, i3d::as_stream(stream), rowptr, N, avg_d,
+              amp, att);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_scale_rows(const float* x, int ldx, const float* s, int64_t M, int F, float* y, int ldy, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldx >= F && ldy >= F && (M == 0 || (x && s && y)), "invalid argument");
+  if (M == 0) return I3D_OK;
+  i3d::launch(i3d::scale_rows_kernel, i3d::grid_for(M * F, 256), 256, 0, i3d::as_stream(stream), x, ldx, s, M, F, y, ldy);
   I3D_LAUNCHED();
   return I3D_OK;
 }

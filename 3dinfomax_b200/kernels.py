@@ -10,7 +10,7 @@ import torch
 
 from . import lib as _lib
 
-ACT = {"none": 0, "relu": 1, "silu": 2}
+ACT = {"none": 0, "relu": 1, "silu": 2, "leakyrelu": 3}
 RO = {"sum": 0, "mean": 1, "max": 2, "min": 3}
 NT, NN, TN = 0, 1, 2
 
@@ -80,12 +80,29 @@ def segment_ptr(counts):
     return ptr
 
 
-def degree_scalers(rowptr):
+def degree_scalers(rowptr, avg_d=None):
+    """amp = ln(D+1) [/ avg_d], att = [avg_d] / ln(D+1); avg_d None = the hard-coded 1.0 of models/pna.py:153"""
     N = rowptr.numel() - 1
     amp = torch.empty(N, dtype=torch.float32, device=rowptr.device)
     att = torch.empty(N, dtype=torch.float32, device=rowptr.device)
-    _lib.check(_L().i3d_degree_scalers(_p(rowptr), N, _p(amp), _p(att), _s()), "i3d_degree_scalers")
+    if avg_d is None:
+        _lib.check(_L().i3d_degree_scalers(_p(rowptr), N, _p(amp), _p(att), _s()), "i3d_degree_scalers")
+    else:
+        _lib.check(_L().i3d_degree_scalers_avg(_p(rowptr), N, float(avg_d), _p(amp), _p(att), _s()),
+                   "i3d_degree_scalers_avg")
     return amp, att
+
+
+def scale_rows(x, s):
+    """y[m, :] = x[m, :] * s[m]"""
+    px, ldx = _mat(x, "x")
+    _vec(s, torch.float32, "s")
+    M, F = x.shape
+    if s.numel() != M:
+        raise ValueError("one scale per row expected")
+    y = torch.empty(M, F, dtype=torch.float32, device=x.device)
+    _lib.check(_L().i3d_scale_rows(px, ldx, _p(s), M, F, _p(y), F, _s()), "i3d_scale_rows")
+    return y
 
 
 class DegreePlan:

@@ -51,6 +51,8 @@ SIGNATURES = {
     "i3d_csr_build_i32": (_I, [_P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
     "i3d_segment_ptr": (_I, [_P, _L, _P, _P]),
     "i3d_degree_scalers": (_I, [_P, _L, _P, _P, _P]),
+    "i3d_degree_scalers_avg": (_I, [_P, _L, _D, _P, _P, _P]),
+    "i3d_scale_rows": (_I, [_P, _I, _P, _L, _I, _P, _I, _P]),
     "i3d_degree_plan": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P]),
     "i3d_posttrans_merge": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
     "i3d_gemm_nt_bucketed": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I,

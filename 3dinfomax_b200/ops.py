@@ -450,6 +450,25 @@ def broadcast_rows(vec, M):
     return _Broadcast.apply(vec, M)
 
 
+class _ScaleRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(s)
+        return K.scale_rows(x, s)
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        return K.scale_rows(g, s), None
+
+
+def scale_rows(x, s):
+    """x * s[:, None] with a per-row factor that needs no gradient (graph_norm, models/pna_original.py:258-259)."""
+    return _ScaleRows.apply(x, s.reshape(-1).contiguous())
+
+
 class _Add(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):

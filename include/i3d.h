@@ -33,6 +33,7 @@ extern "C" {
 #define I3D_ACT_NONE 0
 #define I3D_ACT_RELU 1
 #define I3D_ACT_SILU 2
+#define I3D_ACT_LEAKY_RELU 3 /* nn.LeakyReLU() default slope 0.01 (models/pna_original.py:302) */
 
 #define I3D_GEMM_NT 0 /* C[m,n] = sum_k A[m,k]   * B[n,k]   (y = x W^T: nn.Linear forward) */
 #define I3D_GEMM_NN 1 /* C[m,n] = sum_k A[m,k]   * B[k,n]   (dx = dy W)                    */
@@ -71,6 +72,11 @@ int i3d_segment_ptr(const int64_t* counts, int64_t B, int32_t* ptr, void* stream
 /* amp[v]=(float)ln(D+1), att[v]=(float)(1/ln(D+1)) with D=in-degree; both 0 for D=0.
  * scale_amplification / scale_attenuation with avg_d["log"]=1.0  [models/pna.py:61-68,153]          */
 int i3d_degree_scalers(const int32_t* rowptr, int64_t N, float* amp, float* att, void* stream);
+/* same with the SCALAR avg_d of the tower PNA: amp = (float)(ln(D+1)/avg_d), att = (float)(avg_d/ln(D+1))
+ * [models/pna_original.py:28-35]                                                                        */
+int i3d_degree_scalers_avg(const int32_t* rowptr, int64_t N, double avg_d, float* amp, float* att, void* stream);
+/* y[m, :] = x[m, :] * s[m]  (graph_norm: h * snorm_n, models/pna_original.py:258-259; its backward is the same op) */
+int i3d_scale_rows(const float* x, int ldx, const float* s, int64_t M, int F, float* y, int ldy, void* stream);
 
 /* Degree plan: the reference evaluates the posttrans FC on cat[h, A, A*amp_D, A*att_D] (13F columns,
  * models/pna.py:207,232); amp_D / att_D depend on the in-degree D only (models/pna.py:57-68), so nodes grouped by D

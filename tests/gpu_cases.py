@@ -852,6 +852,48 @@ def case_contrastive_metrics():
     return out
 
 
+# ------------------------------------------------------------------------------------ tower PNA (N2 / P11)
+def case_pna_original():
+    """PNAOriginal (towers, scalar avg_d, graph_norm, LeakyReLU mixing, MLPReadout) against the vectors emitted by the
+    reference's own models/pna_original.py (oracle/pin_pna_original.py) and the CPU oracle.  Tolerances as for PNA:
+    embeddings 1e-4 relative, parameter gradients 1e-3 of the global gradient scale."""
+    from oracle import pna_original_oracle as PO
+    from oracle.pin_pna_original import CASES as PCASES, snorm
+    from oracle.make_golden import grad_fingerprint
+    out = []
+    for name, (bseed, B, shape, wseed, avg_d, c) in PCASES.items():
+        gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        b = syn.make_batch(bseed, B, shape=shape)
+        st = PO.init_state(c, wseed)
+        sn = snorm(b["num_nodes"])
+        for mode in ("eval", "train"):
+            kw = {k: v for k, v in c.items() if k != "gru"}
+            m = i3d.PNAOriginal(avg_d=avg_d, device=DEV, **kw)
+            missing = m.load_state_dict(st, strict=True)
+            m = m.to(DEV)
+            m.train(mode == "train")
+            g2, _ = i3d.batch_from_numpy(b, DEV)
+            z = m(g2, sn)
+            tag = "%s/%s" % (name, mode)
+            out.append((tag + "/z", rel(z, gold["z_" + mode]), 1e-4))
+            if mode == "train":
+                w = torch.randn(z.shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+                (z * w).sum().backward()
+                named = dict(m.named_parameters())
+                scale = float(gold["grad_scale"])
+                worst = 0.0
+                for k, fp in zip(gold["grad_keys"], gold["grad_fp"]):
+                    mine = grad_fingerprint(named[str(k)].grad.cpu())
+                    worst = max(worst, float(np.abs(mine[2:] - fp[2:]).max()) / scale)
+                out.append((tag + "/param_grads(all, sampled)", worst, 1e-3))
+                sd = m.state_dict()
+                for k in gold.files:
+                    if k.startswith("buf/"):
+                        out.append((tag + "/" + k, rel(sd[k[4:]], gold[k]), 1e-4))
+        out.append((name + "/state_dict_keys_identical", float(len(missing.missing_keys) + len(missing.unexpected_keys)), 0))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ whole models
 def _models(s2, s3, trained=True):
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
@@ -1012,4 +1054,4 @@ from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
-             case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_sharded_equals_full]
+             case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_pna_original, case_sharded_equals_full]

@@ -107,3 +107,20 @@ def test_graph_batch_mirrors_dgl_surface():
     assert s.dtype == torch.int64 and len(s) == g2.number_of_edges() == int(g2.batch_num_edges().sum())
     assert g2.ndata["feat"].shape[1] == 9 and g2.edata["feat"].shape[1] == 3 and g3.edata["d"].shape[1] == 1
     assert g2.to("cpu").ndata["feat"].dtype == torch.int64
+
+
+def test_pna_original_state_dict_keys_match_the_oracle_layout():
+    """PNAOriginal builds on the CPU (no kernels run) and owns exactly the reference's state-dict keys / shapes: the
+    oracle state (checked against the reference model with strict=True by oracle/pin_pna_original.py) loads strictly."""
+    import importlib
+    from oracle import pna_original_oracle as PO
+    i3d = importlib.import_module("3dinfomax_b200")
+    for over in ({}, {"hidden_dim": 200, "last_layer_dim": 200, "towers": 4, "edge_hidden_dim": 200,
+                      "divide_input_first": True, "graph_norm": False}):
+        c = PO.cfg(**dict(PO.CONTRASTIVE_PNA_ORIGINAL, **over))
+        st = PO.init_state(c, 1)
+        m = i3d.PNAOriginal(avg_d=2.0, device="cpu", **{k: v for k, v in c.items() if k != "gru"})
+        res = m.load_state_dict(st, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert [k for k, _ in m.named_parameters()] == [k for k in st if not k.endswith(("running_mean", "running_var",
+                                                                                        "num_batches_tracked"))]
