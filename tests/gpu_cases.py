@@ -894,6 +894,42 @@ def case_pna_original():
     return out
 
 
+# ------------------------------------------------------------------------------------ fine-tuning head (config 5)
+def case_finetune_config():
+    """BASELINE config 5 (configs_clean/tune_QM9_homo.yml): PNA with the fine-tuning head (readout min/max/mean/sum,
+    target_dim 1, BN momentum 0.1) and L1Loss, against the vectors of the reference's own PNA (oracle/pin_finetune.py)."""
+    from oracle.pin_finetune import CASE, TUNE_QM9_HOMO, targets
+    from oracle.make_golden import grad_fingerprint
+    name, bseed, B, wseed = CASE
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    b = syn.make_batch(bseed, B)
+    c = O.pna_cfg(**TUNE_QM9_HOMO)
+    st = O.init_pna_state(c, wseed, True)
+    y = targets(B).to(DEV)
+    out = []
+    for mode in ("eval", "train"):
+        m = i3d.PNA(avg_d=1, device=DEV, **TUNE_QM9_HOMO)
+        m.load_state_dict(st)
+        m = m.to(DEV)
+        m.train(mode == "train")
+        g2, _ = i3d.batch_from_numpy(b, DEV)
+        z = m(g2)
+        loss = torch.nn.L1Loss()(z, y)                    # the reference's loss_func for this config is torch's own
+        tag = "finetune/%s" % mode
+        out += [(tag + "/prediction", rel(z, gold["z_" + mode]), 1e-4),
+                (tag + "/l1_loss", abs(loss.item() - float(gold["loss_" + mode])), 1e-5)]
+        if mode == "train":
+            loss.backward()
+            named = dict(m.named_parameters())
+            scale = float(gold["grad_scale"])
+            worst = 0.0
+            for k, fp in zip(gold["grad_keys"], gold["grad_fp"]):
+                mine = grad_fingerprint(named[str(k)].grad.cpu())
+                worst = max(worst, float(np.abs(mine[2:] - fp[2:]).max()) / scale)
+            out.append((tag + "/param_grads(all, sampled)", worst, 1e-3))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ whole models
 def _models(s2, s3, trained=True):
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
@@ -1054,4 +1090,4 @@ from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
-             case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_pna_original, case_sharded_equals_full]
+             case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_pna_original, case_finetune_config, case_sharded_equals_full]

@@ -114,3 +114,30 @@ def test_contrastive_metrics_oracle_matches_reference_vectors(golden_dir):
         x1, x2 = embeddings(seed, B, D, noisy)
         got = O.contrastive_metrics(x1, x2, thr).numpy()
         assert np.array_equal(got, g[name + "/ref"]), name
+
+
+def test_finetune_config_oracle_matches_reference_vectors(golden_dir):
+    """BASELINE config 5: the oracle with the fine-tuning head against the reference's own PNA (oracle/pin_finetune.py)."""
+    from oracle.pin_finetune import CASE, TUNE_QM9_HOMO, targets
+    name, bseed, B, wseed = CASE
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    b = syn.make_batch(bseed, B)
+    g2, xa, ea, _, _ = O.graphs_from_batch(b)
+    c = O.pna_cfg(**TUNE_QM9_HOMO)
+    st = O.init_pna_state(c, wseed, True)
+    z = O.pna_forward(O.as_leaf_params(st), c, g2, xa, ea, False)
+    assert np.abs(z.detach().numpy() - g["z_eval"]).max() == 0.0
+    loss = torch.nn.functional.l1_loss(z, targets(B))
+    assert abs(loss.item() - float(g["loss_eval"])) <= 1e-6
+
+
+def test_pna_original_oracle_matches_reference_vectors(golden_dir):
+    from oracle import pna_original_oracle as PO
+    from oracle.pin_pna_original import CASES as PCASES, snorm
+    for name, (bseed, B, shape, wseed, avg_d, c) in PCASES.items():
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        b = syn.make_batch(bseed, B, shape=shape)
+        g2, xa, ea, _, _ = O.graphs_from_batch(b)
+        st = PO.init_state(c, wseed)
+        z = PO.forward(O.as_leaf_params(st), c, g2, xa, ea, snorm(b["num_nodes"]), avg_d, False)
+        assert np.abs(z.detach().numpy() - g["z_eval"]).max() == 0.0, name
