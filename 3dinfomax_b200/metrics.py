@@ -4,7 +4,8 @@
 (trainer/metrics.py:240-334,444-463) are what configs_clean/pre-train_QM9.yml:15-20 logs.  The reference evaluates each
 one separately — five ``einsum('ik,jk->ij')`` over the same embeddings plus [B,B] masks — here the five share ONE
 similarity GEMM and ONE pass over it (``i3d_contrastive_metrics``): the first metric called on a pair of embedding
-tensors computes all five, the others read the cached device vector (no host sync anywhere).
+tensors with a given threshold computes all five, the others read the cached device vector (no host sync anywhere;
+the threshold-free similarities default to 0.5, so a config with threshold 0.5009 costs two fused evaluations).
 
 Only the global-vs-global case (``pos_mask is None``) that the target configs use has a kernel; a ``pos_mask`` raises.
 """
