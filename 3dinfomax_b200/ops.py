@@ -23,7 +23,7 @@ from . import kernels as K
 # ---------------------------------------------------------------------------------------------------------------
 _dw_lock = threading.Lock()
 _dw_streams = {}          # device index -> side stream
-_dw_join_pending = {}     # device index -> a join callback is queued for the running backward()
+_dw_join_pending = set()  # (device index, autograd graph-task id): a join callback is queued for that backward()
 DW_MIN_ROWS = int(os.environ.get("I3D_DW_MIN_ROWS", "2048"))     # smaller GEMMs stay on the main stream
 
 
@@ -34,15 +34,21 @@ def _dw_min_rows():
 def _dw_fork(device, main, used):
     """Side stream ordered after everything enqueued on ``main`` so far, or None.  ``used``: tensors the side work
     reads that may be freed while it still runs (caching-allocator bookkeeping).  Backward nodes run on autograd's
-    worker thread, the end-of-backward callback on the thread that called backward(): state is global, not thread-local."""
+    worker thread, the end-of-backward callback on the thread that called backward(): state is global, not
+    thread-local, and the "join queued" flag is per backward() call (graph task), so concurrent backward passes of
+    several trainers on one GPU (train.py --multithreaded_seeds) each get their own join."""
     if os.environ.get("I3D_DW_STREAM", "1") == "0":
         return None
+    task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else -1
+    if task < 0:
+        return None                       # not inside backward(): nothing would join the side stream
+    key = (device.index, task)
     with _dw_lock:
         side = _dw_streams.get(device.index)
         if side is None:
             side = _dw_streams[device.index] = torch.cuda.Stream(device=device)
-        queue = not _dw_join_pending.get(device.index, False)
-        _dw_join_pending[device.index] = True
+        queue = key not in _dw_join_pending
+        _dw_join_pending.add(key)
     side.wait_stream(main)
     for t in used:
         if t is not None:
@@ -50,7 +56,7 @@ def _dw_fork(device, main, used):
     if queue:
         def join():
             with _dw_lock:
-                _dw_join_pending[device.index] = False
+                _dw_join_pending.discard(key)
             torch.cuda.current_stream(device).wait_stream(side)
 
         torch.autograd.Variable._execution_engine.queue_callback(join)      # runs when this backward() finishes
