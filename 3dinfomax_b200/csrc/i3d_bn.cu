@@ -150,8 +150,11 @@ constexpr int kColBatch = 4;
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
     bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
-                         int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2) {
+                         int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2,
+                         float* __restrict__ zero_buf, int zero_n) {
   pdl_grid_sync();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_buf[i] = 0.f;
   const int FV = F / V;
   const ColMap m = col_map(FV);
   double acc[2][V];
@@ -397,25 +400,36 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
   return I3D_OK;
 }
 
-int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
-                      const float* save_mean_rstd, double* sums2, void* stream) {
-  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && sums2 && save_mean_rstd && (M == 0 || (Y && dO)),
+int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                         const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && sums2 && save_mean_rstd && (M == 0 || (Y && dO)) &&
+                  zero_n >= 0 && (zero_n == 0 || zero_buf),
               "invalid argument");
   cudaStream_t s = as_stream(stream);
-  I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F, s));
-  if (M == 0) return I3D_OK;
+  const bool prezeroed = (act & I3D_STATS_PREZEROED) != 0;
+  act &= 0xff;
+  if (!prezeroed) I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F, s));
+  if (M == 0) {
+    if (zero_n > 0) I3D_CUDA(cudaMemsetAsync(zero_buf, 0, sizeof(float) * zero_n, s));
+    return I3D_OK;
+  }
   const bool v4 = can_vec4({Y, dO}, {F, ldy, ldd});
   const int V = v4 ? 4 : 1, FV = F / V;
   I3D_REQUIRE(FV <= kColThreads, "feature width too large");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
   if (v4)
     launch(bn_bwd_reduce_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2);
+                                                                      sums2, zero_buf, zero_n);
   else
     launch(bn_bwd_reduce_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2);
+                                                                      sums2, zero_buf, zero_n);
   I3D_LAUNCHED();
   return I3D_OK;
+}
+
+int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                      const float* save_mean_rstd, double* sums2, void* stream) {
+  return i3d_bn_bwd_reduce_ex(dO, ldd, Y, ldy, M, F, act, save_mean_rstd, sums2, nullptr, 0, stream);
 }
 
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,

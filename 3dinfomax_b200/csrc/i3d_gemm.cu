@@ -363,7 +363,9 @@ extern "C" int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm
     I3D_REQUIRE(segs[s].K > 0 && (segs[s].K & 3) == 0 && (segs[s].lda & 3) == 0 && segs[s].A && !segs[s].b_idx &&
                     !segs[s].scale && (reinterpret_cast<uintptr_t>(segs[s].A) & 15u) == 0,
                 "segments must be 16-byte aligned, unscaled, with K a multiple of 4");
-  if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+  const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
+  stats_act &= 0xff;
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
   return gemm_ws_nt_bucketed(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, b_pitch, n_buckets, tile_bucket, row_map,
                              col_stats, stats_act, as_stream(stream));
 }
@@ -407,7 +409,9 @@ extern "C" int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_
   if (M == 0 || N == 0) return I3D_OK;
   I3D_REQUIRE(C != nullptr, "C is null");
   I3D_REQUIRE(i3d_gemm_nt_prepared_ok(M, N, n_seg, segs), "shape not eligible for prepared operands");
-  if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+  const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
+  stats_act &= 0xff;
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
   return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, const_cast<void*>(ws), col_stats, stats_act,
                     as_stream(stream), true);
 }
@@ -421,6 +425,8 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
                            const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats,
                            int stats_act, void* stream) {
   I3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be NT, NN or TN");
+  const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
+  stats_act &= 0xff;
   I3D_REQUIRE(!col_stats || (mode == I3D_GEMM_NT && !accumulate), "col_stats needs NT mode without accumulate");
   I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N, "invalid shape");
   if (M == 0 || N == 0) return I3D_OK;
@@ -431,7 +437,7 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
   if (g_gemm_backend != 1 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
-    if (col_stats) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+    if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
     return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act,
                    as_stream(stream));
   }

@@ -15,6 +15,43 @@ RO = {"sum": 0, "mean": 1, "max": 2, "min": 3}
 NT, NN, TN = 0, 1, 2
 
 
+STATS_PREZEROED = 0x100      # I3D_STATS_PREZEROED (include/i3d.h)
+
+
+class StatsArena:
+    """fp64 scratch for the BatchNorm statistics of ONE training step, zeroed by ONE memset at the start of the step.
+
+    Every FC layer needs a zeroed [2F] fp64 buffer in the forward (column sums from the GEMM epilogue) and another in
+    the backward; zeroing each one separately costs ~50 memset nodes per step, each of which also breaks programmatic
+    dependent launch between its neighbours.  ``take`` hands out consecutive slices (host-side bump pointer); the
+    slices are only valid until the next ``reset`` and never escape the operator that took them."""
+
+    def __init__(self, device, doubles=1 << 17):
+        self.buf = torch.zeros(doubles, dtype=torch.float64, device=device)
+        self.used = 0
+        self.lock = __import__("threading").Lock()
+
+    def reset(self):
+        self.buf.zero_()                       # one memset node (1 MB) per step
+        self.used = 0
+
+    def take(self, n):
+        with self.lock:
+            if self.used + n > self.buf.numel():
+                return None                    # exhausted: the caller falls back to its own buffer + memset
+            out = self.buf[self.used:self.used + n]
+            self.used += n
+            return out
+
+
+def _stats_buffer(arena, n, device):
+    """(buffer, flag): a pre-zeroed arena slice when there is one, else a fresh tensor the library zeroes itself"""
+    t = arena.take(n) if arena is not None else None
+    if t is not None:
+        return t, STATS_PREZEROED
+    return torch.empty(n, dtype=torch.float64, device=device), 0
+
+
 def _L():
     return _lib.load()
 
@@ -160,15 +197,17 @@ class MergedPosttransWeights:
                    "i3d_posttrans_merge")
 
 
-def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None):
+def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None, arena=None):
     b_pitch = b_hi.shape[1]
     """C[plan.perm[m], :] = bias + sum_s A_s[a_idx_s[m] or m, :] @ B[bucket(m)]^T over the plan's virtual rows."""
     pc, ldc = _mat(C, "C")
     arr = _seg_array(segs, need_b=False)
-    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
+    stats, flag = (None, 0)
+    if stats_act is not None:
+        stats, flag = _stats_buffer(arena, 2 * N, C.device)
     _lib.check(_L().i3d_gemm_nt_bucketed(plan.Mv, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
                                          _p(b_hi), _p(b_lo), b_pitch, plan.n_buckets, _p(plan.tile_bucket), _p(plan.perm),
-                                         _p(stats), 0 if stats_act is None else stats_act, _s()),
+                                         _p(stats), 0 if stats_act is None else (stats_act | flag), _s()),
                "i3d_gemm_nt_bucketed")
     return C if stats_act is None else (C, stats)
 
@@ -234,27 +273,29 @@ def _seg_array(segs, need_b=True):
     return arr
 
 
-def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepared=None):
+def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepared=None, arena=None):
     """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld).
     stats_act: activation code -> also returns fp64 [2N] column sums of act(C), act(C)^2 (fused BatchNorm statistics).
     prepared: a ready ``PreparedB`` (NT only): B comes from its scratch, the segments need no "B"."""
     pc, ldc = _mat(C, "C")
     L = _L()
-    stats = torch.empty(2 * N, dtype=torch.float64, device=C.device) if stats_act is not None else None
+    stats, flag = (None, 0)
+    if stats_act is not None:
+        stats, flag = _stats_buffer(arena, 2 * N, C.device)
     if prepared is not None:
         if mode != NT:
             raise ValueError("prepared operands are for NT GEMMs")
         arr = _seg_array(segs, need_b=False)
         _lib.check(L.i3d_gemm_nt_prepared(M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
                                           1 if accumulate else 0, _p(prepared.ws), _p(stats),
-                                          0 if stats_act is None else stats_act, _s()), "i3d_gemm_nt_prepared")
+                                          0 if stats_act is None else (stats_act | flag), _s()), "i3d_gemm_nt_prepared")
         return C if stats_act is None else (C, stats)
     arr = _seg_array(segs)
     nws = int(L.i3d_gemm_ws_bytes(mode, M, N, len(segs), arr))
     ws = torch.empty(nws, dtype=torch.uint8, device=C.device) if nws else None      # tf32 hi/lo copies of B for TMA
     _lib.check(L.i3d_gemm_ex(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                             1 if accumulate else 0, _p(ws), nws, _p(stats), 0 if stats_act is None else stats_act,
-                             _s()), "i3d_gemm")
+                             1 if accumulate else 0, _p(ws), nws, _p(stats),
+                             0 if stats_act is None else (stats_act | flag), _s()), "i3d_gemm")
     return C if stats_act is None else (C, stats)
 
 
@@ -367,22 +408,29 @@ def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum
     return O, save
 
 
-def bn_bwd_reduce(dO, Y, act, save):
+def bn_bwd_reduce(dO, Y, act, save, arena=None, zero=None):
+    """zero: optional fp32 tensor the kernel clears on the way (the dbias accumulator of the following bn_bwd_apply)"""
     pd, ldd = _mat(dO, "dO")
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
-    sums2 = torch.empty(2 * F, dtype=torch.float64, device=Y.device)
-    _lib.check(_L().i3d_bn_bwd_reduce(pd, ldd, py, ldy, M, F, act, _p(save), _p(sums2), _s()), "i3d_bn_bwd_reduce")
+    sums2, flag = _stats_buffer(arena, 2 * F, Y.device)
+    _lib.check(_L().i3d_bn_bwd_reduce_ex(pd, ldd, py, ldy, M, F, act | flag, _p(save), _p(sums2), _p(zero),
+                                         0 if zero is None else zero.numel(), _s()), "i3d_bn_bwd_reduce")
     return sums2
 
 
-def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True):
+def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True, dbias_zeroed=None):
     pd, ldd = _mat(dO, "dO")
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
     dev = Y.device
     dY = torch.empty(M, F, dtype=torch.float32, device=dev)
-    dbias = torch.zeros(F, dtype=torch.float32, device=dev) if want_dbias else None
+    if not want_dbias:
+        dbias = None
+    elif dbias_zeroed is not None:
+        dbias = dbias_zeroed                     # cleared by the preceding bn_bwd_reduce
+    else:
+        dbias = torch.zeros(F, dtype=torch.float32, device=dev)
     dgamma = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     _lib.check(_L().i3d_bn_bwd_apply(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "i3d_act_colstats": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "i3d_bn_apply": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),
     "i3d_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P]),
+    "i3d_bn_bwd_reduce_ex": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P]),
     "i3d_bn_bwd_apply": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "i3d_act_fwd": (_I, [_P, _L, _I, _P, _P]),
     "i3d_act_bwd": (_I, [_P, _P, _L, _I, _P, _P]),

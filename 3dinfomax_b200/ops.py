@@ -124,7 +124,8 @@ class _FC(torch.autograd.Function):
         sums = None
         if cfg.has_bn and cfg.training:
             # statistics from the GEMM epilogue
-            _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act, prepared=ready)
+            _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act, prepared=ready,
+                             arena=getattr(W, "_i3d_arena", None))
         else:
             K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, prepared=ready)
         if cfg.has_bn:
@@ -153,8 +154,11 @@ class _FC(torch.autograd.Function):
         need_b = ctx.needs_input_grad[2]
         dgamma = dbeta = None
         if cfg.has_bn:
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save)
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b)
+            arena = getattr(ctx.w_param, "_i3d_arena", None)
+            dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz)
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
+                                                   dbias_zeroed=dbz)
         elif cfg.act != 0:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
         else:
@@ -259,7 +263,8 @@ class _FCPostMerged(torch.autograd.Function):
         segs = [{"A": h, "K": F, "a_idx": plan.perm}, {"A": agg, "K": 4 * F, "a_idx": plan.perm}]
         sums = save = None
         if cfg.has_bn and cfg.training:
-            _, sums = K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo, stats_act=cfg.act)
+            _, sums = K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo, stats_act=cfg.act,
+                                         arena=getattr(W, "_i3d_arena", None))
         else:
             K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo)
         if cfg.has_bn:
@@ -285,8 +290,11 @@ class _FCPostMerged(torch.autograd.Function):
         need_b = ctx.needs_input_grad[4]
         dgamma = dbeta = None
         if cfg.has_bn:
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save)
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b)
+            arena = getattr(ctx.w_param, "_i3d_arena", None)
+            dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz)
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
+                                                   dbias_zeroed=dbz)
         elif cfg.act != 0:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
         else:

@@ -17,7 +17,7 @@ import torch
 
 from . import dist as D
 from .graph import GraphBatch
-from .kernels import WeightPrep
+from .kernels import StatsArena, WeightPrep
 from .optim import FusedAdam
 
 
@@ -48,12 +48,16 @@ class SelfSupervisedTrainer:
                                **optimizer_params)
         # FC weights get their tf32 hi/lo operand copies (plain and transposed) from one launch per step
         self.prep = WeightPrep(self.device)
+        # BatchNorm statistics scratch of the whole step, zeroed by one memset at the start of forward_pass
+        self.arena = StatsArena(self.device)
         for _, v in named:
             if getattr(v, "_i3d_direct_grad", False):
                 v._i3d_prep = self.prep
+                v._i3d_arena = self.arena
         self.optim.post_step_hooks.append(self.prep.invalidate)
 
     def forward_pass(self, batch):
+        self.arena.reset()
         self.prep.refresh()
         info2d, info3d, *rest = tuple(batch)
         if self.stream3d is not None:

@@ -157,6 +157,11 @@ int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, fl
  * i3d_gemm_ws_bytes returns 0 for problems that do not use scratch.
  */
 size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
+/* OR into `stats_act` (GEMM entry points) or `act` (i3d_bn_bwd_reduce*) when the fp64 statistics buffer handed in is
+ * ALREADY ZERO: the library then skips its own cudaMemsetAsync.  A caller that owns an arena zeroed once per step saves
+ * ~50 memset nodes per training step this way (each one also breaks programmatic dependent launch between its
+ * neighbours). */
+#define I3D_STATS_PREZEROED 0x100
 /* col_stats (optional, NT without accumulate): fp64 [2N] = column sums of act(C) and act(C)^2, i.e. the train-mode
  * BatchNorm statistics of the FCLayer tail, produced by the GEMM epilogue instead of a separate pass over C. */
 int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
@@ -230,6 +235,10 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
 /* sums2[0:F]=sum dO, sums2[F:2F]=sum dO*xhat (fp64; zeroed inside) */
 int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                       const float* save_mean_rstd, double* sums2, void* stream);
+/* same; additionally sets zero_buf[0:zero_n] = 0 (fp32) — the bias-gradient accumulator the following
+ * i3d_bn_bwd_apply adds into, so that no separate fill kernel sits between the two */
+int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                         const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n, void* stream);
 /* dY = act'(Y) * gamma*rstd*(dO - mean(dO) - xhat*mean(dO*xhat))   (training)  |  act'(Y)*gamma*rstd*dO (eval)
  * has_bn==0: dY = act'(Y)*dO.  dbias[F] (caller-zeroed) += sum_rows dY; dgamma/dbeta[F] written.      */
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
