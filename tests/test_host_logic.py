@@ -124,3 +124,21 @@ def test_pna_original_state_dict_keys_match_the_oracle_layout():
         assert not res.missing_keys and not res.unexpected_keys
         assert [k for k, _ in m.named_parameters()] == [k for k in st if not k.endswith(("running_mean", "running_var",
                                                                                         "num_batches_tracked"))]
+
+
+def test_stats_arena_bump_allocator():
+    """StatsArena host logic (runs on CPU tensors): consecutive zeroed slices, exhaustion -> None, reset re-zeroes."""
+    import importlib
+    import torch
+    K = importlib.import_module("3dinfomax_b200.kernels")
+    a = K.StatsArena("cpu", doubles=1000)
+    s1, s2 = a.take(400), a.take(400)
+    assert s1.data_ptr() + 400 * 8 == s2.data_ptr() and float(s1.abs().sum() + s2.abs().sum()) == 0.0
+    assert a.take(400) is None                      # exhausted: callers fall back to their own buffer + memset
+    s1.fill_(3.0)
+    a.reset()
+    assert a.used == 0 and float(a.buf.abs().sum()) == 0.0
+    buf, flag = K._stats_buffer(a, 400, "cpu")
+    assert flag == K.STATS_PREZEROED and buf.data_ptr() == a.buf.data_ptr()
+    buf2, flag2 = K._stats_buffer(None, 400, "cpu")
+    assert flag2 == 0 and buf2.numel() == 400
