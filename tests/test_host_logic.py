@@ -142,3 +142,42 @@ def test_stats_arena_bump_allocator():
     assert flag == K.STATS_PREZEROED and buf.data_ptr() == a.buf.data_ptr()
     buf2, flag2 = K._stats_buffer(None, 400, "cpu")
     assert flag2 == 0 and buf2.numel() == 400
+
+
+def test_graph_batch_carries_the_degree_hint():
+    """max_in_degree (host int that sizes the degree plan) survives pin_memory() / to() and is computed by
+    batch_from_numpy; graphs without a hint keep None (generic posttrans path)."""
+    import importlib
+    import numpy as np
+    import torch
+    i3d = importlib.import_module("3dinfomax_b200")
+    b = i3d.synthetic.make_batch(3, 5)
+    g2, g3 = i3d.batch_from_numpy(b, "cpu")
+    assert g2.max_in_degree == int(np.bincount(b["dst"]).max()) and g3.max_in_degree is None
+    assert g2.to("cpu").max_in_degree == g2.max_in_degree
+    plain = i3d.GraphBatch(torch.from_numpy(b["src"]), torch.from_numpy(b["dst"]), torch.from_numpy(b["num_nodes"]))
+    assert plain.max_in_degree is None
+    assert i3d.annotate_max_in_degree(plain) == g2.max_in_degree and plain.max_in_degree == g2.max_in_degree
+
+
+def test_degree_plan_reference_layout():
+    """the numpy restatement of i3d_degree_plan used by the GPU tests: every node appears once, buckets own whole
+    tiles, chunks never cross a bucket"""
+    import numpy as np
+    from gpu_cases_plan_ref import degree_plan_ref
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 5, size=1000)
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    perm, tile_bucket, chunk, over = degree_plan_ref(rowptr, 5, 4)
+    assert over == 0 and sorted(perm[perm >= 0].tolist()) == list(range(1000))
+    for t, bk in enumerate(tile_bucket):
+        rows = perm[t * 128:(t + 1) * 128]
+        rows = rows[rows >= 0]
+        if bk < 0:
+            assert len(rows) == 0
+        else:
+            assert (deg[rows] == bk).all()
+    for r0, n, bk in chunk.reshape(-1, 3):
+        if n:
+            assert r0 % 128 == 0 and n % 128 == 0 and n <= 4 * 128
+            assert set(tile_bucket[r0 // 128:(r0 + n) // 128].tolist()) == {bk}
