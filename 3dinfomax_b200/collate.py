@@ -5,7 +5,7 @@ The reference builds every batch in Python: B calls of ``QM9Dataset.__getitem__`
 ``contrastive_collate`` = ``dgl.batch`` (datasets/custom_collate.py:105-114), then a host->device copy of both graphs
 (4.8 MB per batch of 512 QM9 molecules).  Here the store of the reference's processed file
 (qm9_dataset.py:454-467) lives in HBM, and a step uploads ONLY the molecule indices plus three offset arrays
-(one pinned buffer, ~16 KB at B = 512); two kernels (i3d_collate_2d / i3d_collate_3d) emit the batched graphs in the
+(one pinned buffer, 29 KB at B = 512); two kernels (i3d_collate_2d / i3d_collate_3d) emit the batched graphs in the
 reference's exact node / edge order, with the 3-D complete graphs and their distances generated implicitly.
 
     store = PackedMoleculeStore(store_dict, device)          # store_dict: numpy arrays, see synthetic.make_store
