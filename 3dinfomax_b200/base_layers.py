@@ -65,16 +65,16 @@ class FCLayer(nn.Module):
             self.linear.weight.uniform_(-bound, bound)
             self.linear.bias.zero_()
 
-    def forward(self, segs, residual=None):
+    def forward(self, segs, residual=None, valid=None):
         if torch.is_tensor(segs):
             segs = [ops.Seg(segs)]
         bn = None
         if self.batch_norm is not None:
             b = self.batch_norm
             bn = (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
-        return ops.fc(segs, self.linear.weight, self.linear.bias, self.act, bn, self.training, residual)
+        return ops.fc(segs, self.linear.weight, self.linear.bias, self.act, bn, self.training, residual, valid)
 
-    def forward_merged(self, plan, h, agg, residual=None):
+    def forward_merged(self, plan, h, agg, residual=None, valid=None):
         """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""
         from .kernels import MergedPosttransWeights
         W = self.linear.weight
@@ -89,7 +89,7 @@ class FCLayer(nn.Module):
         if self.batch_norm is not None:
             b = self.batch_norm
             bn = (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
-        return ops.fc_post_merged(plan, m, h, agg, W, self.linear.bias, self.act, bn, self.training, residual)
+        return ops.fc_post_merged(plan, m, h, agg, W, self.linear.bias, self.act, bn, self.training, residual, valid)
 
 
 class MLP(nn.Module):
@@ -108,9 +108,10 @@ class MLP(nn.Module):
             fcs.append(FCLayer(hidden_size, out_dim, last_activation, dropout, last_batch_norm, batch_norm_momentum))
         self.fully_connected = nn.ModuleList(fcs)
 
-    def forward(self, segs, residual=None):
+    def forward(self, segs, residual=None, valid=None):
+        """valid: device int32 scalar — valid leading rows when the batch is padded to a shape bucket (ops.FCConfig)"""
         x = segs
         last = len(self.fully_connected) - 1
         for i, fcl in enumerate(self.fully_connected):
-            x = fcl(x, residual if i == last else None)
+            x = fcl(x, residual if i == last else None, valid)
         return x

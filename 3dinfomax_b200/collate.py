@@ -18,9 +18,56 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .graph import GraphBatch
+from .graph import GraphBatch, GraphStructure
 
 _FIELDS = ("n_atoms", "atom_slices", "edge_slices", "edge_indices", "atom_features", "edge_features", "coordinates")
+
+
+class _StagingRing:
+    """Pinned host buffers for the per-batch metadata, each guarded by a CUDA event: a slot is rewritten only after
+    the host->device copy that last read it has completed.  (One buffer per batch size, rewritten every call, lets
+    the host overwrite the pinned memory of batch k while its asynchronous copy is still queued behind earlier GPU
+    work — the kernels of batch k would then see the indices of batch k+1.)"""
+
+    def __init__(self, n, slots=4):
+        self.slots = [(torch.empty(n, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(slots)]
+        self.used = [False] * slots
+        self.next = 0
+
+    def acquire(self):
+        i = self.next
+        self.next = (i + 1) % len(self.slots)
+        host, ev = self.slots[i]
+        if self.used[i]:
+            ev.synchronize()
+        self.used[i] = True
+        return host, ev
+
+
+def local_csr(n_atoms, atom_slices, edge_slices, edge_indices):
+    """Molecule-local CSR arrays of a packed store (host, numpy, once per store; int32):
+    in_rowptr_l[Ntot]   in-edges of the earlier atoms of the same molecule
+    in_eid_l[Etot]      local edge id held by local CSR position p (destination-sorted, edge-id stable)
+    out_rowptr_l[Ntot]  same for the CSR-ordered edges sorted by source
+    out_pos_l[Etot]     local CSR position held by local out-slot s
+    dgl.batch only offsets ids, so the CSR of any batch is these arrays plus the batch offsets (i3d_collate_2d_struct)."""
+    M = len(n_atoms)
+    n_edges = np.diff(edge_slices)
+    mol_of_edge = np.repeat(np.arange(M), n_edges)
+    mol_of_atom = np.repeat(np.arange(M), n_atoms)
+    a0, e0 = atom_slices[:-1], edge_slices[:-1]
+    gsrc = edge_indices[0] + a0[mol_of_edge]
+    gdst = edge_indices[1] + a0[mol_of_edge]
+    order = np.argsort(gdst, kind="stable")                      # store edge id at global CSR position
+    in_eid_l = order - e0[mol_of_edge]                           # position p and edge order[p] share the molecule
+    atoms = np.arange(int(atom_slices[-1]))
+    in_rowptr_l = np.searchsorted(gdst[order], atoms, side="left") - e0[mol_of_atom]
+    src_csr = gsrc[order]
+    order2 = np.argsort(src_csr, kind="stable")                  # CSR position at global out-slot
+    out_pos_l = order2 - e0[mol_of_edge]
+    out_rowptr_l = np.searchsorted(src_csr[order2], atoms, side="left") - e0[mol_of_atom]
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return i32(in_rowptr_l), i32(in_eid_l), i32(out_rowptr_l), i32(out_pos_l)
 
 
 class PackedMoleculeStore:
@@ -57,33 +104,50 @@ class PackedMoleculeStore:
         self.atom_features = t(store["atom_features"], np.int64)
         self.edge_features = t(store["edge_features"], np.int64)
         self.coordinates = t(store["coordinates"], np.float32)
+        # conformers: [Ntot, 3*C] fp32, conformer c in columns [3c, 3c+3) (datasets/qmugs_dataset.py `conformations`);
+        # absent = the single conformer of `coordinates` (QM9)
+        conf = store.get("conformations") if hasattr(store, "get") else None
+        self.conformations = self.coordinates if conf is None else t(conf, np.float32)
+        self.n_conformers = int(self.conformations.shape[1]) // 3
         self.CA = int(self.atom_features.shape[1])
         self.CE = int(self.edge_features.shape[1])
+        # molecule-local CSR arrays: the structure of a batch is emitted by the collate kernel without any sort
+        lc = local_csr(self.n_atoms, self.atom_slices_h, self.edge_slices_h, ei)
+        self.in_rowptr_l, self.in_eid_l, self.out_rowptr_l, self.out_pos_l = (torch.from_numpy(a).to(device) for a in lc)
+        self.max_in_degree_all = int(self.max_in_degree.max()) if self.M else 0
         self._staging = {}
 
     def __len__(self):
         return self.M
 
     def _stage(self, B):
-        """pinned host + device buffer holding the per-batch metadata (layout of ``batch_metadata``)"""
+        """event-guarded ring of pinned host buffers for the per-batch metadata (layout of ``batch_metadata``)"""
         st = self._staging.get(B)
         if st is None:
-            n = metadata_len(B)
-            st = (torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.int64, device=self.device))
-            self._staging[B] = st
+            st = self._staging[B] = _StagingRing(metadata_len(B))
         return st
 
-    def collate(self, idx):
-        """Batched (2-D bond graph, 3-D complete graph) of molecules ``idx`` — contrastive_collate of the reference."""
+    def stage_metadata(self, idx, dev_out=None):
+        """Host part of a batch: validate ``idx``, fill a pinned metadata buffer and enqueue its copy to the device
+        (the ONLY host->device traffic of the batch).  Returns (device metadata buffer, (N, E, E3))."""
         idx = np.ascontiguousarray(np.asarray(idx), dtype=np.int64).reshape(-1)
         B = int(len(idx))
         if B == 0:
             raise ValueError("empty batch")
         if idx.min() < 0 or idx.max() >= self.M:
             raise IndexError("molecule index out of range [0, %d)" % self.M)
-        host, dev = self._stage(B)
-        N, E, E3 = batch_metadata(host.numpy(), idx, self.n_atoms, self.n_edges)
-        dev.copy_(host, non_blocking=True)                       # the ONLY host->device traffic of the batch
+        host, ev = self._stage(B).acquire()
+        sizes = batch_metadata(host.numpy(), idx, self.n_atoms, self.n_edges)
+        dev = torch.empty(metadata_len(B), dtype=torch.int64, device=self.device) if dev_out is None else dev_out
+        dev.copy_(host, non_blocking=True)
+        ev.record()                                  # the pinned slot is free again once this copy has run
+        return dev, sizes
+
+    def collate(self, idx):
+        """Batched (2-D bond graph, 3-D complete graph) of molecules ``idx`` — contrastive_collate of the reference."""
+        idx = np.ascontiguousarray(np.asarray(idx), dtype=np.int64).reshape(-1)
+        B = int(len(idx))
+        dev, (N, E, E3) = self.stage_metadata(idx)               # fresh device buffer per batch
         v = metadata_views(dev, B)
         i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=self.device)
         src, dst, x_atom, e_attr = i64(E), i64(E), i64(N, self.CA), i64(E, self.CE)
@@ -98,11 +162,57 @@ class PackedMoleculeStore:
                    "i3d_collate_2d")
         _lib.check(L.i3d_collate_3d(p(v["idx"]), B, p(self.atom_slices), p(self.coordinates), p(v["node_ptr"]),
                                     p(v["edge3_ptr"]), E3, p(src3), p(dst3), p(d3), s), "i3d_collate_3d")
-        # the count tensors are fresh copies: the staging buffer is overwritten by the next batch of this size
-        g2 = GraphBatch(src, dst, v["num_nodes"].clone(), v["num_edges"].clone(), {"feat": x_atom}, {"feat": e_attr}, N,
+        g2 = GraphBatch(src, dst, v["num_nodes"], v["num_edges"], {"feat": x_atom}, {"feat": e_attr}, N,
                         max_in_degree=int(self.max_in_degree[idx].max()))
-        g3 = GraphBatch(src3, dst3, v["num_nodes"].clone(), v["num_edges3"].clone(), {}, {"d": d3}, N)
+        g3 = GraphBatch(src3, dst3, v["num_nodes"], v["num_edges3"], {}, {"d": d3}, N)
         return g2, g3
+
+    def collate_padded(self, meta, B, n_cap, e_cap, e3_cap, conformers=1):
+        """Kernel-only part of a shape-bucketed batch (CUDA-graph capturable): from the DEVICE metadata buffer ``meta``
+        (stage_metadata) emit both graphs padded to the bucket capacities, together with their CSR structures
+        (i3d_collate_2d_struct / i3d_collate_3d_struct: no sort, no atomics).  Valid sizes stay on the device."""
+        C = int(conformers)
+        if C < 1 or C > self.n_conformers:
+            raise ValueError("store holds %d conformer(s) per molecule, %d requested" % (self.n_conformers, C))
+        v = metadata_views(meta, B)
+        dev = self.device
+        i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=dev)
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        n3_cap = C * n_cap
+        src, dst, x_atom, e_attr = i64(e_cap), i64(e_cap), i64(n_cap, self.CA), i64(e_cap, self.CE)
+        rowptr, out_rowptr, graph_ptr = i32(n_cap + 1), i32(n_cap + 1), i32(B + 1)
+        src_csr, dst_csr, eid, out_pos = i32(e_cap), i32(e_cap), i32(e_cap), i32(e_cap)
+        src3, dst3 = i64(e3_cap), i64(e3_cap)
+        d3 = torch.empty(e3_cap, 1, dtype=torch.float32, device=dev)
+        rowptr3, graph_ptr3, nn3 = i32(n3_cap + 1), i32(B * C + 1), i64(B * C)
+        src_csr3, dst_csr3, eid3, out_pos3 = i32(e3_cap), i32(e3_cap), i32(e3_cap), i32(e3_cap)
+        L = _lib.load()
+        s = torch.cuda.current_stream().cuda_stream
+        p = lambda t: t.data_ptr()
+        _lib.check(L.i3d_collate_2d_struct(p(v["idx"]), B, p(self.atom_slices), p(self.edge_slices), p(self.edge_indices),
+                                           self.Etot, p(self.atom_features), self.CA, p(self.edge_features), self.CE,
+                                           p(self.in_rowptr_l), p(self.in_eid_l), p(self.out_rowptr_l),
+                                           p(self.out_pos_l), p(v["node_ptr"]), p(v["edge_ptr"]), n_cap, e_cap, p(src),
+                                           p(dst), p(x_atom), p(e_attr), p(rowptr), p(src_csr), p(dst_csr), p(eid),
+                                           p(out_rowptr), p(out_pos), p(graph_ptr), s), "i3d_collate_2d_struct")
+        _lib.check(L.i3d_collate_3d_struct(p(v["idx"]), B, C, p(self.atom_slices), p(self.conformations),
+                                           int(self.conformations.shape[1]), p(v["node_ptr"]), p(v["edge3_ptr"]), n3_cap,
+                                           e3_cap, p(src3), p(dst3), p(d3), p(rowptr3), p(src_csr3), p(dst_csr3), p(eid3),
+                                           p(out_pos3), p(graph_ptr3), p(nn3), s), "i3d_collate_3d_struct")
+        g2 = GraphBatch(src, dst, v["num_nodes"], v["num_edges"], {"feat": x_atom}, {"feat": e_attr}, n_cap,
+                        max_in_degree=self.max_in_degree_all)
+        g2._i3d_struct = GraphStructure.from_parts(n_cap, e_cap, B, rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos,
+                                                   graph_ptr, True, self.max_in_degree_all, padded=True)
+        g3 = GraphBatch(src3, dst3, nn3, None, {}, {"d": d3}, n3_cap)
+        g3._i3d_struct = GraphStructure.from_parts(n3_cap, e3_cap, B * C, rowptr3, src_csr3, dst_csr3, eid3, rowptr3,
+                                                   out_pos3, graph_ptr3, False, None, padded=True)
+        return g2, g3
+
+    def batch_sizes(self, idx, conformers=1):
+        """(N, E, E3) of the batch ``idx`` from the host copies of the store metadata (no device work)."""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        n = self.n_atoms[idx]
+        return int(n.sum()), int(self.n_edges[idx].sum()), int(conformers) * int((n * (n - 1)).sum())
 
 
 def metadata_len(B):

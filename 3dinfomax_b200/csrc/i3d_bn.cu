@@ -49,8 +49,10 @@ __device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const
 
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
-    act_colstats_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, double* __restrict__ sums) {
+    act_colstats_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, double* __restrict__ sums,
+                        const int32_t* __restrict__ m_valid) {
   pdl_grid_sync();
+  if (m_valid) M = min(M, (int64_t)*m_valid);
   const int FV = F / V;
   const ColMap m = col_map(FV);
   double acc[2][V];
@@ -100,8 +102,11 @@ __global__ void __launch_bounds__(256)
                     int64_t* __restrict__ num_batches_tracked, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float momentum, float eps, int training,
                     float* __restrict__ save_mean_rstd, const float* __restrict__ residual, float* __restrict__ O,
-                    int ldo) {
+                    int ldo, const int32_t* __restrict__ m_valid) {
   pdl_grid_sync();
+  // shape-bucketed batches: rows [*m_valid, M) are padding — excluded from the statistics, written as zeros
+  const int64_t Mrows = M;
+  if (m_valid) M = min(M, (int64_t)*m_valid);
   extern __shared__ float shf[];  // alpha[F], beta[F]
   float* s_alpha = shf;
   float* s_beta = shf + F;
@@ -125,11 +130,16 @@ __global__ void __launch_bounds__(256)
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
   __syncthreads();
   const int FV = F / V;
-  const int64_t total = M * FV;
+  const int64_t total = Mrows * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / FV;
     const int c0 = (int)(t - r * FV) * V;
     Vec<V> y, o;
+    if (r >= M) {
+      o.fill(0.f);
+      o.store(O + r * ldo + c0);
+      continue;
+    }
     y.load(Y + r * ldy + c0);
 #pragma unroll
     for (int i = 0; i < V; ++i) o.v[i] = act_apply(y.v[i], act) * s_alpha[c0 + i] + s_beta[c0 + i];
@@ -151,8 +161,9 @@ template <int V>
 __global__ void __launch_bounds__(kColThreads)
     bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
                          int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2,
-                         float* __restrict__ zero_buf, int zero_n) {
+                         float* __restrict__ zero_buf, int zero_n, const int32_t* __restrict__ m_valid) {
   pdl_grid_sync();
+  if (m_valid) M = min(M, (int64_t)*m_valid);      // padding rows may hold anything (never read)
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_buf[i] = 0.f;
   const int FV = F / V;
@@ -212,8 +223,13 @@ __global__ void __launch_bounds__(kColThreads)
     bn_bwd_apply_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M, int F,
                         int act, int has_bn, int training, const float* __restrict__ save_mean_rstd,
                         const float* __restrict__ gamma, const double* __restrict__ sums2, float* __restrict__ dY,
-                        int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                        int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        const int32_t* __restrict__ m_valid) {
   pdl_grid_sync();
+  // shape-bucketed batches: rows [*m_valid, M) are padding — dY is written as exact zeros there (their dO / Y are
+  // never read), so nothing downstream (dW = dY^T x, dx = dY W, row sums) sees them
+  const int64_t Mrows = M;
+  if (m_valid) M = min(M, (int64_t)*m_valid);
   const int FV = F / V;
   const ColMap m = col_map(FV);
   float mean[V], rstd[V], k1[V], k2[V], gr[V], db[V];
@@ -272,6 +288,14 @@ __global__ void __launch_bounds__(kColThreads)
       y.load(yp + r * ldy);
       d.load(dp + r * ldd);
       one(y, d, r);
+    }
+    if (Mrows > M) {
+      Vec<V> z;
+      z.fill(0.f);
+      // first padding row of this thread's row phase
+      int64_t rz = (int64_t)blockIdx.x * m.RP + m.rg;
+      if (rz < M) rz += ((M - rz + stride - 1) / stride) * stride;
+      for (; rz < Mrows; rz += stride) z.store(op + rz * lddy);
     }
   }
   if (dbias) {
@@ -359,6 +383,11 @@ using namespace i3d;
 extern "C" {
 
 int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double* sums, void* stream) {
+  return i3d_act_colstats_v(Y, M, F, ldy, act, sums, nullptr, stream);
+}
+
+int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, double* sums, const int32_t* m_valid,
+                       void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && sums && (M == 0 || Y), "invalid argument");
   cudaStream_t s = as_stream(stream);
   I3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
@@ -368,9 +397,9 @@ int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double*
   I3D_REQUIRE(FV <= kColThreads, "feature width too large (F <= 1024 when 16B-aligned, else F <= 256)");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
   if (v4)
-    launch(act_colstats_kernel<4>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums);
+    launch(act_colstats_kernel<4>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid);
   else
-    launch(act_colstats_kernel<1>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums);
+    launch(act_colstats_kernel<1>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -379,6 +408,14 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
                  float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
                  float momentum, float eps, int training, float* save_mean_rstd, const float* residual, float* O,
                  int ldo, void* stream) {
+  return i3d_bn_apply_v(Y, M, F, ldy, act, sums, running_mean, running_var, num_batches_tracked, gamma, beta, momentum,
+                        eps, training, save_mean_rstd, residual, O, ldo, nullptr, stream);
+}
+
+int i3d_bn_apply_v(const float* Y, int64_t M, int F, int ldy, int act, const double* sums, float* running_mean,
+                   float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
+                   float momentum, float eps, int training, float* save_mean_rstd, const float* residual, float* O,
+                   int ldo, const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldo >= F && gamma && beta && save_mean_rstd && running_mean &&
                   running_var && (!training || sums) && (M == 0 || (Y && O)),
               "invalid argument");
@@ -391,17 +428,23 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
   if (v4)
     launch(bn_apply_kernel<4>, grid_for(work, 256), 256, smem, s, Y, M, F, ldy, act, sums, running_mean, running_var,
                                                               num_batches_tracked, gamma, beta, momentum, eps,
-                                                              training, save_mean_rstd, residual, O, ldo);
+                                                              training, save_mean_rstd, residual, O, ldo, m_valid);
   else
     launch(bn_apply_kernel<1>, grid_for(work, 256), 256, smem, s, Y, M, F, ldy, act, sums, running_mean, running_var,
                                                               num_batches_tracked, gamma, beta, momentum, eps,
-                                                              training, save_mean_rstd, residual, O, ldo);
+                                                              training, save_mean_rstd, residual, O, ldo, m_valid);
   I3D_LAUNCHED();
   return I3D_OK;
 }
 
 int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                          const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n, void* stream) {
+  return i3d_bn_bwd_reduce_v(dO, ldd, Y, ldy, M, F, act, save_mean_rstd, sums2, zero_buf, zero_n, nullptr, stream);
+}
+
+int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                        const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n,
+                        const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && sums2 && save_mean_rstd && (M == 0 || (Y && dO)) &&
                   zero_n >= 0 && (zero_n == 0 || zero_buf),
               "invalid argument");
@@ -419,10 +462,10 @@ int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int6
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
   if (v4)
     launch(bn_bwd_reduce_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2, zero_buf, zero_n);
+                                                                      sums2, zero_buf, zero_n, m_valid);
   else
     launch(bn_bwd_reduce_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2, zero_buf, zero_n);
+                                                                      sums2, zero_buf, zero_n, m_valid);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -435,6 +478,13 @@ int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                      int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
                      int lddy, float* dbias, float* dgamma, float* dbeta, void* stream) {
+  return i3d_bn_bwd_apply_v(dO, ldd, Y, ldy, M, F, act, has_bn, training, save_mean_rstd, gamma, sums2, dY, lddy, dbias,
+                            dgamma, dbeta, nullptr, stream);
+}
+
+int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
+                       int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
+                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && (M == 0 || (Y && dO && dY)), "invalid argument");
   I3D_REQUIRE(!has_bn || (save_mean_rstd && gamma && sums2 && dgamma && dbeta), "BN tensors missing");
   if (M == 0) return I3D_OK;
@@ -446,11 +496,11 @@ int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t 
   if (v4)
     launch(bn_bwd_apply_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta);
+                                                                     dgamma, dbeta, m_valid);
   else
     launch(bn_bwd_apply_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta);
+                                                                     dgamma, dbeta, m_valid);
   I3D_LAUNCHED();
   return I3D_OK;
 }

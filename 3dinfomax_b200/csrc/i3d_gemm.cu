@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
           const int kk = c >> 5, mq = (c & 31) << 2;
           const int gk = k0 + kk;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gk < kend) {
-            const int64_t row = a_idx ? (int64_t)__ldg(a_idx + gk) : (int64_t)gk;
+          const int64_t row = gk < kend ? (a_idx ? (int64_t)__ldg(a_idx + gk) : (int64_t)gk) : -1;
+          if (row >= 0) {                                  // negative gather index (padding row) = zero row
             const float* src = A + row * lda + m0 + mq;
             if (vecA && m0 + mq + 3 < M) {
               v = __ldg(reinterpret_cast<const float4*>(src));
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
         const int kk = tid >> 4, nq = (tid & 15) << 2;
         const int gk = k0 + kk;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gk < kend) {
-          const int64_t row = (MODE == I3D_GEMM_TN && b_idx) ? (int64_t)__ldg(b_idx + gk) : (int64_t)gk;
+        const int64_t row = gk < kend ? ((MODE == I3D_GEMM_TN && b_idx) ? (int64_t)__ldg(b_idx + gk) : (int64_t)gk) : -1;
+        if (row >= 0) {
           const float* src = B + row * ldb + n0 + nq;
           if (vecB && n0 + nq + 3 < N) {
             v = __ldg(reinterpret_cast<const float4*>(src));
@@ -275,7 +275,8 @@ __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int l
 namespace i3d {
 bool gemm_tc_eligible(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream);
+            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream,
+            const int32_t* m_valid);
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs);
 
 // out[c, r] = in[r, c]  (32x32 shared-memory tiles, coalesced on both sides)
@@ -333,10 +334,12 @@ int gemm_prep_describe(int N, int n_seg, const i3d_gemm_seg* segs, int transpose
                        i3d_prep_item* out, int* tiles_out);
 int gemm_prep_run(const i3d_prep_item* dev_items, int n_items, int total_tiles, cudaStream_t stream);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared);
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared,
+               const int32_t* m_valid);
 int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                         const float* hi, const float* lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
-                        const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream);
+                        const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream,
+                        const int32_t* m_valid);
 int gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int64_t c_bucket_stride,
                     const int32_t* chunk_tab, int n_chunks, cudaStream_t stream);
 bool gemm_ws_available();
@@ -352,6 +355,14 @@ extern "C" int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm
                                     const float* bias, const float* b_hi, const float* b_lo, int b_pitch,
                                     int n_buckets, const int32_t* tile_bucket, const int32_t* row_map,
                                     double* col_stats, int stats_act, void* stream) {
+  return i3d_gemm_nt_bucketed_v(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, b_pitch, n_buckets, tile_bucket, row_map,
+                                col_stats, stats_act, nullptr, stream);
+}
+
+extern "C" int i3d_gemm_nt_bucketed_v(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                                      const float* bias, const float* b_hi, const float* b_lo, int b_pitch,
+                                      int n_buckets, const int32_t* tile_bucket, const int32_t* row_map,
+                                      double* col_stats, int stats_act, const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(Mv > 0 && (Mv % 128) == 0 && N >= 16 && (N & 3) == 0 && n_seg >= 1 && n_seg <= 4 && segs && C &&
                   ldc >= N && b_hi && b_lo && n_buckets >= 1 && n_buckets <= 16 && tile_bucket && row_map,
               "invalid argument");
@@ -367,7 +378,7 @@ extern "C" int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm
   stats_act &= 0xff;
   if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
   return gemm_ws_nt_bucketed(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, b_pitch, n_buckets, tile_bucket, row_map,
-                             col_stats, stats_act, as_stream(stream));
+                             col_stats, stats_act, as_stream(stream), m_valid);
 }
 
 extern "C" int i3d_gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg* seg, float* C, int ldc,
@@ -404,6 +415,12 @@ extern "C" int i3d_gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_ge
 extern "C" int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                                     const float* bias, int accumulate, const void* ws, double* col_stats,
                                     int stats_act, void* stream) {
+  return i3d_gemm_nt_prepared_v(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, col_stats, stats_act, nullptr, stream);
+}
+
+extern "C" int i3d_gemm_nt_prepared_v(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                                      const float* bias, int accumulate, const void* ws, double* col_stats,
+                                      int stats_act, const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(M >= 0 && N >= 0 && n_seg >= 1 && n_seg <= 4 && segs && ldc >= N && ws, "invalid shape");
   I3D_REQUIRE(!col_stats || !accumulate, "col_stats needs accumulate == 0");
   if (M == 0 || N == 0) return I3D_OK;
@@ -413,7 +430,7 @@ extern "C" int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_
   stats_act &= 0xff;
   if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
   return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, const_cast<void*>(ws), col_stats, stats_act,
-                    as_stream(stream), true);
+                    as_stream(stream), true, m_valid);
 }
 
 extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
@@ -424,6 +441,13 @@ extern "C" int i3d_gemm(int mode, int64_t M, int N, int n_seg, const i3d_gemm_se
 extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                            const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats,
                            int stats_act, void* stream) {
+  return i3d_gemm_ex_v(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act, nullptr,
+                       stream);
+}
+
+extern "C" int i3d_gemm_ex_v(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                             const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats,
+                             int stats_act, const int32_t* m_valid, void* stream) {
   I3D_REQUIRE(mode >= 0 && mode <= 2, "mode must be NT, NN or TN");
   const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
   stats_act &= 0xff;
@@ -439,7 +463,7 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
   if (g_gemm_backend != 1 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
     if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
     return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act,
-                   as_stream(stream));
+                   as_stream(stream), m_valid);
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -482,7 +506,7 @@ extern "C" int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm
     launch(gemm_kernel<I3D_GEMM_NT>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);
     if (col_stats) {
       I3D_LAUNCHED();
-      return i3d_act_colstats(C, M, N, ldc, stats_act, col_stats, stream);
+      return i3d_act_colstats_v(C, M, N, ldc, stats_act, col_stats, m_valid, stream);
     }
   } else {
     launch(gemm_kernel<I3D_GEMM_NN>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);

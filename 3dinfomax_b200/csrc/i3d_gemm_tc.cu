@@ -43,6 +43,7 @@ struct TcParams {
   // into the output block of bucket tab[3z+2] (C + bucket * c_bucket_stride); always atomic, caller pre-zeroes C
   const int32_t* chunk_tab;
   int64_t c_bucket_stride;
+  const int32_t* m_valid;   // optional device scalar: rows >= *m_valid are excluded from `stats`
 };
 
 // =================================================================================================================
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const float* __restrict__ B = p.seg[0].B;
       const int lda = p.seg[0].lda, ldb = p.seg[0].ldb;
       const int cg = (lane & 3) * 4;
-      const bool kvalid = tn_arow >= 0;
+      const bool kvalid = tn_arow >= 0 && tn_brow >= 0;     // negative gather index (padding row) = zero row
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t m = m0 + ((warp + 8 * i) >> 2) * 16 + cg;       // 8 column blocks of 16
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const bool atomic = (MODE == I3D_GEMM_TN) && p.splits > 1;
   tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, Cout, p.ldc,
                   (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic,
-                  MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act);
+                  MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act, nullptr, 0xffffffffu, p.m_valid);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -362,7 +363,8 @@ int gemm_tn_ws(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc, int 
 bool g_tn_ws = false;
 size_t gemm_ws_bytes(int N, int n_seg, const i3d_gemm_seg* segs);
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared);
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared,
+               const int32_t* m_valid);
 
 // bytes of scratch that let the NT kernel stream the B operand by TMA (hi + lo copies, K padded per segment)
 size_t gemm_tc_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs) {
@@ -406,12 +408,14 @@ int gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg& sg, float* C, int ldc,
 }
 
 int gemm_tc(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream) {
+            int accumulate, void* ws, size_t ws_bytes, double* stats, int stats_act, cudaStream_t stream,
+            const int32_t* m_valid) {
   const size_t need = gemm_tc_ws_bytes(mode, M, N, n_seg, segs);
   if (mode == I3D_GEMM_NT && ws && need > 0 && ws_bytes >= need && gemm_ws_available())
-    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stats, stats_act, stream, false);
+    return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, ws, stats, stats_act, stream, false, m_valid);
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.m_valid = m_valid;
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];
   p.n_seg = n_seg, p.M = M, p.N = N, p.C = C, p.ldc = ldc, p.bias = bias, p.accumulate = accumulate;
   p.kchunk = 0, p.splits = 1, p.stats = stats, p.stats_act = stats_act;

@@ -76,6 +76,7 @@ struct WsParams {
   const int32_t* row_map;
   int b_rows_total;                 // rows of the prepared B (n_buckets * N); 0 = plain mode (N rows)
   int b_pitch;                      // row pitch (floats) of the prepared B; 0 = the padded K extent
+  const int32_t* m_valid;           // optional device scalar: output rows >= *m_valid are excluded from `stats`
 };
 
 // OCC = CTAs resident per SM.  OCC 1: deepest ring (5 stages at BN = 208).  OCC 2: two CTAs share an SM (2-3 stages
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
   const long long dbg_epi_t0 = clock64();
 #endif
   tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false,
-                                     p.stats, p.stats_act, row_map, L::DUAL ? tmem + L::ACC_COLS : 0xffffffffu);
+                                     p.stats, p.stats_act, row_map, L::DUAL ? tmem + L::ACC_COLS : 0xffffffffu,
+                                     p.m_valid);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -578,9 +580,11 @@ static int ws_dispatch(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t
 
 // NT GEMM through the warp-specialised kernel.  ws: device scratch of gemm_ws_bytes(...) for the hi/lo weight copies.
 int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
-               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared) {
+               int accumulate, void* ws, double* stats, int stats_act, cudaStream_t stream, bool prepared,
+               const int32_t* m_valid) {
   WsParams p;
   memset(&p, 0, sizeof(p));
+  p.m_valid = m_valid;
   int ktot = 0;
   for (int s = 0; s < n_seg; ++s) {
     p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;
@@ -616,9 +620,11 @@ int gemm_ws_nt(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, 
 // prepared [n_buckets * N, ktot] hi/lo operands, output rows scattered through row_map.
 int gemm_ws_nt_bucketed(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                         const float* hi, const float* lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
-                        const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream) {
+                        const int32_t* row_map, double* stats, int stats_act, cudaStream_t stream,
+                        const int32_t* m_valid) {
   WsParams p;
   memset(&p, 0, sizeof(p));
+  p.m_valid = m_valid;
   int ktot = 0;
   for (int s = 0; s < n_seg; ++s) {
     p.A[s] = segs[s].A, p.a_idx[s] = segs[s].a_idx, p.scale[s] = segs[s].scale;

@@ -83,12 +83,22 @@ __global__ void csr_rowsort_kernel(const int32_t* __restrict__ rowptr, int64_t N
   }
 }
 
+// Edges whose key lies outside [0, N) (padding edges of a shape-bucketed batch carry key = other = -1) are in no row:
+// they occupy the positions [rowptr[N], E) behind the last row and get col = rowid = -1, eid = own position, so every
+// consumer that gathers through col / rowid reads a zero row for them (negative gather index = zero row).
 template <typename K>
 __global__ void csr_finalize_kernel(const K* __restrict__ key, const K* __restrict__ other, int64_t E,
-                                    const int32_t* __restrict__ eid, int32_t* __restrict__ col,
-                                    int32_t* __restrict__ rowid) {
+                                    const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ eid,
+                                    int32_t* __restrict__ col, int32_t* __restrict__ rowid) {
   pdl_grid_sync();
+  const int64_t e_valid = rowptr[N];
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < E; k += (int64_t)gridDim.x * blockDim.x) {
+    if (k >= e_valid) {
+      eid[k] = (int32_t)k;
+      if (col) col[k] = -1;
+      if (rowid) rowid[k] = -1;
+      continue;
+    }
     const int32_t e = eid[k];
     if (col) col[k] = (int32_t)other[e];
     if (rowid) rowid[k] = (int32_t)key[e];
@@ -119,10 +129,8 @@ static int csr_build_impl(const K* key, const K* other, int64_t E, int64_t N, in
     I3D_LAUNCHED();
     launch(csr_rowsort_kernel, grid_for(N, 128), 128, 0, s, rowptr, N, eid);
     I3D_LAUNCHED();
-    if (col || rowid) {
-      launch(csr_finalize_kernel<K>, grid_for(E, 256), 256, 0, s, key, other, E, eid, col, rowid);
-      I3D_LAUNCHED();
-    }
+    launch(csr_finalize_kernel<K>, grid_for(E, 256), 256, 0, s, key, other, E, rowptr, N, eid, col, rowid);
+    I3D_LAUNCHED();
   }
   return I3D_OK;
 }
@@ -456,6 +464,197 @@ int i3d_collate_3d(const int64_t* idx, int64_t B, const int64_t* atom_slices, co
   if (E3 == 0) return I3D_OK;
   i3d::launch(i3d::collate_3d_kernel, i3d::grid_for(E3, 256), 256, 0, i3d::as_stream(stream), idx, (int)B, atom_slices,
               coordinates, node_ptr, edge3_ptr, E3, src3, dst3, d3);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shape-bucketed batch construction (SURVEY.md §8f N1 + the captured-step requirement of static shapes).
+// Real epochs give every batch a different (N, E, E3) (train.py:595-598, datasets/custom_collate.py:105-114); a CUDA
+// graph needs static shapes.  These two kernels emit the batch PADDED to a bucket's capacities (n_cap, e_cap), with the
+// valid sizes read from the device metadata (node_ptr[B], edge_ptr[B], edge3_ptr[B]) so that one captured graph serves
+// every batch of the bucket, and they emit the CSR structure directly instead of sorting:
+//   * dgl.batch keeps every molecule's node and edge order and only offsets the ids, so the destination-sorted,
+//     edge-id-stable CSR of the batch is the concatenation of the per-molecule CSRs.  The store carries those once
+//     (in_rowptr_l / in_eid_l / out_rowptr_l / out_pos_l, molecule-local, computed at store construction); the batch
+//     arrays are offsets added to them.  Bit-equal to i3d_csr_build on the collated edge list (tests).
+//   * the 3-D graphs are complete digraphs in a fixed order (qm9_dataset.py:210-219), so their CSR is closed form:
+//     in-edges of local node j come from i != j ascending; CSR position e0 + j(n-1) + q holds edge id
+//     e0 + i(n-1) + (j < i ? j : j-1) with i = q < j ? q : q+1.
+// Padding convention: nodes [n_valid, n_cap) have no edges (rowptr = e_valid) and feature index 0; edges
+// [e_valid, e_cap) have src = dst = -1 (both id orders), eid = out_pos = own position.
+// ------------------------------------------------------------------------------------------------
+namespace i3d {
+
+__global__ void __launch_bounds__(256)
+    collate_2d_struct_kernel(const int64_t* __restrict__ idx, int B, const int64_t* __restrict__ atom_slices,
+                             const int64_t* __restrict__ edge_slices, const int64_t* __restrict__ edge_indices,
+                             int64_t Etot, const int64_t* __restrict__ atom_features, int CA,
+                             const int64_t* __restrict__ edge_features, int CE, const int32_t* __restrict__ in_rowptr_l,
+                             const int32_t* __restrict__ in_eid_l, const int32_t* __restrict__ out_rowptr_l,
+                             const int32_t* __restrict__ out_pos_l, const int64_t* __restrict__ node_ptr,
+                             const int64_t* __restrict__ edge_ptr, int64_t n_cap, int64_t e_cap,
+                             int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t* __restrict__ x_atom,
+                             int64_t* __restrict__ e_attr, int32_t* __restrict__ rowptr, int32_t* __restrict__ src_csr,
+                             int32_t* __restrict__ dst_csr, int32_t* __restrict__ eid, int32_t* __restrict__ out_rowptr,
+                             int32_t* __restrict__ out_pos, int32_t* __restrict__ graph_ptr) {
+  pdl_grid_sync();
+  const int64_t n_valid = node_ptr[B], e_valid = edge_ptr[B];
+  const int64_t node_items = (n_cap + 1), total = node_items + e_cap + (B + 1);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < node_items) {
+      const int64_t v = t;
+      if (v < n_valid) {
+        const int k = find_segment(node_ptr, B, v);
+        const int64_t a = atom_slices[idx[k]] + (v - node_ptr[k]);
+        const int32_t eb = (int32_t)edge_ptr[k];
+        rowptr[v] = eb + in_rowptr_l[a];
+        out_rowptr[v] = eb + out_rowptr_l[a];
+        for (int c = 0; c < CA; ++c) x_atom[v * CA + c] = atom_features[a * CA + c];
+      } else {
+        rowptr[v] = (int32_t)e_valid;
+        out_rowptr[v] = (int32_t)e_valid;
+        if (v < n_cap)
+          for (int c = 0; c < CA; ++c) x_atom[v * CA + c] = 0;
+      }
+    } else if (t < node_items + e_cap) {
+      const int64_t e = t - node_items;
+      if (e < e_valid) {
+        const int k = find_segment(edge_ptr, B, e);
+        const int64_t le = e - edge_ptr[k];
+        const int64_t s0 = edge_slices[idx[k]];
+        const int64_t off = node_ptr[k];
+        const int32_t eb = (int32_t)edge_ptr[k];
+        src[e] = edge_indices[s0 + le] + off;
+        dst[e] = edge_indices[Etot + s0 + le] + off;
+        for (int c = 0; c < CE; ++c) e_attr[e * CE + c] = edge_features[(s0 + le) * CE + c];
+        const int32_t leid = in_eid_l[s0 + le];              // local edge id at CSR position le of this molecule
+        eid[e] = eb + leid;
+        src_csr[e] = (int32_t)(edge_indices[s0 + leid] + off);
+        dst_csr[e] = (int32_t)(edge_indices[Etot + s0 + leid] + off);
+        out_pos[e] = eb + out_pos_l[s0 + le];
+      } else {
+        src[e] = -1, dst[e] = -1;
+        for (int c = 0; c < CE; ++c) e_attr[e * CE + c] = 0;
+        eid[e] = (int32_t)e, out_pos[e] = (int32_t)e;
+        src_csr[e] = -1, dst_csr[e] = -1;
+      }
+    } else {
+      const int64_t k = t - node_items - e_cap;
+      graph_ptr[k] = (int32_t)node_ptr[k];
+    }
+  }
+}
+
+// C conformers per molecule, molecule-major (datasets/qmugs_dataset.py:149-166 batches the conformer graphs of one
+// molecule with dgl.batch; custom_collate.py:105-114 then batches the molecules): graph k*C + c has nodes
+// [C node_ptr[k] + c n, + n) and edges [C edge3_ptr[k] + c n(n-1), + n(n-1)).  coords: [Ntot, 3*C_store] fp32, conformer c
+// in columns [3c, 3c+3) (qmugs_dataset.py `conformations`; C_store = 1 for QM9's `coordinates`).
+__global__ void __launch_bounds__(256)
+    collate_3d_struct_kernel(const int64_t* __restrict__ idx, int B, int C, const int64_t* __restrict__ atom_slices,
+                             const float* __restrict__ coords, int ldc, const int64_t* __restrict__ node_ptr,
+                             const int64_t* __restrict__ edge3_ptr, int64_t n_cap, int64_t e_cap,
+                             int64_t* __restrict__ src3, int64_t* __restrict__ dst3, float* __restrict__ d3,
+                             int32_t* __restrict__ rowptr, int32_t* __restrict__ src_csr, int32_t* __restrict__ dst_csr,
+                             int32_t* __restrict__ eid, int32_t* __restrict__ out_pos, int32_t* __restrict__ graph_ptr,
+                             int64_t* __restrict__ num_nodes3) {
+  pdl_grid_sync();
+  const int64_t n_valid = C * node_ptr[B], e_valid = C * edge3_ptr[B];
+  const int64_t node_items = n_cap + 1, graphs = (int64_t)B * C;
+  const int64_t total = node_items + e_cap + graphs + 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < node_items) {
+      const int64_t v = t;
+      int32_t rp = (int32_t)e_valid;
+      if (v < n_valid) {
+        const int k = find_segment(node_ptr, B, v / C);     // node_ptr[k] <= v / C  <=>  C node_ptr[k] <= v (integers)
+        const int64_t n = node_ptr[k + 1] - node_ptr[k];
+        const int64_t lv = v - C * node_ptr[k];
+        const int64_t c = lv / n, j = lv - c * n;
+        rp = (int32_t)(C * edge3_ptr[k] + c * n * (n - 1) + j * (n - 1));
+      }
+      rowptr[v] = rp;                                        // the out-CSR row pointer is the same array (symmetric)
+    } else if (t < node_items + e_cap) {
+      const int64_t e = t - node_items;
+      if (e < e_valid) {
+        const int k = find_segment(edge3_ptr, B, e / C);
+        const int64_t n = node_ptr[k + 1] - node_ptr[k];
+        const int64_t per = n * (n - 1);
+        const int64_t le = e - C * edge3_ptr[k];
+        const int64_t c = le / per, l = le - c * per;
+        const int64_t b0 = C * node_ptr[k] + c * n, e0 = C * edge3_ptr[k] + c * per;
+        const int64_t a = l / (n - 1), r = l - a * (n - 1);
+        const int64_t o = r < a ? r : r + 1;
+        // edge-id order: edge e goes a -> o (src = repeat_interleave, dst ascending)
+        src3[e] = b0 + a, dst3[e] = b0 + o;
+        const float* base = coords + atom_slices[idx[k]] * (int64_t)ldc + 3 * c;
+        const float* xa = base + a * (int64_t)ldc;
+        const float* xb = base + o * (int64_t)ldc;
+        const float dx = __fsub_rn(xa[0], xb[0]), dy = __fsub_rn(xa[1], xb[1]), dz = __fsub_rn(xa[2], xb[2]);
+        d3[e] = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+        // CSR position e: destination a, q-th in-edge comes from o (ascending source)
+        dst_csr[e] = (int32_t)(b0 + a), src_csr[e] = (int32_t)(b0 + o);
+        eid[e] = (int32_t)(e0 + o * (n - 1) + (a < o ? a : a - 1));
+        // out-CSR slot e: r-th out-edge of a (ascending destination o) sits at CSR position of (dst o, src a)
+        out_pos[e] = (int32_t)(e0 + o * (n - 1) + (a < o ? a : a - 1));
+      } else {
+        src3[e] = -1, dst3[e] = -1, d3[e] = 0.f;
+        dst_csr[e] = -1, src_csr[e] = -1, eid[e] = (int32_t)e, out_pos[e] = (int32_t)e;
+      }
+    } else {
+      const int64_t g = t - node_items - e_cap;               // graph_ptr[g], g in [0, B*C]
+      if (g == graphs) {
+        graph_ptr[g] = (int32_t)n_valid;
+      } else {
+        const int64_t k = g / C, c = g - k * C;
+        const int64_t n = node_ptr[k + 1] - node_ptr[k];
+        graph_ptr[g] = (int32_t)(C * node_ptr[k] + c * n);
+        if (num_nodes3) num_nodes3[g] = n;
+      }
+    }
+  }
+}
+
+}  // namespace i3d
+
+extern "C" {
+
+int i3d_collate_2d_struct(const int64_t* idx, int64_t B, const int64_t* atom_slices, const int64_t* edge_slices,
+                          const int64_t* edge_indices, int64_t Etot, const int64_t* atom_features, int n_atom_feat,
+                          const int64_t* edge_features, int n_edge_feat, const int32_t* in_rowptr_l,
+                          const int32_t* in_eid_l, const int32_t* out_rowptr_l, const int32_t* out_pos_l,
+                          const int64_t* node_ptr, const int64_t* edge_ptr, int64_t n_cap, int64_t e_cap, int64_t* src,
+                          int64_t* dst, int64_t* x_atom, int64_t* e_attr, int32_t* rowptr, int32_t* src_csr,
+                          int32_t* dst_csr, int32_t* eid, int32_t* out_rowptr, int32_t* out_pos, int32_t* graph_ptr,
+                          void* stream) {
+  I3D_REQUIRE(B >= 1 && B < (1 << 30) && n_cap >= 0 && e_cap >= 0 && n_cap < (1ll << 31) - 1 && e_cap < (1ll << 31) &&
+                  Etot >= 0 && n_atom_feat >= 1 && n_edge_feat >= 0 && idx && atom_slices && edge_slices && node_ptr &&
+                  edge_ptr && rowptr && out_rowptr && graph_ptr && (n_cap == 0 || (atom_features && x_atom && in_rowptr_l &&
+                  out_rowptr_l)) && (e_cap == 0 || (edge_indices && src && dst && src_csr && dst_csr && eid && out_pos &&
+                  in_eid_l && out_pos_l && (n_edge_feat == 0 || (edge_features && e_attr)))),
+              "invalid argument");
+  const int64_t work = n_cap + 1 + e_cap + B + 1;
+  i3d::launch(i3d::collate_2d_struct_kernel, i3d::grid_for(work, 256), 256, 0, i3d::as_stream(stream), idx, (int)B,
+              atom_slices, edge_slices, edge_indices, Etot, atom_features, n_atom_feat, edge_features, n_edge_feat,
+              in_rowptr_l, in_eid_l, out_rowptr_l, out_pos_l, node_ptr, edge_ptr, n_cap, e_cap, src, dst, x_atom, e_attr,
+              rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos, graph_ptr);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_collate_3d_struct(const int64_t* idx, int64_t B, int C, const int64_t* atom_slices, const float* coords,
+                          int ld_coords, const int64_t* node_ptr, const int64_t* edge3_ptr, int64_t n_cap, int64_t e_cap,
+                          int64_t* src3, int64_t* dst3, float* d3, int32_t* rowptr, int32_t* src_csr, int32_t* dst_csr,
+                          int32_t* eid, int32_t* out_pos, int32_t* graph_ptr, int64_t* num_nodes3, void* stream) {
+  I3D_REQUIRE(B >= 1 && C >= 1 && B * (int64_t)C < (1 << 30) && n_cap >= 0 && e_cap >= 0 && n_cap < (1ll << 31) - 1 &&
+                  e_cap < (1ll << 31) && ld_coords >= 3 * C && idx && atom_slices && coords && node_ptr && edge3_ptr &&
+                  rowptr && graph_ptr && (e_cap == 0 || (src3 && dst3 && d3 && src_csr && dst_csr && eid && out_pos)),
+              "invalid argument");
+  const int64_t work = n_cap + 1 + e_cap + B * (int64_t)C + 1;
+  i3d::launch(i3d::collate_3d_struct_kernel, i3d::grid_for(work, 256), 256, 0, i3d::as_stream(stream), idx, (int)B, C,
+              atom_slices, coords, ld_coords, node_ptr, edge3_ptr, n_cap, e_cap, src3, dst3, d3, rowptr, src_csr, dst_csr,
+              eid, out_pos, graph_ptr, num_nodes3);
   I3D_LAUNCHED();
   return I3D_OK;
 }

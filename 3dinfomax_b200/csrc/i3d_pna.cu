@@ -545,9 +545,20 @@ __global__ void segment_readout_fwd_kernel(const float* __restrict__ x, int ldx,
 template <int V>
 __global__ void segment_readout_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, int ldx,
                                            const float* __restrict__ out, const int32_t* __restrict__ ptr, int64_t B,
-                                           int F, RoOps ops, float* __restrict__ dx, int lddx) {
+                                           int F, RoOps ops, float* __restrict__ dx, int lddx, int64_t n_rows) {
   pdl_grid_sync();
   const int FV = F / V;
+  // rows behind the last graph (padding nodes of a shape-bucketed batch) belong to no readout: zero gradient
+  {
+    const int64_t r0 = ptr[B];
+    const int64_t ztotal = n_rows > r0 ? (n_rows - r0) * FV : 0;
+    Vec<V> z;
+    z.fill(0.f);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ztotal; t += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = r0 + t / FV;
+      z.store(dx + r * lddx + (int)(t % FV) * V);
+    }
+  }
   const int64_t total = B * FV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t gi = t / FV;
@@ -641,6 +652,11 @@ __global__ void segment_sum_bwd_kernel(const float* __restrict__ g, const int32_
     const int c0 = (int)(t - k * FV) * V;
     const int32_t v = __ldg(rowid + k);
     Vec<V> gv;
+    if (v < 0) {                       // padding edge of a shape-bucketed batch: in no row
+      gv.fill(0.f);
+      gv.store(gx + k * F + c0);
+      continue;
+    }
     gv.load(g + (int64_t)v * F + c0);
     if (mean) {
       const float d = (float)max(__ldg(rowptr + v + 1) - __ldg(rowptr + v), 1);
@@ -803,13 +819,19 @@ int i3d_segment_readout_fwd(const float* x, int ldx, const int32_t* ptr, int64_t
 
 int i3d_segment_readout_bwd(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
                             int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, void* stream) {
+  return i3d_segment_readout_bwd_v(g, x, ldx, out, ptr, B, F, n_ops, ops, dx, lddx, 0, stream);
+}
+
+int i3d_segment_readout_bwd_v(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
+                              int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, int64_t n_rows,
+                              void* stream) {
   RoOps r;
   I3D_REQUIRE(B >= 0 && F > 0 && ldx >= F && lddx >= F && ptr && make_ops(n_ops, ops, &r) == 0, "invalid argument");
   if (B == 0) return I3D_OK;
   const bool v4 = can_vec4({g, x, out, dx}, {F, ldx, lddx});
   const int64_t work = B * (F / (v4 ? 4 : 1));
   I3D_DISPATCH_VEC(v4, segment_readout_bwd_kernel, grid_for(work, 128), 128, as_stream(stream), g, x, ldx, out, ptr, B,
-                   F, r, dx, lddx);
+                   F, r, dx, lddx, n_rows);
   I3D_LAUNCHED();
   return I3D_OK;
 }

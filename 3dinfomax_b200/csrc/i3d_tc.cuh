@@ -154,7 +154,10 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
                                             int accumulate, bool atomic, double* __restrict__ stats = nullptr,
                                             int stats_act = 0, const int32_t* __restrict__ row_map = nullptr,
-                                            uint32_t tmem2 = 0xffffffffu) {
+                                            uint32_t tmem2 = 0xffffffffu,
+                                            const int32_t* __restrict__ m_valid = nullptr) {
+  // m_valid (shape-bucketed batches): output rows >= *m_valid are padding — stored like any row, but excluded from the
+  // fused BatchNorm statistics
   // tmem2: optional second accumulator (same shape) that is added to the first while the tile is drained
   // row_map (degree-bucketed GEMMs): tile row r is written to output row row_map[m0 + r]; negative = padding row that
   // is neither stored nor counted in the statistics
@@ -191,7 +194,9 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
   if (stats) {
     // fused FCLayer statistics (models/base_layers.py:102-110): column sums of act(y) and act(y)^2 over the valid rows
     // of this tile, accumulated in fp64 (BatchNorm inputs with mean^2 >> var), one atomic pair per column and CTA
-    const int rows = (int)(M - m0 < TC_BM ? M - m0 : TC_BM);
+    const int64_t mv = m_valid ? (int64_t)__ldg(m_valid) : (int64_t)0x7fffffff;
+    const int64_t mlim = (!row_map && mv < M) ? mv : M;
+    const int rows = (int)(mlim - m0 < TC_BM ? (mlim - m0 > 0 ? mlim - m0 : 0) : TC_BM);
     for (int c = tid; tid < NTHR && c < BN; c += NTHR) {
       if (n0 + c >= N) continue;
       const float b = bias ? __ldg(bias + n0 + c) : 0.f;
@@ -201,14 +206,14 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       for (; r + 4 <= rows; r += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const bool valid = !row_map || s_row[r + u] >= 0;
+          const bool valid = !row_map || (s_row[r + u] >= 0 && s_row[r + u] < mv);
           const double h = valid ? (double)act_apply(ctile[(r + u) * LDT + c] + b, stats_act) : 0.0;
           s1[u] += h;
           s2[u] = fma(h, h, s2[u]);
         }
       }
       for (; r < rows; ++r) {
-        if (row_map && s_row[r] < 0) continue;
+        if (row_map && (s_row[r] < 0 || s_row[r] >= mv)) continue;
         const double h = (double)act_apply(ctile[r * LDT + c] + b, stats_act);
         s1[0] += h;
         s2[0] = fma(h, h, s2[0]);

@@ -107,6 +107,35 @@ class GraphStructure:
     """
 
     MAX_PLAN_BUCKETS = 16
+    # shape-bucketed (padded) batches only: device int32 scalars with the number of valid nodes / edges; rows behind
+    # them are padding (include/i3d.h "Padding convention").  None = every row is valid.
+    n_valid = None
+    e_valid = None
+
+    @classmethod
+    def from_parts(cls, N, E, B, rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos, graph_ptr, need_scalers=True,
+                   max_in_degree=None, padded=False):
+        """Structure whose CSR arrays were emitted by the collate kernels (i3d_collate_2d_struct / _3d_struct)."""
+        st = cls.__new__(cls)
+        st.N, st.E, st.B = int(N), int(E), int(B)
+        st.rowptr, st.src_csr, st.dst_csr, st.eid = rowptr, src_csr, dst_csr, eid
+        st.out_rowptr, st.out_pos, st.graph_ptr = out_rowptr, out_pos, graph_ptr
+        if padded:
+            st.n_valid = graph_ptr[st.B:st.B + 1]            # graph_ptr[B] = number of valid nodes
+            st.e_valid = rowptr[st.N:st.N + 1]               # rowptr[n_cap] = number of valid edges
+        st.amp = st.att = None
+        st.plan = None
+        if need_scalers:
+            st.amp, st.att = K.degree_scalers(rowptr)
+            st._maybe_plan(max_in_degree)
+        return st
+
+    def _maybe_plan(self, max_in_degree):
+        use_plan = os.environ.get("I3D_POSTTRANS", "merged") != "generic"
+        min_nodes = int(os.environ.get("I3D_PLAN_MIN_NODES", "256"))
+        if (use_plan and max_in_degree is not None and self.N >= min_nodes
+                and int(max_in_degree) + 1 <= self.MAX_PLAN_BUCKETS):
+            self.plan = K.DegreePlan(self.rowptr, int(max_in_degree) + 1)
 
     def __init__(self, src, dst, batch_num_nodes, num_nodes, need_out=True, need_scalers=True, max_in_degree=None):
         if not src.is_cuda:
@@ -130,11 +159,8 @@ class GraphStructure:
         else:
             self.amp = self.att = None
         self.plan = None
-        use_plan = os.environ.get("I3D_POSTTRANS", "merged") != "generic"
-        min_nodes = int(os.environ.get("I3D_PLAN_MIN_NODES", "256"))     # tiny batches: padding to whole tiles per
-        if (need_scalers and use_plan and max_in_degree is not None and self.N >= min_nodes      # bucket outweighs K
-                and int(max_in_degree) + 1 <= self.MAX_PLAN_BUCKETS):
-            self.plan = K.DegreePlan(self.rowptr, int(max_in_degree) + 1)
+        if need_scalers:          # tiny batches (< I3D_PLAN_MIN_NODES): padding to whole tiles per bucket outweighs K
+            self._maybe_plan(max_in_degree)
 
     def check_plan(self):
         """Host check (device->host sync) that no node exceeded the ``max_in_degree`` the plan was built for."""

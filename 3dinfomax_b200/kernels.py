@@ -81,6 +81,15 @@ def _mat(t, name):
     return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
 
 
+def _valid(t):
+    """device int32 scalar holding the number of valid leading rows of a padded (shape-bucketed) batch, or None"""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.int32 or t.numel() != 1:
+        raise TypeError("valid-row count must be a 1-element int32 CUDA tensor")
+    return t.data_ptr()
+
+
 def _vec(t, dtype, name):
     _req(t, dtype, name)
     if t is not None and not t.is_contiguous():
@@ -197,18 +206,19 @@ class MergedPosttransWeights:
                    "i3d_posttrans_merge")
 
 
-def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None, arena=None):
+def gemm_nt_bucketed(plan, N, segs, C, bias, b_hi, b_lo, stats_act=None, arena=None, valid=None):
+    """C[plan.perm[m], :] = bias + sum_s A_s[a_idx_s[m] or m, :] @ B[bucket(m)]^T over the plan's virtual rows.
+    valid: optional device int32 scalar — output rows >= valid[0] (padding of a bucketed batch) stay out of the stats."""
     b_pitch = b_hi.shape[1]
-    """C[plan.perm[m], :] = bias + sum_s A_s[a_idx_s[m] or m, :] @ B[bucket(m)]^T over the plan's virtual rows."""
     pc, ldc = _mat(C, "C")
     arr = _seg_array(segs, need_b=False)
     stats, flag = (None, 0)
     if stats_act is not None:
         stats, flag = _stats_buffer(arena, 2 * N, C.device)
-    _lib.check(_L().i3d_gemm_nt_bucketed(plan.Mv, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                                         _p(b_hi), _p(b_lo), b_pitch, plan.n_buckets, _p(plan.tile_bucket), _p(plan.perm),
-                                         _p(stats), 0 if stats_act is None else (stats_act | flag), _s()),
-               "i3d_gemm_nt_bucketed")
+    _lib.check(_L().i3d_gemm_nt_bucketed_v(plan.Mv, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                                           _p(b_hi), _p(b_lo), b_pitch, plan.n_buckets, _p(plan.tile_bucket),
+                                           _p(plan.perm), _p(stats), 0 if stats_act is None else (stats_act | flag),
+                                           _valid(valid), _s()), "i3d_gemm_nt_bucketed")
     return C if stats_act is None else (C, stats)
 
 
@@ -273,7 +283,7 @@ def _seg_array(segs, need_b=True):
     return arr
 
 
-def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepared=None, arena=None):
+def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepared=None, arena=None, valid=None):
     """segs: list of dicts {A, B, K, a_idx?, b_idx?, scale?}; A/B are 2-D views (their stride(0) is the ld).
     stats_act: activation code -> also returns fp64 [2N] column sums of act(C), act(C)^2 (fused BatchNorm statistics).
     prepared: a ready ``PreparedB`` (NT only): B comes from its scratch, the segments need no "B"."""
@@ -286,16 +296,17 @@ def gemm(mode, M, N, segs, C, bias=None, accumulate=False, stats_act=None, prepa
         if mode != NT:
             raise ValueError("prepared operands are for NT GEMMs")
         arr = _seg_array(segs, need_b=False)
-        _lib.check(L.i3d_gemm_nt_prepared(M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                                          1 if accumulate else 0, _p(prepared.ws), _p(stats),
-                                          0 if stats_act is None else (stats_act | flag), _s()), "i3d_gemm_nt_prepared")
+        _lib.check(L.i3d_gemm_nt_prepared_v(M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                                            1 if accumulate else 0, _p(prepared.ws), _p(stats),
+                                            0 if stats_act is None else (stats_act | flag), _valid(valid), _s()),
+                   "i3d_gemm_nt_prepared")
         return C if stats_act is None else (C, stats)
     arr = _seg_array(segs)
     nws = int(L.i3d_gemm_ws_bytes(mode, M, N, len(segs), arr))
     ws = torch.empty(nws, dtype=torch.uint8, device=C.device) if nws else None      # tf32 hi/lo copies of B for TMA
-    _lib.check(L.i3d_gemm_ex(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
-                             1 if accumulate else 0, _p(ws), nws, _p(stats),
-                             0 if stats_act is None else (stats_act | flag), _s()), "i3d_gemm")
+    _lib.check(L.i3d_gemm_ex_v(mode, M, N, len(segs), arr, pc, ldc, _vec(bias, torch.float32, "bias"),
+                               1 if accumulate else 0, _p(ws), nws, _p(stats),
+                               0 if stats_act is None else (stats_act | flag), _valid(valid), _s()), "i3d_gemm")
     return C if stats_act is None else (C, stats)
 
 
@@ -322,6 +333,7 @@ class WeightPrep:
         self.entries = {}
         self.epoch = 0
         self._table = None
+        self._old_tables = []
         self._pinned = []
         self._tiles = 0
 
@@ -347,6 +359,8 @@ class WeightPrep:
         self._tiles += tiles.value
         e.epoch, e.w_version = -1, -1
         self.entries[k] = e
+        if self._table is not None:
+            self._old_tables.append(self._table)            # graphs captured earlier still point at their table
         self._table = None
         return e
 
@@ -390,7 +404,8 @@ def act_colstats(Y, act):
     return sums
 
 
-def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum, eps, training, residual, out=None):
+def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum, eps, training, residual, out=None,
+             valid=None):
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
     O = torch.empty(M, F, dtype=torch.float32, device=Y.device) if out is None else out
@@ -402,24 +417,24 @@ def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum
     else:
         pr = None
     save = torch.empty(2 * F, dtype=torch.float32, device=Y.device)
-    _lib.check(_L().i3d_bn_apply(py, M, F, ldy, act, _p(sums), _p(running_mean), _p(running_var), _p(nbt),
-                                 _p(gamma), _p(beta), float(momentum), float(eps), 1 if training else 0, _p(save),
-                                 pr, po, ldo, _s()), "i3d_bn_apply")
+    _lib.check(_L().i3d_bn_apply_v(py, M, F, ldy, act, _p(sums), _p(running_mean), _p(running_var), _p(nbt),
+                                   _p(gamma), _p(beta), float(momentum), float(eps), 1 if training else 0, _p(save),
+                                   pr, po, ldo, _valid(valid), _s()), "i3d_bn_apply")
     return O, save
 
 
-def bn_bwd_reduce(dO, Y, act, save, arena=None, zero=None):
+def bn_bwd_reduce(dO, Y, act, save, arena=None, zero=None, valid=None):
     """zero: optional fp32 tensor the kernel clears on the way (the dbias accumulator of the following bn_bwd_apply)"""
     pd, ldd = _mat(dO, "dO")
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
     sums2, flag = _stats_buffer(arena, 2 * F, Y.device)
-    _lib.check(_L().i3d_bn_bwd_reduce_ex(pd, ldd, py, ldy, M, F, act | flag, _p(save), _p(sums2), _p(zero),
-                                         0 if zero is None else zero.numel(), _s()), "i3d_bn_bwd_reduce")
+    _lib.check(_L().i3d_bn_bwd_reduce_v(pd, ldd, py, ldy, M, F, act | flag, _p(save), _p(sums2), _p(zero),
+                                        0 if zero is None else zero.numel(), _valid(valid), _s()), "i3d_bn_bwd_reduce")
     return sums2
 
 
-def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True, dbias_zeroed=None):
+def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True, dbias_zeroed=None, valid=None):
     pd, ldd = _mat(dO, "dO")
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
@@ -433,9 +448,9 @@ def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=Tr
         dbias = torch.zeros(F, dtype=torch.float32, device=dev)
     dgamma = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
-    _lib.check(_L().i3d_bn_bwd_apply(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,
-                                     _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), _p(dgamma), _p(dbeta),
-                                     _s()), "i3d_bn_bwd_apply")
+    _lib.check(_L().i3d_bn_bwd_apply_v(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,
+                                       _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), _p(dgamma), _p(dbeta),
+                                       _valid(valid), _s()), "i3d_bn_bwd_apply")
     return dY, dbias, dgamma, dbeta
 
 
@@ -495,8 +510,9 @@ def segment_readout_bwd(g, x, out, ptr, ops):
     B = ptr.numel() - 1
     F = x.shape[1]
     dx = torch.empty(x.shape[0], F, dtype=torch.float32, device=x.device)
-    _lib.check(_L().i3d_segment_readout_bwd(_p(g), px, ldx, _p(out), _p(ptr), B, F, len(ops),
-                                            ctypes.cast(_ops_arr(ops), ctypes.c_void_p), _p(dx), F, _s()),
+    # rows behind the last graph (padding nodes of a bucketed batch) get a zero gradient
+    _lib.check(_L().i3d_segment_readout_bwd_v(_p(g), px, ldx, _p(out), _p(ptr), B, F, len(ops),
+                                              ctypes.cast(_ops_arr(ops), ctypes.c_void_p), _p(dx), F, x.shape[0], _s()),
                "i3d_segment_readout_bwd")
     return dx
 

@@ -62,6 +62,18 @@ SIGNATURES = {
     "i3d_posttrans_unmerge": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "i3d_collate_2d": (_I, [_P, _L, _P, _P, _P, _L, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
     "i3d_collate_3d": (_I, [_P, _L, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
+    "i3d_collate_2d_struct": (_I, [_P, _L, _P, _P, _P, _L, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P,
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "i3d_collate_3d_struct": (_I, [_P, _L, _I, _P, _P, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "i3d_gemm_ex_v": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, ctypes.c_size_t, _P, _I, _P,
+                           _P]),
+    "i3d_gemm_nt_prepared_v": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    "i3d_gemm_nt_bucketed_v": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I,
+                                    _P, _P]),
+    "i3d_act_colstats_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P]),
+    "i3d_bn_apply_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P, _P]),
+    "i3d_bn_bwd_reduce_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "i3d_gemm_backend": (_I, [_I]),
@@ -85,6 +97,7 @@ SIGNATURES = {
     "i3d_pna_aggregate_bwd": (_I, [_P, _I, _P, _P, _I, _P, _L, _I, _P, _P]),
     "i3d_segment_readout_fwd": (_I, [_P, _I, _P, _L, _I, _I, _P, _P, _P]),
     "i3d_segment_readout_bwd": (_I, [_P, _P, _I, _P, _P, _L, _I, _I, _P, _P, _I, _P]),
+    "i3d_segment_readout_bwd_v": (_I, [_P, _P, _I, _P, _P, _L, _I, _I, _P, _P, _I, _L, _P]),
     "i3d_segment_sum_fwd": (_I, [_P, _I, _P, _P, _L, _I, _I, _P, _I, _P, _I, _P]),
     "i3d_segment_sum_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P, _P]),
     "i3d_fourier_encode": (_I, [_P, _P, _L, _I, _P, _P]),

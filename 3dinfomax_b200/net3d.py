@@ -37,13 +37,13 @@ class Net3DLayer(nn.Module):
         # models/net3d.py:112-118
         msg = self.message_network([ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
                                     ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr),
-                                    ops.Seg(d)])
+                                    ops.Seg(d)], valid=st.e_valid)
         d_next = ops.add(d, msg) if update_edges else None            # edges.data['d'] += message
         m = ops.soft_gate(msg, self.soft_edge_network.weight, self.soft_edge_network.bias)
         # fn.sum / fn.mean over in-edges, fused with "+ feat"  (models/net3d.py:94-96,122)
         agg = ops.segment_reduce(m, st.rowptr, st.dst_csr, self.reduce_mean, addend=h)
         # models/net3d.py:120-125
-        return self.update_network(agg, residual=h), d_next
+        return self.update_network(agg, residual=h, valid=st.n_valid), d_next
 
 
 class Net3D(nn.Module):
@@ -91,12 +91,12 @@ class Net3D(nn.Module):
         dist = dist.reshape(-1).contiguous()
         # commons/utils.py:103-110, emitted in CSR order (k = 0: the raw distance column only)
         e_in = K.fourier_encode(dist, st.eid, self.fourier_encodings)
-        d = ops.activation(self.edge_input(e_in), "silu")                       # models/net3d.py:80-81
+        d = ops.activation(self.edge_input(e_in, valid=st.e_valid), "silu")     # models/net3d.py:80-81
         n_layers = len(self.mp_layers)
         for i, layer in enumerate(self.mp_layers):
             h, d = layer(st, h, d, update_edges=i + 1 < n_layers)
         if self.node_wise_output_layers > 0:
-            h = self.node_wise_output_network(h)                                # models/net3d.py:70-71
+            h = self.node_wise_output_network(h, valid=st.n_valid)              # models/net3d.py:70-71
         graph.ndata["feat"] = h
         ro = ops.readout(h, st.graph_ptr, self.readout_aggregators)            # models/net3d.py:73-74
         return self.output(ro)                                                  # models/net3d.py:75

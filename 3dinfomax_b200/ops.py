@@ -83,13 +83,17 @@ class Seg:
 
 
 class FCConfig:
-    __slots__ = ("segs", "act", "has_bn", "training", "running_mean", "running_var", "nbt", "momentum", "eps")
+    """valid: optional device int32 scalar — the number of valid leading rows when the batch is padded to a shape
+    bucket (trainer.BucketedStep).  Rows beyond it stay out of the BatchNorm statistics, leave the normalisation as
+    zeros and get an exactly-zero gradient (kernels.*: the *_v entry points of include/i3d.h)."""
+    __slots__ = ("segs", "act", "has_bn", "training", "running_mean", "running_var", "nbt", "momentum", "eps", "valid")
 
     def __init__(self, segs, act, has_bn, training, running_mean=None, running_var=None, nbt=None, momentum=0.1,
-                 eps=1e-5):
+                 eps=1e-5, valid=None):
         self.segs, self.act, self.has_bn, self.training = segs, act, has_bn, training
         self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
         self.momentum, self.eps = momentum, eps
+        self.valid = valid
 
 
 class _NullCtx:
@@ -125,12 +129,12 @@ class _FC(torch.autograd.Function):
         if cfg.has_bn and cfg.training:
             # statistics from the GEMM epilogue
             _, sums = K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, stats_act=cfg.act, prepared=ready,
-                             arena=getattr(W, "_i3d_arena", None))
+                             arena=getattr(W, "_i3d_arena", None), valid=cfg.valid)
         else:
             K.gemm(K.NT, M, Fout, gsegs, Y, bias=b, prepared=ready)
         if cfg.has_bn:
             O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
-                                 cfg.momentum, cfg.eps, cfg.training, residual)
+                                 cfg.momentum, cfg.eps, cfg.training, residual, valid=cfg.valid)
         else:
             O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
             if residual is not None:
@@ -156,11 +160,12 @@ class _FC(torch.autograd.Function):
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
             dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz)
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz)
-        elif cfg.act != 0:
-            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
+                                                   dbias_zeroed=dbz, valid=cfg.valid)
+        elif cfg.act != 0 or cfg.valid is not None:
+            # (padded batches: the pass also writes the exact zeros of the padding rows)
+            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:
             dY = dO
             db = K.colsum(dO) if need_b else None
@@ -236,14 +241,15 @@ class _FC(torch.autograd.Function):
         return (None, dW, db, dgamma, dbeta, dres) + tuple(dxs)
 
 
-def fc(segs, W, b, act, bn=None, training=True, residual=None):
-    """FCLayer over a virtual concat.  ``bn``: None or (gamma, beta, running_mean, running_var, nbt, momentum, eps)."""
+def fc(segs, W, b, act, bn=None, training=True, residual=None, valid=None):
+    """FCLayer over a virtual concat.  ``bn``: None or (gamma, beta, running_mean, running_var, nbt, momentum, eps).
+    ``valid``: device int32 scalar, valid leading rows of a padded batch (FCConfig)."""
     if bn is None:
-        cfg = FCConfig(segs, act, False, training)
+        cfg = FCConfig(segs, act, False, training, valid=valid)
         gamma = beta = None
     else:
         gamma, beta, rm, rv, nbt, mom, eps = bn
-        cfg = FCConfig(segs, act, True, training, rm, rv, nbt, mom, eps)
+        cfg = FCConfig(segs, act, True, training, rm, rv, nbt, mom, eps, valid=valid)
     return _FC.apply(cfg, W, b, gamma, beta, residual, *[s.x for s in segs])
 
 
@@ -264,12 +270,12 @@ class _FCPostMerged(torch.autograd.Function):
         sums = save = None
         if cfg.has_bn and cfg.training:
             _, sums = K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo, stats_act=cfg.act,
-                                         arena=getattr(W, "_i3d_arena", None))
+                                         arena=getattr(W, "_i3d_arena", None), valid=cfg.valid)
         else:
             K.gemm_nt_bucketed(plan, Fout, segs, Y, b, merged.fwd_hi, merged.fwd_lo)
         if cfg.has_bn:
             O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
-                                 cfg.momentum, cfg.eps, cfg.training, residual)
+                                 cfg.momentum, cfg.eps, cfg.training, residual, valid=cfg.valid)
         else:
             O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
             if residual is not None:
@@ -292,11 +298,11 @@ class _FCPostMerged(torch.autograd.Function):
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
             dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz)
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz)
-        elif cfg.act != 0:
-            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b)
+                                                   dbias_zeroed=dbz, valid=cfg.valid)
+        elif cfg.act != 0 or cfg.valid is not None:
+            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:
             dY = dO
             db = K.colsum(dO) if need_b else None
@@ -324,14 +330,14 @@ class _FCPostMerged(torch.autograd.Function):
         return None, None, None, dW, db, dgamma, dbeta, dres, dh, dagg
 
 
-def fc_post_merged(plan, merged, h, agg, W, b, act, bn=None, training=True, residual=None):
+def fc_post_merged(plan, merged, h, agg, W, b, act, bn=None, training=True, residual=None, valid=None):
     """Degree-merged posttrans FCLayer; arguments as ``fc``."""
     if bn is None:
-        cfg = FCConfig(None, act, False, training)
+        cfg = FCConfig(None, act, False, training, valid=valid)
         gamma = beta = None
     else:
         gamma, beta, rm, rv, nbt, mom, eps = bn
-        cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps)
+        cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps, valid=valid)
     return _FCPostMerged.apply(cfg, plan, merged, W, b, gamma, beta, residual, h, agg)
 
 

@@ -158,6 +158,18 @@ class FusedAdam:
             if hyper != self._hyper_host[gi]:
                 self._upload_hyper(gi, hyper)
 
+    def packed_grads(self):
+        """{parameter: view of its gradient inside the flat buffer} as the last ``step()`` saw them (after the pack and,
+        when data parallel, the all-reduce).  Valid until the next ``zero_grad()``; this is how gradients are read
+        back after a captured step, where ``p.grad`` of the packed parameters lives in the graph's private pool."""
+        out = {}
+        for g, fl in zip(self.param_groups, self._flat):
+            if fl is None:
+                continue
+            for p, o, n in zip(g["params"], fl["offs"], fl["sizes"]):
+                out[p] = fl["g"][o:o + n].view(p.shape)
+        return out
+
     def zero_grad(self, set_to_none=True):
         self._needs_zero = False
         for g, fl in zip(self.param_groups, self._flat):

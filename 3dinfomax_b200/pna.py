@@ -90,7 +90,7 @@ class PNALayer(nn.Module):
         # models/pna.py:203,237-252 — edge MLP over cat[h[src], h[dst], e], rows emitted in CSR order
         msg = self.pretrans([ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
                              ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr),
-                             ops.Seg(ef_csr)])
+                             ops.Seg(ef_csr)], valid=st.e_valid)
         # models/pna.py:206,221-235
         agg = ops.pna_aggregate(msg, st.rowptr)
         # models/pna.py:207-211 — cat[h, agg, agg*amp, agg*att] -> posttrans -> + h
@@ -99,12 +99,12 @@ class PNALayer(nn.Module):
             # the degree scalers depend on the in-degree only: nodes grouped by degree share one merged weight
             # W_id + amp_D W_amp + att_D W_att, and the first posttrans FC runs with K = 5F instead of 13F
             fcs = self.posttrans.fully_connected
-            x = fcs[0].forward_merged(st.plan, h, agg, res if len(fcs) == 1 else None)
+            x = fcs[0].forward_merged(st.plan, h, agg, res if len(fcs) == 1 else None, st.n_valid)
             for i in range(1, len(fcs)):
-                x = fcs[i](x, res if i == len(fcs) - 1 else None)
+                x = fcs[i](x, res if i == len(fcs) - 1 else None, st.n_valid)
             return x, msg
         return self.posttrans([ops.Seg(h), ops.Seg(agg), ops.Seg(agg, scale=st.amp), ops.Seg(agg, scale=st.att)],
-                              residual=res), msg
+                              residual=res, valid=st.n_valid), msg
 
 
 class PNAGNN(nn.Module):

@@ -184,10 +184,12 @@ def slice_batch(b, lo, hi):
     }
 
 
-def make_store(seed, n_molecules, shape="qm9"):
+def make_store(seed, n_molecules, shape="qm9", conformers=1, conformer_noise=0.3):
     """A packed molecule store with the fields of the reference's processed file (datasets/qm9_dataset.py:454-467):
     n_atoms [M], atom_slices / edge_slices [M+1] (leading 0), edge_indices [2, Etot] with molecule-LOCAL node ids,
-    atom_features int64 [Ntot, 9], edge_features int64 [Etot, 3], coordinates fp32 [Ntot, 3]."""
+    atom_features int64 [Ntot, 9], edge_features int64 [Etot, 3], coordinates fp32 [Ntot, 3].
+    conformers > 1 adds ``conformations`` fp32 [Ntot, 3*conformers] (datasets/qmugs_dataset.py:96-101: conformer c in
+    columns [3c, 3c+3), conformer 0 == coordinates); drawn from a separate generator so the other fields do not change."""
     rng = np.random.default_rng(seed)
     counts = _sample_atom_counts(rng, n_molecules, shape)
     heavy_z = np.array([5, 6, 7, 8])
@@ -210,9 +212,15 @@ def make_store(seed, n_molecules, shape="qm9"):
         xyz_l.append(pos)
         atom_slices.append(atom_slices[-1] + n)
         edge_slices.append(edge_slices[-1] + 2 * nb)
-    return {"n_atoms": counts.astype(np.int64), "atom_slices": np.array(atom_slices, dtype=np.int64),
-            "edge_slices": np.array(edge_slices, dtype=np.int64),
-            "edge_indices": np.concatenate(ei_l, axis=1).astype(np.int64),
-            "atom_features": np.concatenate(xf_l).astype(np.int64),
-            "edge_features": np.concatenate(ef_l).astype(np.int64).reshape(-1, 3),
-            "coordinates": np.concatenate(xyz_l).astype(np.float32)}
+    out = {"n_atoms": counts.astype(np.int64), "atom_slices": np.array(atom_slices, dtype=np.int64),
+           "edge_slices": np.array(edge_slices, dtype=np.int64),
+           "edge_indices": np.concatenate(ei_l, axis=1).astype(np.int64),
+           "atom_features": np.concatenate(xf_l).astype(np.int64),
+           "edge_features": np.concatenate(ef_l).astype(np.int64).reshape(-1, 3),
+           "coordinates": np.concatenate(xyz_l).astype(np.float32)}
+    if conformers > 1:
+        rng2 = np.random.default_rng([seed, 77])
+        xyz = out["coordinates"].astype(np.float64)
+        cols = [xyz] + [xyz + rng2.normal(0.0, conformer_noise, size=xyz.shape) for _ in range(conformers - 1)]
+        out["conformations"] = np.concatenate(cols, axis=1).astype(np.float32)
+    return out

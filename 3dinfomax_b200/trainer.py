@@ -11,8 +11,10 @@ reference's own (out of scope): the modules here are plain ``nn.M
 [all-reduce] -> Adam) as ONE CUDA graph fed from static device buffers: at these sizes the step is launch-bound
 (~350 kernels of a few microseconds each), and a graph is the B200-idiomatic way to remove the host from the loop.
 """
+import math
 from itertools import chain
 
+import numpy as np
 import torch
 
 from . import dist as D
@@ -56,6 +58,31 @@ class SelfSupervisedTrainer:
                 v._i3d_arena = self.arena
         self.optim.post_step_hooks.append(self.prep.invalidate)
 
+    # --- state that a step mutates (used to make CUDA-graph warm-up runs side-effect free) ---------------------
+    def snapshot_state(self):
+        """Copies of everything ``process_batch`` mutates: parameters, Adam moments and step counters, BatchNorm
+        buffers.  ``restore_state`` puts them back (same storage: views handed to modules / captured graphs stay valid)."""
+        o = self.optim
+        bufs = [b for m in (self.model, self.model3d) for b in m.buffers()]
+        return {"flat": [None if fl is None else (fl["p"].clone(), fl["m"].clone(), fl["v"].clone()) for fl in o._flat],
+                "step": o._step, "step_dev": None if o._step_dev is None else o._step_dev.clone(),
+                "bufs": [b.clone() for b in bufs], "optim_steps": self.optim_steps}
+
+    @torch.no_grad()
+    def restore_state(self, snap):
+        o = self.optim
+        for fl, c in zip(o._flat, snap["flat"]):
+            if fl is not None:
+                fl["p"].copy_(c[0]), fl["m"].copy_(c[1]), fl["v"].copy_(c[2])
+        o._step = snap["step"]
+        if o._step_dev is not None:
+            o._step_dev.copy_(snap["step_dev"])
+        bufs = [b for m in (self.model, self.model3d) for b in m.buffers()]
+        for b, c in zip(bufs, snap["bufs"]):
+            b.copy_(c)
+        self.optim_steps = snap["optim_steps"]
+        self.prep.invalidate()
+
     def forward_pass(self, batch):
         self.arena.reset()
         self.prep.refresh()
@@ -65,11 +92,11 @@ class SelfSupervisedTrainer:
             self.stream3d.wait_stream(main)
             with torch.cuda.stream(self.stream3d):
                 view3d = self.model3d(*info3d)
-            view2d = self.model(*info2d)
+            view2d = self.model(*info2d, *rest)      # *snorm_n of PNAOriginal (self_supervised_trainer.py:25-26)
             main.wait_stream(self.stream3d)
             view3d.record_stream(main)
         else:
-            view2d = self.model(*info2d)
+            view2d = self.model(*info2d, *rest)
             view3d = self.model3d(*info3d)
         if self.world > 1:
             # global negative set: every rank's 3-D embeddings; the local rows sit at row_offset in column space
@@ -103,7 +130,10 @@ class CapturedStep:
     static device buffers — shapes must match the capture; ``run()`` replays; ``loss`` is a device scalar.
     """
 
-    def __init__(self, trainer, example_g2, example_g3, warmup=3):
+    def __init__(self, trainer, example_g2, example_g3, warmup=3, keep_warmup_updates=False):
+        if not trainer.optim.graph_safe:
+            raise ValueError("CapturedStep needs SelfSupervisedTrainer(..., graph_safe=True): with host-side "
+                             "hyper-parameters the learning rate and Adam's step count would be frozen into the graph")
         self.tr = trainer
         dev = trainer.device
         self.static = {
@@ -117,6 +147,9 @@ class CapturedStep:
         self.max_in_degree = getattr(example_g2, "max_in_degree", None)   # sizes the degree plan inside the graph
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph = None
+        # the warm-up runs are real steps on the example batch (lazy initialisation, allocator warm-up): unless asked
+        # otherwise everything they changed (weights, Adam state, BatchNorm buffers, step counters) is put back
+        snap = None if keep_warmup_updates else trainer.snapshot_state()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -125,6 +158,9 @@ class CapturedStep:
                 self.tr.optim_steps += 1
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if snap is not None:
+            trainer.restore_state(snap)
+            torch.cuda.synchronize(dev)
         from . import lib as _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
@@ -173,3 +209,210 @@ class CapturedStep:
         if self.tr.lr_scheduler is not None:
             self.tr.lr_scheduler.step()
         return self.loss
+
+
+class BucketLadder:
+    """Shape buckets for batches of ``batch_size`` molecules drawn from ``store``.
+
+    N, E and E3 of a batch are sums over its molecules, so they concentrate around ``B * mean`` with a standard
+    deviation of ``sqrt(B) * std`` (QM9, B = 512: 0.7 % of N, 1.5 % of E3).  Level k holds every batch whose three sizes
+    stay below ``B * mean + (k + 1) * step * sqrt(B) * std`` (rounded up to ``align`` rows): ~84 % of the batches of an
+    epoch land in level 0, ~14 % in level 1, and the padding costs 1-3 % of the rows.  Every rank of a data-parallel job
+    derives the same ladder from the same store."""
+
+    def __init__(self, store, batch_size, conformers=1, step=1.0, align=128):
+        n = store.n_atoms.astype(np.float64)
+        e = store.n_edges.astype(np.float64)
+        e3 = float(conformers) * n * (n - 1.0)
+        B = int(batch_size)
+        self.B, self.C, self.step, self.align = B, int(conformers), float(step), int(align)
+        self.mean = [B * float(x.mean()) for x in (n, e, e3)]
+        self.sd = [max(math.sqrt(B) * float(x.std()), 1.0) for x in (n, e, e3)]
+        self.lo = [int(np.sort(x)[:B].sum()) for x in (n, e, e3)] if B <= len(n) else None
+
+    def caps(self, level):
+        """(n_cap, e_cap, e3_cap) of ``level``; n_cap counts 2-D nodes (the 3-D graph has conformers * n_cap)"""
+        up = lambda x: int(-(-int(math.ceil(x)) // self.align) * self.align)
+        return tuple(max(up(m + (level + 1) * self.step * sd), self.align) for m, sd in zip(self.mean, self.sd))
+
+    def level_of(self, sizes):
+        lv = 0
+        for x, m, sd in zip(sizes, self.mean, self.sd):
+            lv = max(lv, int(math.ceil((x - m) / (self.step * sd))) - 1)
+        while any(x > c for x, c in zip(sizes, self.caps(lv))):
+            lv += 1
+        return lv
+
+
+class _Bucket:
+    __slots__ = ("graph", "meta", "caps", "launches", "replays")
+
+
+class BucketedStep:
+    """The batch loop of ``train.py`` (train.py:595-598 -> trainer/trainer.py:116-124) on captured CUDA graphs although
+    every batch of an epoch has a different (N, E, E3): batches are built ON THE DEVICE from a ``PackedMoleculeStore``
+    padded to a small ladder of shape buckets, one captured graph per (batch size, bucket, train/eval).
+
+        run = BucketedStep(trainer, store, conformers=1)
+        for idx in sampler:                  # host int array of molecule ids, any batch size (the last one is short)
+            loss = run.step(idx)             # device scalar; run.predictions / run.targets = z2d / z3d of the step
+
+    Per step the host computes the batch's three sizes (O(B) integer adds), picks the bucket, uploads 7B+3 int64 of
+    metadata from an event-guarded pinned ring and replays the graph; the graph holds collate (both graphs + CSR
+    structures, no sort), both encoders, the loss, backward, [NCCL], Adam.  Padding rows are masked where they would
+    matter (BatchNorm statistics and counts; see include/i3d.h "Padding convention") and are exact zeros in every
+    gradient, so a padded step equals the unpadded one up to fp32 summation order (tests: case_bucketed_step).
+
+    Data parallel: every rank replays its own bucket's graph — all graphs issue the same collectives in the same order
+    with the same sizes.  Capturing needs an eager warm-up run (with collectives), so under DP the levels
+    ``0..dp_levels-1`` of a batch size are captured together, on all ranks, the first time that batch size is seen; a
+    batch beyond the ladder runs eagerly (same collectives)."""
+
+    def __init__(self, trainer, store, conformers=1, sigma_step=1.0, dp_levels=6, keep_graph_outputs=True):
+        if not trainer.optim.graph_safe:
+            raise ValueError("BucketedStep needs SelfSupervisedTrainer(..., graph_safe=True)")
+        self.tr, self.store, self.C = trainer, store, int(conformers)
+        self.sigma_step, self.dp_levels = float(sigma_step), int(dp_levels)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.buckets, self.ladders = {}, {}
+        dev = trainer.device
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.keep_outputs = keep_graph_outputs
+        self.predictions = self.targets = None
+        self._out = {}
+        self.stats = {"steps": 0, "captures": 0, "eager": 0, "levels": {}}
+        for m in (trainer.model, trainer.model3d):
+            gnn = getattr(m, "node_gnn", None)
+            if gnn is not None and hasattr(gnn, "keep_edge_side_effects"):
+                gnn.keep_edge_side_effects = False        # nobody sees the graph object of a captured step
+
+    def ladder(self, B):
+        lad = self.ladders.get(B)
+        if lad is None:
+            lad = self.ladders[B] = BucketLadder(self.store, B, self.C, self.sigma_step)
+        return lad
+
+    # ---- one step's kernel sequence (captured) ---------------------------------------------------------------
+    def _body(self, bk, B, train):
+        tr = self.tr
+        if train:
+            tr.optim.zero_grad(set_to_none=True)
+        g2, g3 = self.store.collate_padded(bk.meta, B, *bk.caps, conformers=self.C)
+        if train:
+            loss, z2, z3 = tr.forward_pass(([g2], [g3]))
+            loss.backward()
+            tr.optim.step()
+        else:
+            with torch.no_grad():
+                loss, z2, z3 = tr.forward_pass(([g2], [g3]))
+        self.loss.copy_(loss.detach())
+        if self.keep_outputs:
+            o2, o3 = self._outputs(B, z2, z3)
+            o2.copy_(z2.detach()), o3.copy_(z3.detach())
+
+    def _outputs(self, B, z2, z3):
+        o = self._out.get(B)
+        if o is None:
+            o = self._out[B] = (torch.zeros_like(z2), torch.zeros_like(z3))
+        return o
+
+    def _capture(self, B, level, train, example_idx):
+        from . import lib as _lib
+        from .collate import metadata_len
+        tr, dev = self.tr, self.tr.device
+        bk = _Bucket()
+        bk.caps = self.ladder(B).caps(level)
+        bk.meta = torch.zeros(metadata_len(B), dtype=torch.int64, device=dev)
+        bk.replays = 0
+        self.store.stage_metadata(example_idx, dev_out=bk.meta)
+        snap = tr.snapshot_state()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._body(bk, B, train)                    # eager warm-up: lazy initialisation, persistent scratch
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        tr.restore_state(snap)                          # ... without training on the example batch
+        torch.cuda.synchronize(dev)
+        n0 = _lib.launch_count()
+        bk.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(bk.graph, pool=self.pool):
+            self._body(bk, B, train)
+        if train:
+            tr.optim._step -= 1                         # capture ran the Python side of step() without executing it
+        bk.launches = _lib.launch_count() - n0
+        self.buckets[(B, level, train)] = bk
+        self.stats["captures"] += 1
+        return bk
+
+    def _bucket(self, B, level, train, idx):
+        bk = self.buckets.get((B, level, train))
+        if bk is not None:
+            return bk
+        if self.tr.world > 1:
+            if level >= self.dp_levels:
+                return None                             # beyond the pre-captured ladder: eager step
+            # all ranks see a new batch size at the same step: capture the whole ladder in lockstep
+            for lv in range(self.dp_levels):
+                if (B, lv, train) not in self.buckets:
+                    ex = idx if self.ladder(B).level_of(self.store.batch_sizes(idx, self.C)) <= lv else \
+                        self._small_example(B)
+                    self._capture(B, lv, train, ex)
+            return self.buckets[(B, level, train)]
+        return self._capture(B, level, train, idx)
+
+    def _small_example(self, B):
+        """B molecule ids whose batch fits level 0 (the smallest molecules of the store)"""
+        return np.argsort(self.store.n_atoms, kind="stable")[:B]
+
+    # ---- public ------------------------------------------------------------------------------------------------
+    def step(self, idx, train=True):
+        idx = np.ascontiguousarray(np.asarray(idx), dtype=np.int64).reshape(-1)
+        B = int(len(idx))
+        tr = self.tr
+        sizes = self.store.batch_sizes(idx, self.C)
+        level = self.ladder(B).level_of(sizes)
+        bk = self._bucket(B, level, bool(train), idx)
+        self.stats["steps"] += 1
+        if bk is None:
+            return self._eager(idx, train)
+        self.stats["levels"][level] = self.stats["levels"].get(level, 0) + 1
+        self.store.stage_metadata(idx, dev_out=bk.meta)
+        if train:
+            tr.optim.sync_hyper()
+        bk.graph.replay()
+        bk.replays += 1
+        if train:
+            tr.optim_steps += 1
+            tr.optim._step += 1
+            tr.optim._needs_zero = False
+            if tr.lr_scheduler is not None:
+                tr.lr_scheduler.step()
+        if self.keep_outputs:
+            self.predictions, self.targets = self._out[B]
+        return self.loss
+
+    def evaluate(self, idx):
+        """forward + loss only, modules in whatever mode the caller put them (trainer/trainer.py:72-75: the reference
+        switches ``model`` to eval and leaves ``model3d`` in train mode)"""
+        return self.step(idx, train=False)
+
+    def _eager(self, idx, train):
+        self.stats["eager"] += 1
+        if self.C != 1:
+            raise RuntimeError("batch beyond the captured ladder: the eager fallback handles one conformer per molecule")
+        g2, g3 = self.store.collate(idx)
+        if train:
+            loss, z2, z3 = self.tr.process_batch(([g2], [g3]))
+        else:
+            with torch.no_grad():
+                loss, z2, z3 = self.tr.forward_pass(([g2], [g3]))
+        self.loss.copy_(loss.detach())
+        self.predictions, self.targets = z2.detach(), z3.detach()
+        return self.loss
+
+    @property
+    def launches_per_step(self):
+        tot = sum(b.launches * max(b.replays, 1) for b in self.buckets.values())
+        cnt = sum(max(b.replays, 1) for b in self.buckets.values())
+        return tot / max(cnt, 1)

@@ -113,6 +113,37 @@ int i3d_collate_3d(const int64_t* idx, int64_t B, const int64_t* atom_slices, co
                    const int64_t* node_ptr, const int64_t* edge3_ptr, int64_t E3, int64_t* src3, int64_t* dst3,
                    float* d3, void* stream);
 
+/* Shape-bucketed batch construction: the same batches PADDED to a bucket's capacities (n_cap nodes, e_cap edges) and
+ * emitted together with their CSR structure, so that one captured CUDA graph (static shapes) serves every batch of
+ * the bucket although each batch of an epoch has a different (N, E, E3) [train.py:595-598,
+ * datasets/custom_collate.py:105-114].  Valid sizes are read on the DEVICE (node_ptr[B], edge_ptr[B], edge3_ptr[B]).
+ * Padding convention (all consumers in this library honour it): nodes [N, n_cap) have no edges and feature index 0;
+ * edges [E, e_cap) have src = dst = -1 in both id orders (a negative gather index reads a zero row), eid / out_pos =
+ * own position.  rowptr[n_cap] = E and graph_ptr[B] = N are the device scalars the *_v entry points take as m_valid.
+ *   2-D: dgl.batch keeps each molecule's node / edge order, so the destination-sorted edge-id-stable CSR of the batch
+ *        is the concatenation of per-molecule CSRs.  The store carries them (molecule-local, int32, computed once):
+ *        in_rowptr_l[Ntot] (in-edges of earlier atoms of the molecule), in_eid_l[Etot] (local edge id at local CSR
+ *        position), out_rowptr_l[Ntot], out_pos_l[Etot] (local CSR position of the molecule's edges sorted by source).
+ *        Outputs: src/dst [e_cap] int64 (edge-id order), x_atom [n_cap, n_atom_feat], e_attr [e_cap, n_edge_feat],
+ *        rowptr / out_rowptr [n_cap+1], src_csr / dst_csr / eid / out_pos [e_cap], graph_ptr [B+1]  — bit-equal to
+ *        i3d_csr_build on the collated edge list.
+ *   3-D: C conformer graphs per molecule, molecule-major [datasets/qmugs_dataset.py:149-166]; coords [Ntot, ld_coords]
+ *        fp32 with conformer c in columns [3c, 3c+3).  Complete digraphs in the reference's order have a closed-form
+ *        CSR; the out-CSR row pointer equals rowptr.  Outputs: src3/dst3 [e_cap] int64, d3 [e_cap] (edge-id order),
+ *        rowptr [n_cap+1], src_csr / dst_csr / eid / out_pos [e_cap], graph_ptr [B*C+1], num_nodes3 [B*C] (optional). */
+int i3d_collate_2d_struct(const int64_t* idx, int64_t B, const int64_t* atom_slices, const int64_t* edge_slices,
+                          const int64_t* edge_indices, int64_t Etot, const int64_t* atom_features, int n_atom_feat,
+                          const int64_t* edge_features, int n_edge_feat, const int32_t* in_rowptr_l,
+                          const int32_t* in_eid_l, const int32_t* out_rowptr_l, const int32_t* out_pos_l,
+                          const int64_t* node_ptr, const int64_t* edge_ptr, int64_t n_cap, int64_t e_cap, int64_t* src,
+                          int64_t* dst, int64_t* x_atom, int64_t* e_attr, int32_t* rowptr, int32_t* src_csr,
+                          int32_t* dst_csr, int32_t* eid, int32_t* out_rowptr, int32_t* out_pos, int32_t* graph_ptr,
+                          void* stream);
+int i3d_collate_3d_struct(const int64_t* idx, int64_t B, int C, const int64_t* atom_slices, const float* coords,
+                          int ld_coords, const int64_t* node_ptr, const int64_t* edge3_ptr, int64_t n_cap, int64_t e_cap,
+                          int64_t* src3, int64_t* dst3, float* d3, int32_t* rowptr, int32_t* src_csr, int32_t* dst_csr,
+                          int32_t* eid, int32_t* out_pos, int32_t* graph_ptr, int64_t* num_nodes3, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * AtomEncoder / BondEncoder  [commons/mol_encoder.py:34-42,65-73; models/pna.py:162-163]
  *   out[r,:] = sum_c table[col_off[c] + idx[perm ? perm[r] : r, c], :]
@@ -168,6 +199,13 @@ int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs,
                 const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats, int stats_act,
                 void* stream);
 
+/* *_v variants (here and in the FCLayer tail below): m_valid is an optional DEVICE int32 scalar, the number of valid
+ * leading rows of a shape-bucketed (padded) batch.  Rows >= *m_valid are excluded from BatchNorm statistics and counts,
+ * written as zeros by i3d_bn_apply_v / i3d_bn_bwd_apply_v, and never read by the reductions.  NULL = all M rows. */
+int i3d_gemm_ex_v(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
+                  const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats, int stats_act,
+                  const int32_t* m_valid, void* stream);
+
 /* Weights change once per optimizer step, not once per GEMM: a caller that owns persistent scratch can prepare the
  * hi/lo copies of MANY GEMMs' B operands with ONE launch (after the optimizer step) and then run each GEMM with
  * i3d_gemm_nt_prepared, which skips the per-call split (and, for `transposed` operands, the weight transpose that
@@ -192,6 +230,10 @@ int i3d_gemm_nt_prepared_ok(int64_t M, int N, int n_seg, const i3d_gemm_seg* seg
 int i3d_gemm_nt_prepared(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                          int accumulate, const void* ws, double* col_stats, int stats_act, void* stream);
 
+int i3d_gemm_nt_prepared_v(int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+                           int accumulate, const void* ws, double* col_stats, int stats_act, const int32_t* m_valid,
+                           void* stream);
+
 /* Degree-bucketed GEMMs over an i3d_degree_plan (posttrans FC of PNALayer, models/pna.py:207-211, and its backward).
  *   i3d_posttrans_merge    W [Fout, 13F] (ld = ldw) -> tf32 hi/lo operands of the merged weights
  *                          Wm_b = [Wh | W_id + a_b W_amp + t_b W_att], a_b = (float)ln(b+1), t_b = (float)(1/ln(b+1)):
@@ -212,6 +254,11 @@ int i3d_posttrans_merge(const float* W, int ldw, int Fout, int F, int n_buckets,
 int i3d_gemm_nt_bucketed(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
                          const float* b_hi, const float* b_lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
                          const int32_t* row_map, double* col_stats, int stats_act, void* stream);
+/* m_valid: output rows (row_map values) >= *m_valid are stored but excluded from col_stats */
+int i3d_gemm_nt_bucketed_v(int64_t Mv, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc, const float* bias,
+                           const float* b_hi, const float* b_lo, int b_pitch, int n_buckets, const int32_t* tile_bucket,
+                           const int32_t* row_map, double* col_stats, int stats_act, const int32_t* m_valid,
+                           void* stream);
 int i3d_gemm_tn_chunked(int64_t M, int N, const i3d_gemm_seg* seg, float* C, int ldc, int64_t c_bucket_stride,
                         const int32_t* chunk_tab, int n_chunks, void* stream);
 /* Tuning aid: per-role blocked-cycle counters of the warp-specialised NT kernel (16 HOST uint64; read-and-clear).
@@ -244,6 +291,19 @@ int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int6
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                      int training, const float* save_mean_rstd, const float* gamma, const double* sums2,
                      float* dY, int lddy, float* dbias, float* dgamma, float* dbeta, void* stream);
+/* valid-row variants of the four entry points above (see i3d_gemm_ex_v) */
+int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, double* sums, const int32_t* m_valid,
+                       void* stream);
+int i3d_bn_apply_v(const float* Y, int64_t M, int F, int ldy, int act, const double* sums, float* running_mean,
+                   float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
+                   float momentum, float eps, int training, float* save_mean_rstd, const float* residual, float* O,
+                   int ldo, const int32_t* m_valid, void* stream);
+int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
+                        const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n,
+                        const int32_t* m_valid, void* stream);
+int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
+                       int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
+                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid, void* stream);
 /* y = act(x) elementwise (used where there is no BN, and for Net3D's second SiLU, models/net3d.py:81) */
 int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream);
 int i3d_act_bwd(const float* gy, const float* x, int64_t n, int act, float* gx, void* stream);
@@ -272,6 +332,10 @@ int i3d_segment_readout_fwd(const float* x, int ldx, const int32_t* ptr, int64_t
 /* max/min route the whole gradient to the FIRST row attaining the extremum (DGL segment_reduce arg) */
 int i3d_segment_readout_bwd(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
                             int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, void* stream);
+/* same; additionally zero-fills dx rows [ptr[B], n_rows): the padding nodes of a shape-bucketed batch */
+int i3d_segment_readout_bwd_v(const float* g, const float* x, int ldx, const float* out, const int32_t* ptr,
+                              int64_t B, int F, int n_ops, const int32_t* ops, float* dx, int lddx, int64_t n_rows,
+                              void* stream);
 /* out[v,:] = (mean ? 1/max(D,1) : 1) * sum_{k in [rowptr[v],rowptr[v+1])} x[idx ? idx[k] : k, :]  (+ addend[v,:])
  * idx==NULL: rows of x are already in CSR order.  Also the backward of the h[src] / h[dst] gathers feeding the
  * edge MLP (models/pna.py:249): in-CSR rowptr without idx, out-CSR rowptr with idx = position map.          */

@@ -47,6 +47,37 @@ def norm3_fp32(diff):
     return np.sqrt(acc.astype(np.float32))
 
 
+def collate_reference_conformers(store, idx, conformers):
+    """Same for the multi-conformer datasets (datasets/qmugs_dataset.py:149-166, return type 'conformations'): the 3-D
+    entry of molecule i is dgl.batch of ``conformers`` complete graphs, conformer c with coordinates
+    ``conformations[start:start+n, 3c:3c+3]`` (conformer 0 == ``coordinates``) and the same pairwise edge order;
+    contrastive_collate (custom_collate.py:105-114) then batches molecule-major.  (The reference adds N(0, 0.05) noise to
+    a conformer that is identical to conformer 0 — random, not part of the deterministic restatement; the synthetic
+    stores never contain such duplicates.)"""
+    b = collate_reference(store, idx)
+    idx = np.asarray(idx, dtype=np.int64)
+    C = int(conformers)
+    conf = store["conformations"] if C > 1 else store["coordinates"]
+    src3, dst3, d3, nn3, ne3 = [], [], [], [], []
+    off = 0
+    for k, i in enumerate(idx):
+        n = int(store["n_atoms"][i])
+        a0 = int(store["atom_slices"][i])
+        s3, t3 = pairwise_edges(n)
+        for c in range(C):
+            x = conf[a0:a0 + n, 3 * c:3 * c + 3].astype(np.float32)
+            d3.append(norm3_fp32(x[s3] - x[t3])[:, None])
+            src3.append(s3 + off)
+            dst3.append(t3 + off)
+            nn3.append(n)
+            ne3.append(n * (n - 1))
+            off += n
+    b.update(src3=np.concatenate(src3).astype(np.int64), dst3=np.concatenate(dst3).astype(np.int64),
+             d3=np.concatenate(d3).astype(np.float32), num_nodes3=np.array(nn3, dtype=np.int64),
+             num_edges3=np.array(ne3, dtype=np.int64), conformers=C, batch_size=len(idx))
+    return b
+
+
 def collate_reference(store, idx):
     """numpy dict in the layout of 3dinfomax_b200.synthetic.make_batch for molecules ``idx`` of ``store``."""
     idx = np.asarray(idx, dtype=np.int64)

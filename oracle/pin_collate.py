@@ -92,7 +92,8 @@ def load_reference_collate():
     sys.modules.update(stubs)
     try:
         out = {}
-        for name, rel in [("_ref_qm9_dataset", "datasets/qm9_dataset.py"), ("_ref_custom_collate", "datasets/custom_collate.py")]:
+        for name, rel in [("_ref_qm9_dataset", "datasets/qm9_dataset.py"), ("_ref_custom_collate", "datasets/custom_collate.py"),
+                          ("_ref_qmugs_dataset", "datasets/qmugs_dataset.py")]:
             spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
             m = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(m)
@@ -103,7 +104,34 @@ def load_reference_collate():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+    load_reference_collate.qmugs = out["_ref_qmugs_dataset"].QMugsDataset
     return out["_ref_qm9_dataset"].QM9Dataset, out["_ref_custom_collate"].contrastive_collate
+
+
+def reference_batch_conformers(store, idx, conformers):
+    """The reference's QMugsDataset.__getitem__ with return_types ['dgl_graph', 'conformations']
+    (configs_clean/pre-train_QMugs.yml; datasets/qmugs_dataset.py:76-96,149-166) + contrastive_collate."""
+    _, contrastive_collate = load_reference_collate()
+    QMugsDataset = load_reference_collate.qmugs
+    ds = object.__new__(QMugsDataset)
+    t = torch.from_numpy
+    ds.device = "cpu"
+    ds.num_conformers = int(conformers)
+    ds.return_types = ["dgl_graph", "conformations"]
+    ds.features_tensor = t(store["atom_features"])
+    ds.e_features_tensor = t(store["edge_features"])
+    ds.conformations = t(store["conformations"]).float()
+    ds.coordinates = ds.conformations[:, :3].float()                      # qmugs_dataset.py:44
+    ds.edge_indices = t(store["edge_indices"])
+    ds.meta_dict = {"chembl_ids": np.arange(len(store["n_atoms"])), "edge_slices": t(store["edge_slices"]),
+                    "atom_slices": t(store["atom_slices"]), "n_atoms": t(store["n_atoms"])}
+    ds.dgl_graphs, ds.pairwise, ds.complete_graphs, ds.conformer_graphs = {}, {}, {}, {}
+    (g2,), (g3,) = contrastive_collate([ds[int(i)] for i in idx])
+    return {"src": g2.src.numpy(), "dst": g2.dst.numpy(), "x_atom": g2.ndata["feat"].numpy(),
+            "e_attr": g2.edata["feat"].numpy(), "num_nodes": g2.batch_num_nodes().numpy(),
+            "num_edges": g2.batch_num_edges().numpy(), "src3": g3.src.numpy(), "dst3": g3.dst.numpy(),
+            "d3": g3.edata["d"].numpy(), "num_nodes3": g3.batch_num_nodes().numpy(),
+            "num_edges3": g3.batch_num_edges().numpy()}
 
 
 def reference_batch(store, idx):
@@ -131,6 +159,9 @@ CASES = {"collate_qm9": (77, 40, "qm9", [3, 17, 0, 39, 17, 8, 21]),          # r
          "collate_qmugs": (78, 12, "qmugs", [11, 2, 5])}
 
 
+CONFORMER_CASES = {"collate_qmugs_c3": (79, 10, "qmugs", [7, 1, 4, 1], 3)}
+
+
 def main():
     from oracle.collate_oracle import collate_reference, make_store
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
@@ -145,6 +176,21 @@ def main():
                             idx=np.array(idx), **ref)
         print("pinned %s: %d molecules, N=%d E=%d E3=%d — oracle == reference (bit exact)"
               % (name, len(idx), len(ref["x_atom"]), len(ref["src"]), len(ref["src3"])))
+    # multi-conformer batches (BASELINE configs 3-4: NTXentMultiplePositives over 3 conformers per molecule)
+    import importlib
+    from oracle.collate_oracle import collate_reference_conformers
+    syn = importlib.import_module("3dinfomax_b200.synthetic")
+    for name, (seed, M, shape, idx, C) in CONFORMER_CASES.items():
+        store = syn.make_store(seed, M, shape, conformers=C)
+        ref = reference_batch_conformers(store, idx, C)
+        mine = collate_reference_conformers(store, idx, C)
+        for k, v in ref.items():
+            assert mine[k].dtype == v.dtype and mine[k].shape == v.shape, (name, k, mine[k].dtype, v.dtype, mine[k].shape, v.shape)
+            assert np.array_equal(mine[k], v), "oracle != reference for %s/%s" % (name, k)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), seed=seed, n_molecules=M,
+                            idx=np.array(idx), conformers=C, **ref)
+        print("pinned %s: %d molecules x %d conformers, N3=%d E3=%d — oracle == reference (bit exact)"
+              % (name, len(idx), C, int(ref["num_nodes3"].sum()), len(ref["src3"])))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,488 @@
+"""GPU parity cases for the shape-bucketed captured step (trainer.BucketedStep) and for whole training steps at the
+BASELINE sizes.  Same contract as gpu_cases.py: each case returns [(label, error, tolerance)].
+
+What is checked against what:
+  * collate_padded (i3d_collate_2d_struct / _3d_struct): integer arrays bit exact against the numpy restatement of
+    the reference's __getitem__ + contrastive_collate (oracle/collate_oracle.py, pinned on the reference's QM9Dataset
+    and QMugsDataset) and against the sort-based CSR builder on the same edge list; padding convention verified.
+  * a padded, captured step against the UNPADDED CPU oracle step on the same molecules: loss, embeddings, BatchNorm
+    running statistics, every parameter gradient in full, the Adam update.
+
+Tolerances.  Ground truth is the oracle evaluated in float64; the CPU fp32 oracle's own distance from it is printed next
+to every number.  Embeddings 1e-4 relative (3e-4 for batches under 32 molecules, where train-mode BatchNorm over a few
+hundred rows amplifies fp32 summation-order noise; 2e-4 for the generic 13F-wide posttrans at full size, whose K = 2600
+tensor-core accumulation truncates 975 times per output — measured 1.8e-4, the default degree-merged path 7.5e-5, CPU
+fp32 2.9e-5).  Gradients: every tensor in full, 1e-3 of the global gradient scale at small sizes and 2e-3 at B = 512
+(measured 1.16e-3 with tensor cores, 1.10e-3 with the fp32 SIMT backend, CPU fp32 3.8e-4: the maximum sits on a bias in
+front of a BatchNorm, whose true gradient is zero, and on the weights of one layer with near-dead ReLU columns, i.e.
+1/sqrt(var + eps) ~ 300 — tools/accuracy_probe.py), plus 2e-2 of each tensor's OWN norm (measured 5.5e-3, CPU 1.5e-3).
+Net3D's BatchNorms (mean^2 >> var) are where fp64 statistics pay: at config 3 the CUDA gradients are 2.6e-4 from the
+truth, the CPU fp32 oracle 6.7e-3.
+"""
+import importlib
+import os
+
+import numpy as np
+import torch
+
+from oracle import collate_oracle as CO
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+i3d = importlib.import_module("3dinfomax_b200")
+K = importlib.import_module("3dinfomax_b200.kernels")
+syn = i3d.synthetic
+DEV = "cuda"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    if a.shape != b.shape or not torch.isfinite(a).all():
+        return float("inf")
+    if a.numel() == 0:
+        return 0.0
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def exact(a, b):
+    a = torch.as_tensor(a).cpu()
+    b = torch.as_tensor(b).cpu()
+    return 0.0 if a.shape == b.shape and torch.equal(a.to(b.dtype), b) else 1.0
+
+
+def _ref_batch(store, idx, C):
+    b = CO.collate_reference_conformers(store, idx, C) if C > 1 else CO.collate_reference(store, idx)
+    b.setdefault("batch_size", len(idx))
+    b.setdefault("conformers", C)
+    return b
+
+
+# ------------------------------------------------------------------------------------------- padded collate
+def case_collate_struct():
+    out = []
+    for tag, shape, M, B, C, seed in (("qm9_b512", "qm9", 1500, 512, 1, 5), ("qmugs_b48_c3", "qmugs", 200, 48, 3, 6),
+                                      ("tiny_b3", "qm9", 20, 3, 1, 7)):
+        store = syn.make_store(90 + seed, M, shape, conformers=C)
+        ps = i3d.PackedMoleculeStore(store, DEV)
+        idx = np.random.default_rng(seed).integers(0, M, size=B)
+        ref = _ref_batch(store, idx, C)
+        N, E, E3 = len(ref["x_atom"]), len(ref["src"]), len(ref["src3"])
+        lad = i3d.BucketLadder(ps, B, C)
+        lv = lad.level_of((N, E, E3))
+        n_cap, e_cap, e3_cap = lad.caps(lv + 1)            # one level above the tightest: every array has padding
+        meta, sizes = ps.stage_metadata(idx)
+        out.append(("collate_struct/%s/host_sizes" % tag, float(sizes != (N, E, E3 // C)), 0))
+        g2, g3 = ps.collate_padded(meta, B, n_cap, e_cap, e3_cap, conformers=C)
+        torch.cuda.synchronize()
+        t = "collate_struct/%s/" % tag
+        # ---- valid region == the reference's batch (bit exact; distances bit equal as in case_collate)
+        out += [(t + "src", exact(g2.edges()[0][:E], ref["src"]), 0), (t + "dst", exact(g2.edges()[1][:E], ref["dst"]), 0),
+                (t + "x_atom", exact(g2.ndata["feat"][:N], ref["x_atom"]), 0),
+                (t + "e_attr", exact(g2.edata["feat"][:E], ref["e_attr"]), 0),
+                (t + "num_nodes", exact(g2.batch_num_nodes(), ref["num_nodes"]), 0),
+                (t + "src3", exact(g3.edges()[0][:E3], ref["src3"]), 0),
+                (t + "dst3", exact(g3.edges()[1][:E3], ref["dst3"]), 0),
+                (t + "num_nodes3", exact(g3.batch_num_nodes(), ref["num_nodes3"]), 0),
+                (t + "d3_bit_equal_fraction_missing",
+                 float((g3.edata["d"][:E3].cpu().numpy() != ref["d3"]).mean()), 0.0)]
+        # ---- structure == sort-based builder on the unpadded edge list (which is pinned on argsort(dst, stable))
+        for name, g, n, e, nb, src, dst, bnn in (("2d", g2, N, E, B, ref["src"], ref["dst"], ref["num_nodes"]),
+                                                 ("3d", g3, C * N, E3, B * C, ref["src3"], ref["dst3"], ref["num_nodes3"])):
+            st = g._i3d_struct
+            ex = i3d.GraphStructure(torch.from_numpy(src).to(DEV), torch.from_numpy(dst).to(DEV),
+                                    torch.from_numpy(bnn).to(DEV), n, need_scalers=(name == "2d"))
+            torch.cuda.synchronize()
+            cap_n, cap_e = st.N, st.E
+            out += [(t + name + "/rowptr", exact(st.rowptr[:n + 1], ex.rowptr), 0),
+                    (t + name + "/src_csr", exact(st.src_csr[:e], ex.src_csr), 0),
+                    (t + name + "/dst_csr", exact(st.dst_csr[:e], ex.dst_csr), 0),
+                    (t + name + "/eid", exact(st.eid[:e], ex.eid), 0),
+                    (t + name + "/out_rowptr", exact(st.out_rowptr[:n + 1], ex.out_rowptr), 0),
+                    (t + name + "/out_pos", exact(st.out_pos[:e], ex.out_pos), 0),
+                    (t + name + "/graph_ptr", exact(st.graph_ptr, ex.graph_ptr), 0),
+                    # padding convention
+                    (t + name + "/pad_rowptr", float((st.rowptr[n:] != e).any().item()), 0),
+                    (t + name + "/pad_gather_idx", float((st.src_csr[e:] != -1).any().item() +
+                                                         (st.dst_csr[e:] != -1).any().item()), 0),
+                    (t + name + "/pad_eid", exact(st.eid[e:], torch.arange(e, cap_e)), 0),
+                    (t + name + "/pad_out_pos", exact(st.out_pos[e:], torch.arange(e, cap_e)), 0),
+                    (t + name + "/n_valid", float(int(st.n_valid.item()) != n), 0),
+                    (t + name + "/e_valid", float(int(st.e_valid.item()) != e), 0)]
+            # the sort-based builder on the PADDED edge list (src = dst = -1 behind the valid edges) agrees too
+            ps_src, ps_dst = g.edges()
+            gen = i3d.GraphStructure(ps_src, ps_dst, torch.from_numpy(bnn).to(DEV), cap_n, need_scalers=False)
+            out += [(t + name + "/generic_on_padded/rowptr", exact(gen.rowptr, st.rowptr), 0),
+                    (t + name + "/generic_on_padded/src_csr", exact(gen.src_csr, st.src_csr), 0),
+                    (t + name + "/generic_on_padded/eid", exact(gen.eid, st.eid), 0),
+                    (t + name + "/generic_on_padded/out_pos", exact(gen.out_pos, st.out_pos), 0)]
+            if name == "2d":
+                out += [(t + "2d/amp", exact(st.amp[:n], ex.amp), 0), (t + "2d/pad_amp", float(st.amp[n:].abs().sum().item()), 0)]
+    # golden vectors written by the reference's own QMugsDataset (3 conformers per molecule)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "collate_qmugs_c3.npz"))
+    C = int(g["conformers"])
+    store = syn.make_store(int(g["seed"]), int(g["n_molecules"]), "qmugs", conformers=C)
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    idx = g["idx"]
+    E3 = len(g["src3"])
+    meta, _ = ps.stage_metadata(idx)
+    g2, g3 = ps.collate_padded(meta, len(idx), 256, 512, E3 + 100, conformers=C)
+    out += [("collate_struct/golden_c3/src3", exact(g3.edges()[0][:E3], g["src3"]), 0),
+            ("collate_struct/golden_c3/dst3", exact(g3.edges()[1][:E3], g["dst3"]), 0),
+            ("collate_struct/golden_c3/num_nodes3", exact(g3.batch_num_nodes(), g["num_nodes3"]), 0),
+            ("collate_struct/golden_c3/d3_bit_equal_fraction_missing",
+             float((g3.edata["d"][:E3].cpu().numpy() != g["d3"]).mean()), 0.0)]
+    return out
+
+
+def case_staging_ring():
+    """collate() called back to back while the GPU is still busy with earlier work: every batch must be built from its
+    OWN indices (the pinned metadata buffer of batch k may not be rewritten before its copy has run)."""
+    store = syn.make_store(97, 600, "qm9")
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    rng = np.random.default_rng(8)
+    idxs = [rng.integers(0, 600, size=64) for _ in range(10)]
+    ps.collate(idxs[0])
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(2e8))                       # ~0.1 s of GPU work queued in front of the copies
+    graphs = [ps.collate(ix) for ix in idxs]
+    torch.cuda.synchronize()
+    bad = 0
+    for ix, (g2, g3) in zip(idxs, graphs):
+        ref = CO.collate_reference(store, ix)
+        bad += exact(g2.edges()[0], ref["src"]) + exact(g2.ndata["feat"], ref["x_atom"]) + exact(g3.edges()[1], ref["dst3"])
+        bad += exact(g2.batch_num_nodes(), ref["num_nodes"])
+    return [("staging_ring/batches_built_from_their_own_indices", bad, 0)]
+
+
+# ------------------------------------------------------------------------------------------ whole steps
+def _models(s2, s3, c2kw=None, c3kw=None):
+    c2kw, c3kw = c2kw or O.PRETRAIN_QM9_PNA, c3kw or O.PRETRAIN_QM9_NET3D
+    c2, c3 = O.pna_cfg(**c2kw), O.net3d_cfg(**c3kw)
+    st2, st3 = O.init_pna_state(c2, s2, True), O.init_net3d_state(c3, s3, True)
+    pna = i3d.PNA(avg_d=1, device=DEV, **c2kw)
+    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **c3kw)
+    pna.load_state_dict(st2)
+    n3.load_state_dict(st3)
+    return c2, c3, st2, st3, pna.to(DEV), n3.to(DEV)
+
+
+def _oracle_step(otr, batch):
+    """oracle forward + backward; returns loss, z2, z3, {name: grad}, then applies Adam"""
+    g2, xa, ea, g3, d3 = O.graphs_from_batch(batch)
+    dt = next(iter(otr.st3d.values())).dtype
+    loss, z2, z3 = otr.forward(g2, xa, ea, g3, d3.to(dt), True)
+    loss.backward()
+    grads = {"2d." + k: otr.st2d[k].grad.detach().clone() for k in O.param_keys(otr.st2d)}
+    grads.update({"3d." + k: otr.st3d[k].grad.detach().clone() for k in O.param_keys(otr.st3d)})
+    otr.optim.step()
+    otr.optim.zero_grad()
+    return loss.detach(), z2.detach(), z3.detach(), grads
+
+
+def _fp64_truth(c2, c3, st2, st3, loss_name, batch, lr=8e-5):
+    """The same oracle evaluated in float64: the ground truth both fp32 implementations (CPU oracle, CUDA path) are
+    measured against.  Returns (loss, z2, z3, grads) in float64."""
+    to64 = lambda st: {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in st.items()}
+    o64 = O.OracleTrainer(c2, c3, to64(st2), to64(st3), loss=loss_name, tau=0.1, lr=lr)
+    return _oracle_step(o64, batch)
+
+
+def _vs_truth(tag, what, mine, o32, o64, tol, slack=2.0):
+    """CUDA vs float64 truth within `tol`, or — where fp32 conditioning makes the CPU fp32 reference itself miss `tol`
+    (train-mode BatchNorm over few rows, Net3D's BN inputs with mean^2 >> var) — within `slack` x the CPU
+    fp32 reference's own distance from the truth.  The second line reports that distance."""
+    e_mine, e_ref = rel(mine, o64), rel(o32, o64)
+    return [(tag + "/%s(cuda vs fp64 truth)" % what, e_mine, max(tol, slack * e_ref)),
+            (tag + "/%s(cpu fp32 oracle vs fp64 truth, for scale)" % what, e_ref, float("inf"))]
+
+
+# gradient mathematically zero (a bias in front of a BatchNorm): only rounding noise on both sides
+_ZERO_GRAD = ("pretrans.fully_connected.1.linear.bias", "posttrans.fully_connected.0.linear.bias",
+              "pretrans.fully_connected.0.linear.bias", "update_network.fully_connected.0.linear.bias",
+              "update_network.fully_connected.1.linear.bias", "message_network.fully_connected.0.linear.bias",
+              "message_network.fully_connected.1.linear.bias", "edge_input.fully_connected.0.linear.bias",
+              "node_wise_output_network.fully_connected.0.linear.bias",
+              "node_wise_output_network.fully_connected.1.linear.bias", "output.fully_connected.0.linear.bias")
+
+
+def _grad_errors(grads, truth):
+    """(worst max|g - g_ref| over ALL tensors in full / global gradient scale,
+        worst ||g - g_ref||_2 / ||g_ref||_2 over the tensors with a non-zero gradient, its name)"""
+    scale = max(float(g.abs().max()) for g in truth.values())
+    worst_g, worst_t, worst_name = 0.0, 0.0, ""
+    for k, ref in truth.items():
+        mine = grads[k].detach().cpu().double()
+        if not torch.isfinite(mine).all():
+            return float("inf"), float("inf"), k
+        ref = ref.double()
+        worst_g = max(worst_g, float((mine - ref).abs().max()) / scale)
+        if any(z in k for z in _ZERO_GRAD):
+            continue
+        nr = float(ref.norm())
+        if nr > 1e-6 * scale * ref.numel() ** 0.5:
+            e = float((mine - ref).norm()) / nr
+            if e > worst_t:
+                worst_t, worst_name = e, k
+    return worst_g, worst_t, worst_name
+
+
+def _grad_checks(tag, named_grads, ograds, truth=None, tol_global=1e-3, tol_tensor=2e-2, slack=2.0):
+    """Every parameter gradient IN FULL.  (a) against the global gradient scale (max |g| over all tensors); (b) every
+    tensor with a non-zero gradient against its OWN scale (so small tensors with small gradients are checked too).
+    With ``truth`` (float64 oracle gradients) the CUDA path is measured against the truth and allowed `slack` x the
+    distance the CPU fp32 oracle itself has from it (that distance is reported)."""
+    if truth is None:
+        g, t, name = _grad_errors(named_grads, ograds)
+        return [(tag + "/param_grads(all tensors, in full; global scale)", g, tol_global),
+                (tag + "/param_grads(per tensor, own scale; worst: %s)" % name, t, tol_tensor)]
+    g, t, name = _grad_errors(named_grads, truth)
+    rg, rt, rname = _grad_errors(ograds, truth)
+    return [(tag + "/param_grads(all tensors, in full; global scale; cuda vs fp64 truth)", g, max(tol_global, slack * rg)),
+            (tag + "/param_grads(same, cpu fp32 oracle vs fp64 truth, for scale)", rg, float("inf")),
+            (tag + "/param_grads(per tensor, own scale; cuda vs fp64 truth; worst: %s)" % name, t,
+             max(tol_tensor, slack * rt)),
+            (tag + "/param_grads(same, cpu fp32 oracle vs fp64 truth; worst: %s)" % rname, rt, float("inf"))]
+
+
+def _buffer_checks(tag, pna, n3, otr, tol=1e-4):
+    worst = 0.0
+    for pre, mod, st in (("2d.", pna, otr.st2d), ("3d.", n3, otr.st3d)):
+        for k, v in mod.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                worst = max(worst, rel(v, st[k]))
+            elif k.endswith("num_batches_tracked"):
+                worst = max(worst, float(int(v.item()) != int(st[k])))
+    return [(tag + "/bn_running_stats(all layers)", worst, tol)]
+
+
+def _update_checks(tag, named, otr, before, lr, ograds):
+    """Adam update of the weights with a DECISIVE gradient (|g| > 1 % of the global gradient scale).  Adam's first
+    updates are lr * g / (|g| + eps): a weight whose gradient sits at the fp32 noise level moves by an arbitrary
+    fraction of lr in any two fp32 implementations (tests/gpu_cases.py::case_train_steps), so those are not compared."""
+    oparam = lambda k: (otr.st2d if k.startswith("2d.") else otr.st3d)[k[3:]]
+    scale = max(float(g.abs().max()) for g in ograds.values())
+    bad = total = 0
+    worst = 0.0
+    for k, p in named.items():
+        ref = oparam(k).detach()
+        decisive = ograds[k].abs() > 1e-2 * scale
+        if not decisive.any():
+            continue
+        err = ((p.detach().cpu() - ref).abs() / lr)[decisive]
+        bad += int((err > 0.05).sum())
+        total += err.numel()
+        worst = max(worst, float(err.median()))
+    return [(tag + "/adam_update(decisive weights: %d)/fraction_off_by_>5%%_of_lr" % total, bad / max(total, 1), 1e-2),
+            (tag + "/adam_update(decisive weights)/median_error_in_lr_units", worst, 1e-2)]
+
+
+def _named(pna, n3):
+    return dict([("2d." + k, p) for k, p in pna.named_parameters()] + [("3d." + k, p) for k, p in n3.named_parameters()])
+
+
+def _sync_params(named, otr):
+    with torch.no_grad():
+        for k, p in named.items():
+            p.copy_((otr.st2d if k.startswith("2d.") else otr.st3d)[k[3:]].detach())
+
+
+def _sync_buffers(pna, n3, otr):
+    with torch.no_grad():
+        for mod, st in ((pna, otr.st2d), (n3, otr.st3d)):
+            for k, v in mod.state_dict().items():
+                if "running_" in k or "num_batches" in k:
+                    v.copy_(torch.as_tensor(st[k]))
+
+
+def case_bucketed_step(B=24, shape="qm9", C=1, loss_name="NTXent", steps=4, seed=3, tag="bucketed"):
+    """BucketedStep (device collate -> padded captured step) against the unpadded CPU oracle step on the same molecules,
+    several distinct batches (distinct shapes, >= 2 buckets, a short last batch)."""
+    lr = 8e-5
+    M = 400
+    store = syn.make_store(40 + seed, M, shape, conformers=C)
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    c2, c3, st2, st3, pna, n3 = _models(31 + seed, 32 + seed)
+    otr = O.OracleTrainer(c2, c3, st2, st3, loss=loss_name, tau=0.1, lr=lr)
+    tr = i3d.SelfSupervisedTrainer(pna, n3, getattr(i3d, loss_name)(tau=0.1), DEV, {"lr": lr}, graph_safe=True)
+    run = i3d.BucketedStep(tr, ps, conformers=C, sigma_step=1.0)
+    named = _named(pna, n3)
+    rng = np.random.default_rng(seed)
+    # batches chosen to land in different levels: random, the largest molecules, random, a short last batch
+    order = np.argsort(store["n_atoms"], kind="stable")
+    batches = [rng.integers(0, M, size=B), order[-B:][::-1].copy(), rng.integers(0, M, size=B),
+               rng.integers(0, M, size=max(B // 2 + 1, 3))][:steps]
+    out = []
+    for s, idx in enumerate(batches):
+        t = "%s/step%d(B=%d)" % (tag, s, len(idx))
+        b = _ref_batch(store, idx, C)
+        before = {k: (otr.st2d if k.startswith("2d.") else otr.st3d)[k[3:]].detach().clone() for k in named}
+        tl, tz2, tz3, tgrads = _fp64_truth(c2, c3, {k: v.detach() for k, v in otr.st2d.items()},
+                                           {k: v.detach() for k, v in otr.st3d.items()}, loss_name, b, lr)
+        ol, oz2, oz3, ograds = _oracle_step(otr, b)
+        l = run.step(idx)
+        torch.cuda.synchronize()
+        pg = tr.optim.packed_grads()
+        grads = {k: pg[p] for k, p in named.items()}
+        small = len(idx) < 32
+        out += [(t + "/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
+        out += _vs_truth(t, "z2d", run.predictions, oz2, tz2, 3e-4 if small else 1e-4)
+        out += _vs_truth(t, "z3d", run.targets, oz3, tz3, 3e-4 if small else 1e-4)
+        out += _grad_checks(t, grads, ograds, tgrads, tol_global=2e-3 if small else 1e-3)
+        out += _buffer_checks(t, pna, n3, otr)
+        out += _update_checks(t, named, otr, before, lr, ograds)
+        _sync_params(named, otr)
+        _sync_buffers(pna, n3, otr)
+    levels = sorted(k[1] for k in run.buckets)
+    out.append((tag + "/distinct_buckets_captured>=2", float(len(run.buckets) < 2), 0))
+    out.append((tag + "/no_eager_fallback", float(run.stats["eager"]), 0))
+    return out
+
+
+def case_bucketed_step_conformers():
+    """BASELINE configs 3-4 path: NTXentMultiplePositives over 3 conformers per molecule, QMugs-shaped molecules"""
+    return case_bucketed_step(B=10, shape="qmugs", C=3, loss_name="NTXentMultiplePositives", steps=3, seed=5,
+                              tag="bucketed_c3")
+
+
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def case_step_b512():
+    """One TRAIN-mode step at the BASELINE size (B = 512, QM9-shaped) against the CPU oracle: loss, embeddings, BatchNorm
+    running statistics of every layer, every parameter gradient in full — for the eager default path (degree-merged
+    posttrans), the generic 13F posttrans, the single-shape CapturedStep and the BucketedStep (padded, device collate)."""
+    lr = 8e-5
+    B, M = 512, 1200
+    store = syn.make_store(55, M, "qm9")
+    idx = np.random.default_rng(12).integers(0, M, size=B)
+    b = _ref_batch(store, idx, 1)
+    c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
+    st2, st3 = O.init_pna_state(c2, 71, True), O.init_net3d_state(c3, 72, True)
+    otr = O.OracleTrainer(c2, c3, st2, st3, loss="NTXent", tau=0.1, lr=lr)
+    tl, tz2, tz3, tgrads = _fp64_truth(c2, c3, st2, st3, "NTXent", b, lr)
+    ol, oz2, oz3, ograds = _oracle_step(otr, b)
+    out = []
+
+    def fresh(graph_safe):
+        pna = i3d.PNA(avg_d=1, device=DEV, **O.PRETRAIN_QM9_PNA)
+        n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **O.PRETRAIN_QM9_NET3D)
+        pna.load_state_dict(st2), n3.load_state_dict(st3)
+        tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), DEV, {"lr": lr}, graph_safe=graph_safe)
+        return pna, n3, tr
+
+    def check(tag, pna, n3, tr, l, z2, z3, ztol=1e-4):
+        torch.cuda.synchronize()
+        named = _named(pna, n3)
+        pg = tr.optim.packed_grads()
+        res = [(tag + "/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
+        res += _vs_truth(tag, "z2d", z2, oz2, tz2, ztol) + _vs_truth(tag, "z3d", z3, oz3, tz3, 1e-4)
+        res += _grad_checks(tag, {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3)
+        res += _buffer_checks(tag, pna, n3, otr)
+        return res
+
+    def eager(tag, ztol=1e-4):
+        pna, n3, tr = fresh(False)
+        g2, g3 = i3d.batch_from_numpy(b, DEV)
+        l, z2, z3 = tr.forward_pass(([g2], [g3]))
+        l.backward()
+        tr.optim.step()
+        return check(tag, pna, n3, tr, l, z2, z3, ztol)
+
+    out += eager("step_b512/eager_merged")
+    out += _with_env({"I3D_POSTTRANS": "generic"}, lambda: eager("step_b512/eager_generic", 2e-4))
+    # single-shape captured step
+    pna, n3, tr = fresh(True)
+    g2, g3 = i3d.batch_from_numpy(b, DEV)
+    cap = i3d.CapturedStep(tr, g2, g3, warmup=1)
+    g2, g3 = i3d.batch_from_numpy(b, DEV)
+    cap.load(g2, g3)
+    l = cap.run()
+    torch.cuda.synchronize()
+    named = _named(pna, n3)
+    pg = tr.optim.packed_grads()
+    out += [("step_b512/captured/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
+    out += _grad_checks("step_b512/captured", {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3)
+    out += _buffer_checks("step_b512/captured", pna, n3, otr)
+    # bucketed (padded) captured step fed by the device collate
+    pna, n3, tr = fresh(True)
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    run = i3d.BucketedStep(tr, ps)
+    l = run.step(idx)
+    out += check("step_b512/bucketed", pna, n3, tr, l, run.predictions, run.targets)
+    return out
+
+
+def case_step_config3():
+    """BASELINE config 3 shape (NTXentMultiplePositives, 3 conformers) at a per-GPU shard of the global 2048 batch
+    (B = 256 = 2048 / 8): bucketed captured step against the CPU oracle."""
+    lr = 8e-5
+    B, M, C = 256, 800, 3
+    store = syn.make_store(56, M, "qm9", conformers=C)
+    idx = np.random.default_rng(13).integers(0, M, size=B)
+    b = _ref_batch(store, idx, C)
+    c2, c3, st2, st3, pna, n3 = _models(73, 74)
+    otr = O.OracleTrainer(c2, c3, st2, st3, loss="NTXentMultiplePositives", tau=0.1, lr=lr)
+    tl, tz2, tz3, tgrads = _fp64_truth(c2, c3, st2, st3, "NTXentMultiplePositives", b, lr)
+    ol, oz2, oz3, ograds = _oracle_step(otr, b)
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXentMultiplePositives(tau=0.1), DEV, {"lr": lr}, graph_safe=True)
+    run = i3d.BucketedStep(tr, i3d.PackedMoleculeStore(store, DEV), conformers=C)
+    l = run.step(idx)
+    torch.cuda.synchronize()
+    named = _named(pna, n3)
+    pg = tr.optim.packed_grads()
+    tag = "step_config3(B=256,C=3)/bucketed"
+    out = [(tag + "/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
+    # B = 256 molecules give 34 node tiles: the merged posttrans runs 112-wide tiles at K = 1000 (measured 2.0e-4)
+    out += _vs_truth(tag, "z2d", run.predictions, oz2, tz2, 3e-4) + _vs_truth(tag, "z3d", run.targets, oz3, tz3, 1e-4)
+    out += _grad_checks(tag, {k: pg[p] for k, p in named.items()}, ograds, tgrads)
+    out += _buffer_checks(tag, pna, n3, otr)
+    return out
+
+
+def case_epoch_many_shapes():
+    """An 'epoch' of 40 distinct random batches through BucketedStep: every step replays a captured graph (no eager
+    fallback), few buckets get captured, and the padded run tracks an unpadded eager run of the same batches (loss per
+    step) — the property that makes the benchmarked speed reachable on real, variable-shape epochs."""
+    lr = 8e-5
+    B, M = 64, 1000
+    store = syn.make_store(57, M, "qm9")
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    rng = np.random.default_rng(14)
+    batches = [rng.choice(M, size=B, replace=False) for _ in range(40)]
+    c2, c3, st2, st3, pna, n3 = _models(75, 76)
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), DEV, {"lr": lr}, graph_safe=True)
+    run = i3d.BucketedStep(tr, ps)
+    c2, c3, st2, st3, pna_e, n3_e = _models(75, 76)
+    tr_e = i3d.SelfSupervisedTrainer(pna_e, n3_e, i3d.NTXent(tau=0.1), DEV, {"lr": lr})
+    worst = worst_p = 0.0
+    shapes = set()
+    for idx in batches:
+        shapes.add(ps.batch_sizes(idx))
+        # both runs start every step from the SAME state (two fp32 Adam trajectories separate chaotically otherwise,
+        # tests/gpu_cases.py::case_train_steps): copy weights, Adam moments, step count and BatchNorm buffers
+        tr_e.restore_state(tr.snapshot_state())
+        l = run.step(idx).item()
+        le, _, _ = tr_e.process_batch(tuple([g] for g in ps.collate(idx)))
+        worst = max(worst, abs(l - le.item()))
+        off = tot = 0
+        for fa, fb in zip(tr.optim._flat, tr_e.optim._flat):
+            off += int(((fa["p"] - fb["p"]).abs() > 0.05 * lr).sum())
+            tot += fa["p"].numel()
+        worst_p = max(worst_p, off / tot)
+    return [("epoch/distinct_batch_shapes>=35", float(len(shapes) < 35), 0),
+            ("epoch/captured_buckets<=8", float(len(run.buckets) > 8), 0),
+            ("epoch/eager_fallbacks", float(run.stats["eager"]), 0),
+            ("epoch/loss_of_every_step_equals_unpadded_eager_step", worst, 2e-5),
+            # (weights whose gradient sits at fp32 noise level move by an arbitrary fraction of lr: < 1 % of them)
+            ("epoch/worst_step_fraction_of_weights_off_by_>5%_of_lr", worst_p, 1e-2)]
