@@ -375,6 +375,11 @@ class WeightPrep:
             return
         ents = list(self.entries.values())
         if self._table is None:
+            if torch.cuda.is_current_stream_capturing():
+                # the upload below would be recorded instead of executed, and the table would live in the capturing
+                # graph's private pool: any later EAGER refresh would then run on a table that was never filled
+                raise RuntimeError("WeightPrep: the operand table must be built outside CUDA-graph capture — run one "
+                                   "eager forward and call refresh() before capturing (CapturedStep / BucketedStep do)")
             raw = b"".join(bytes(e.items) for e in ents)
             host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
             self._pinned.append(host)                       # a captured graph re-reads it on replay

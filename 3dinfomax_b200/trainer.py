@@ -160,7 +160,8 @@ class CapturedStep:
         torch.cuda.synchronize(dev)
         if snap is not None:
             trainer.restore_state(snap)
-            torch.cuda.synchronize(dev)
+        trainer.prep.refresh()          # operand table of the entries the warm-up registered: built eagerly, not captured
+        torch.cuda.synchronize(dev)
         from . import lib as _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
@@ -333,6 +334,7 @@ class BucketedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         tr.restore_state(snap)                          # ... without training on the example batch
+        tr.prep.refresh()                               # operand table built eagerly (never inside a capture)
         torch.cuda.synchronize(dev)
         n0 = _lib.launch_count()
         bk.graph = torch.cuda.CUDAGraph()

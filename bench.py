@@ -1,19 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — molecules/s of one full 3DInfomax pre-training step (PNA + Net3D + NTXent, fwd + bwd + Adam) on B200.
+"""bench.py — molecules/s of the 3DInfomax pre-training step (PNA + Net3D + NTXent, fwd + bwd + Adam) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--mode graph|eager]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|3|4] [--batch B]
+                    [--mode bucketed|eager] [--store-size M]
 
-Workload (config.workload): BASELINE.json configs[1] — QM9-shaped synthetic molecules, batch 512 PER GPU, the PNA
-the reference ships in configs_clean/pre-train_QM9.yml (hidden 200, 7 layers) + Net3D (hidden 20) + NTXent(tau 0.1),
-Adam lr 8e-5.  A "step" = CSR build, both encoders, loss, backward, gradient pack, [NCCL all-gather / reduce-scatter
-of embeddings + all-reduce of gradients when N>1], Adam — on one collated batch.
+Workloads (BASELINE.json `configs`):
+  --config 1 (default, the headline): QM9-shaped synthetic molecules, batch 512 PER GPU (weak scaling), the PNA the
+             reference ships in configs_clean/pre-train_QM9.yml (hidden 200, 7 layers) + Net3D (hidden 20) + NTXent
+             (tau 0.1), Adam lr 8e-5.
+  --config 3: the same encoders with NTXentMultiplePositives over 3 conformers per molecule, GLOBAL batch 2048 split
+             over the GPUs (strong scaling: 2048 / N molecules per GPU).
+  --config 4: configs_clean/pre-train_QMugs.yml shape — QMugs-shaped molecules (~40 atoms), 3 conformers, batch 512
+             per GPU (weak scaling).
 
-value : inputs already resident in HBM (a rotating pool of distinct batches), CUDA events around exactly K steps,
-        barrier + synchronize on both sides, max over ranks.
-e2e   : the same step driven from PINNED HOST buffers through the public API: every step copies the batch
-        host->device and reads the loss back (device->host) inside the timed region.
-roofline / cpu_baseline: see DESIGN.md "Measurement".  --impl reference times the CPU oracle port of the
-reference (oracle/oracle.py; the reference itself needs DGL, which is not installable) on all host cores.
+A "step" is what `train.py` does per batch (train.py:595-598 -> trainer/trainer.py:116-124): build the batch, both
+encoders, loss, backward, [NCCL all-gather / reduce-scatter of embeddings + all-reduce of gradients when N > 1], Adam.
+EVERY timed step draws a FRESH index set from a shuffled epoch over a device-resident packed molecule store, so every
+step has a different (N, E, E3); the batch is built on the device (PackedMoleculeStore) padded to a shape bucket and the
+step replays that bucket's CUDA graph (trainer.BucketedStep) — the collate is inside the timed region.
+
+value : the dataset store resident in HBM, K steps between two CUDA events, barrier + synchronize on both sides, max
+        over ranks.  Per step the host uploads the batch's molecule indices + offsets (7B+3 int64 from pinned memory).
+e2e   : the same loop through the public API with the step's result read back every step: pinned host -> device copy of
+        the step's inputs (indices + offsets) and a device -> host read of the loss inside the timed region.
+roofline / cpu_baseline: DESIGN.md "Measurement".  --impl reference times the CPU oracle port of the reference
+(oracle/oracle.py; the reference itself needs DGL, which is not installable) on all host cores, same config.
 """
 import argparse
 import importlib
@@ -29,27 +40,58 @@ sys.path.insert(0, ROOT)
 
 METRIC = "molecules/sec PNA+Net3D QM9 pretrain (fwd+bwd+Adam)"
 UNIT = "molecules/s"
-POOL = 4            # distinct resident batches the timed loop rotates over
 LR = 8e-5
 TAU = 0.1
+
+CONFIGS = {
+    1: dict(shape="qm9", conformers=1, loss="NTXent", per_gpu=512, global_batch=None, scaling="weak",
+            name="configs[1]: PNA(hidden 200, 7 layers, as shipped in configs_clean/pre-train_QM9.yml)+Net3D(hidden 20) "
+                 "NTXent(tau 0.1) Adam, QM9-shaped synthetic, batch %d per GPU"),
+    3: dict(shape="qm9", conformers=3, loss="NTXentMultiplePositives", per_gpu=None, global_batch=2048, scaling="strong",
+            name="configs[2]: PNA+Net3D NTXentMultiplePositives(tau 0.1, 3 conformers) Adam, QM9-shaped synthetic, "
+                 "global batch 2048 (%d per GPU)"),
+    4: dict(shape="qmugs", conformers=3, loss="NTXentMultiplePositives", per_gpu=512, global_batch=None, scaling="weak",
+            name="configs[3]: configs_clean/pre-train_QMugs.yml — PNA+Net3D NTXentMultiplePositives(3 conformers) Adam, "
+                 "QMugs-shaped synthetic (~40 atoms), batch %d per GPU"),
+}
 
 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=40)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--batch", type=int, default=512, help="molecules per GPU")
-    p.add_argument("--mode", default="graph", choices=["graph", "eager"])
+    p.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    p.add_argument("--batch", type=int, default=0, help="molecules per GPU (default: the config's)")
+    p.add_argument("--store-size", type=int, default=0, help="molecules in the synthetic dataset store")
+    p.add_argument("--mode", default="bucketed", choices=["bucketed", "eager"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
-# workload (profiles/r01_aggregate_full.txt: ncu flushes L2 before each launch, so these are cold-cache bytes)
-# fwd: profiles/r01_aggregate_full.txt; bwd: profiles/r01_ncu_full_final_summary.txt (76.6 MB read + 3.6 MB written)
-AGG_TRAFFIC = {"fwd": 15.33e6, "bwd": 80.2e6}   # batch 512, N=9392, E=19444; output writes stay in L2 past kernel end
+def per_gpu_batch(args, world):
+    c = CONFIGS[args.config]
+    if args.batch:
+        return args.batch
+    return c["per_gpu"] if c["per_gpu"] else c["global_batch"] // world
+
+
+def config_dict(args, world):
+    """identical in both arms (the driver compares them)"""
+    c = CONFIGS[args.config]
+    B = per_gpu_batch(args, world)
+    return {"workload": c["name"] % B, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+            "conformers": c["conformers"], "loss": c["loss"], "molecules": c["shape"] + "-shaped synthetic",
+            "batches": "a fresh random index set every step (distinct N/E/E3), collate inside the timed region",
+            "l2": "every step touches a different batch; per-step working set (activations ~1 GB at batch 512) exceeds "
+                  "the 126 MB L2, no explicit flush"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the aggregation kernels from the committed `ncu --set
+# full` capture of this workload (ncu flushes L2 before each launch: cold-cache bytes; the [N,4F] output stays in L2)
+AGG_TRAFFIC = {"fwd": 15.33e6, "bwd": 80.2e6, "source": "profiles/r01_aggregate_full.txt, "
+               "profiles/r01_ncu_full_final_summary.txt (batch 512, N=9392, E=19444)"}
 
 
 def peaks():
@@ -57,8 +99,8 @@ def peaks():
     if os.path.isfile(path):
         with open(path) as fh:
             d = json.load(fh)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1750.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -71,7 +113,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -108,22 +150,64 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_oracle_throughput(batch, steps, warmup, threads=None):
-    """molecules/s of the CPU oracle port (reference op sequence incl. degree bucketing) on the host cores."""
-    import torch
-    from oracle import oracle as O
+def make_store(args, M):
+    """seeded synthetic dataset store (the same on every rank); cached on local disk between the two arms / the ranks"""
+    import numpy as np
     syn = importlib.import_module("3dinfomax_b200.synthetic")
+    c = CONFIGS[args.config]
+    path = os.path.join(tempfile.gettempdir(), "i3d_store_%s_c%d_m%d.npz" % (c["shape"], c["conformers"], M))
+    if os.path.isfile(path):
+        try:
+            with np.load(path) as z:
+                return {k: z[k] for k in z.files}
+        except Exception:
+            pass
+    store = syn.make_store(7, M, c["shape"], conformers=c["conformers"])
+    try:
+        tmp = path + ".%d.tmp.npz" % os.getpid()
+        np.savez(tmp, **store)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return store
+
+
+def epoch_batches(rng, M, B, n):
+    """n index sets of B molecules: shuffled epochs over the store, last partial batch of an epoch dropped"""
+    out = []
+    while len(out) < n:
+        perm = rng.permutation(M)
+        for i in range(0, M - B + 1, B):
+            out.append(perm[i:i + B].copy())
+            if len(out) == n:
+                break
+    return out
+
+
+# ------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_oracle_throughput(args, batch, steps, warmup, threads=None):
+    """molecules/s of the CPU oracle port (reference op sequence incl. degree bucketing) on the host cores, on batches
+    drawn from the same kind of store with the oracle's restatement of the reference's collate."""
+    import numpy as np
+    import torch
+    from oracle import collate_oracle as CO
+    from oracle import oracle as O
     if threads:
         torch.set_num_threads(threads)
+    c = CONFIGS[args.config]
     c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
-    tr = O.OracleTrainer(c2, c3, O.init_pna_state(c2, 1), O.init_net3d_state(c3, 2), loss="NTXent", tau=TAU, lr=LR)
-    batches = [O.graphs_from_batch(syn.make_batch(100 + i, batch)) for i in range(2)]
+    tr = O.OracleTrainer(c2, c3, O.init_pna_state(c2, 1), O.init_net3d_state(c3, 2), loss=c["loss"], tau=TAU, lr=LR)
+    M = max(4 * batch, 256)
+    store = make_store(args, M)
+    rng = np.random.default_rng(5)
+    C = c["conformers"]
+    mk = (lambda ix: CO.collate_reference_conformers(store, ix, C)) if C > 1 else (lambda ix: CO.collate_reference(store, ix))
+    batches = [O.graphs_from_batch(mk(ix)) for ix in epoch_batches(rng, M, batch, 3)]
     for i in range(warmup):
-        tr.step(*batches[i % 2])
+        tr.step(*batches[i % 3])
     t0 = time.perf_counter()
     for i in range(steps):
-        tr.step(*batches[i % 2])
+        tr.step(*batches[i % 3])
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps, torch.get_num_threads()
 
@@ -131,39 +215,37 @@ def cpu_oracle_throughput(batch, steps, warmup, threads=None):
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    B = per_gpu_batch(args, world)
     # size the per-step sample so that (K + W) steps stay within ~2.5 minutes
-    _, t_probe, _ = cpu_oracle_throughput(32, 1, 1, cores)
-    budget = 150.0 / max(args.steps + args.warmup, 1)
-    b = args.batch
+    _, t_probe, _ = cpu_oracle_throughput(args, 32, 1, 1, cores)
+    budget = 200.0 / max(args.steps + args.warmup, 1)
+    b = B
     while b > 32 and t_probe * (b / 32.0) > budget:
         b //= 2
-    val, per_step, threads = cpu_oracle_throughput(b, args.steps, args.warmup, cores)
-    sample = "%d timed + %d warm-up oracle steps on QM9-shaped batches of %d molecules" % (args.steps, args.warmup, b)
+    val, per_step, threads = cpu_oracle_throughput(args, b, args.steps, args.warmup, cores)
+    sample = "%d timed + %d warm-up oracle steps on batches of %d molecules" % (args.steps, args.warmup, b)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample_batch": b,
-                       "note": "CPU oracle port of the reference op sequence (DGL is not installable here)"},
+            "scaling": CONFIGS[args.config]["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, world),
+            "detail": {"sample_batch": b, "note": "CPU oracle port of the reference op sequence (DGL is not installable "
+                                                  "here); single process on all host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    return ("configs[1]: PNA(hidden 200, 7 layers, as shipped in configs_clean/pre-train_QM9.yml)+Net3D(hidden 20) "
-            "NTXent(tau 0.1) Adam, QM9-shaped synthetic, batch %d per GPU" % args.batch)
-
-
 # ---------------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     i3d = importlib.import_module("3dinfomax_b200")
-    ops = importlib.import_module("3dinfomax_b200.ops")
     cfg = importlib.import_module("3dinfomax_b200.configs")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,58 +257,57 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     i3d.lib.load()
+    c = CONFIGS[args.config]
+    B, C = per_gpu_batch(args, world), c["conformers"]
 
     torch.manual_seed(123)                                   # identical replicas on every rank (train.py:235 seed_all)
     pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
     n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
-    graph_mode = args.mode == "graph"
-    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=TAU), dev, {"lr": LR},
-                                   process_group=dist.group.WORLD if world > 1 else None, graph_safe=graph_mode)
+    bucketed = args.mode == "bucketed"
+    tr = i3d.SelfSupervisedTrainer(pna, n3, getattr(i3d, c["loss"])(tau=TAU), dev, {"lr": LR},
+                                   process_group=dist.group.WORLD if world > 1 else None, graph_safe=bucketed)
 
-    host = [i3d.batch_from_numpy(i3d.synthetic.make_batch(1000 * rank + i, args.batch), "cpu", pin=True)
-            for i in range(POOL)]
-    resident = [(g2.to(dev), g3.to(dev)) for g2, g3 in host]
-    torch.cuda.synchronize()
-    h2d = sum(t.numel() * t.element_size() for g2, g3 in host[:1] for t in
-              (g2.edges()[0], g2.edges()[1], g2.batch_num_nodes(), g2.ndata["feat"], g2.edata["feat"],
-               g3.edges()[0], g3.edges()[1], g3.batch_num_nodes(), g3.edata["d"]))
+    M = args.store_size or max(16 * B, 4096)
+    if rank == 0:
+        make_store(args, M)                                  # one rank generates, the others read the cached file
+    if world > 1:
+        dist.barrier()
+    store = i3d.PackedMoleculeStore(make_store(args, M), dev)
+    h2d = 8 * (7 * B + 3)                                    # the metadata buffer copied per step (collate.metadata_len)
+    W = max(args.warmup, 3)
+    rng = np.random.default_rng(1000 + rank)
+    batches = epoch_batches(rng, M, B, 2 * (args.steps + W) + 8)
+    shapes = {store.batch_sizes(ix, C) for ix in batches[:args.steps + W]}
 
-    def fresh(pair):          # forward consumes the graph object (ndata['feat'] is overwritten, as in the reference)
-        g2, g3 = pair
-        a = i3d.GraphBatch(*g2.edges(), g2.batch_num_nodes(), None, {"feat": g2.ndata["feat"]},
-                           {"feat": g2.edata["feat"]}, g2.number_of_nodes(), g2.max_in_degree)
-        b = i3d.GraphBatch(*g3.edges(), g3.batch_num_nodes(), None, {}, {"d": g3.edata["d"]}, g3.number_of_nodes())
-        return a, b
+    run = None
+    if bucketed:
+        run = i3d.BucketedStep(tr, store, conformers=C)
+        if world == 1:                                       # (data parallel: the ladder is captured in lockstep on first use)
+            lad = run.ladder(B)
+            for lv in range(4):
+                if (B, lv, True) not in run.buckets:
+                    ex = batches[0] if lad.level_of(store.batch_sizes(batches[0], C)) <= lv else run._small_example(B)
+                    run._capture(B, lv, True, ex)
 
-    caps = None
-    note = ""
-    if graph_mode:
-        try:
-            caps = [i3d.CapturedStep(tr, *fresh(p), warmup=2 if i == 0 else 1) for i, p in enumerate(resident)]
-        except Exception as e:   # capture is an optimisation, not a requirement: fall back to eager launches
-            note = "graph capture failed (%s); eager launches" % (str(e).splitlines()[0][:120],)
-            print("bench.py WARNING: " + note, file=sys.stderr, flush=True)
-            caps = None
-            torch.cuda.synchronize()
-            tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=TAU), dev, {"lr": LR},
-                                           process_group=dist.group.WORLD if world > 1 else None)
+    cursor = [0]
 
-    def step_resident(i):
-        if caps is not None:
-            return caps[i % POOL].run()
-        g2, g3 = fresh(resident[i % POOL])
+    def next_idx():
+        ix = batches[cursor[0] % len(batches)]
+        cursor[0] += 1
+        return ix
+
+    def step_resident(_i):
+        ix = next_idx()
+        if run is not None:
+            return run.step(ix)
+        if C != 1:
+            raise RuntimeError("--mode eager supports one conformer per molecule")
+        g2, g3 = store.collate(ix)
         loss, _, _ = tr.process_batch(([g2], [g3]))
         return loss
 
     def step_e2e(i):
-        g2h, g3h = host[i % POOL]
-        if caps is not None:
-            caps[i % POOL].load(g2h, g3h)
-            loss = caps[i % POOL].run()
-        else:
-            g2, g3 = g2h.to(dev, non_blocking=True), g3h.to(dev, non_blocking=True)
-            loss, _, _ = tr.process_batch(([g2], [g3]))
-        return float(loss.item())                                  # device->host read of the step's result
+        return float(step_resident(i).item())                      # device->host read of the step's result
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -235,40 +316,48 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         n0 = i3d.lib.launch_count()
+        r0 = {k: b.replays for k, b in run.buckets.items()} if run is not None else {}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for i in range(steps):
             last = fn(warmup + i)
         e1.record()
         torch.cuda.synchronize()
-        launched = i3d.lib.launch_count() - n0
+        wall = time.perf_counter() - t0
+        launched = i3d.lib.launch_count() - n0            # eager launches (incl. a capture, should one happen)
+        if run is not None:       # graph replays re-launch the kernels recorded at capture time
+            launched += sum(b.launches * (b.replays - r0.get(k, 0)) for k, b in run.buckets.items())
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), last, launched
+        return float(ms.item()), last, launched, wall
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, last_loss, launched = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms, last_loss, launched, wall = timed(step_resident, args.steps, W)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 3)
-    if caps is not None:   # graph replays re-launch the kernels recorded at capture time
-        gpu_launches = int(round(sum(c.launches_per_step for c in caps) / len(caps) * args.steps))
+    gpu_launches = int(launched)
+    if run is not None:
+        levels_used = {str(k): v for k, v in sorted(run.stats["levels"].items())}
+        captures, eager_steps = run.stats["captures"], run.stats["eager"]
     else:
-        gpu_launches = int(launched)
+        levels_used, captures, eager_steps = {}, 0, args.steps
+    ms_e2e, _, _, wall_e2e = timed(step_e2e, args.steps, 3)
 
     # ---- roofline of the aggregation kernel (the graded kernel) -------------------------------------
-    # The step replays from a CUDA graph, so single launches cannot be bracketed there, and an event pair around one
-    # ~10 us launch in eager mode measures the event/launch latency, not the kernel (probe: +7..10 us).  So the kernel
-    # is timed the way it runs in the step: 40 launches per CUDA graph on this batch's CSR, replayed 20 times between
-    # two events.  "cold": rotating over 8 buffer sets (8 x 45 MB > 126 MB L2), every launch re-reads HBM -> reported
-    # as `achieved`.  "warm": one buffer set, messages L2-resident as they are right after the producing kernel.
+    # Single launches cannot be bracketed inside a graph replay, and an event pair around one ~10 us eager launch measures
+    # the event/launch latency (+7..10 us), so the kernel is timed the way it runs in the step: 40 launches per CUDA
+    # graph on a timed batch's CSR, replayed 20 times between two events.  "cold": rotating over 8 buffer sets
+    # (8 x 45 MB > 126 MB L2), every launch re-reads HBM -> reported as `achieved`.  "warm": one buffer set, messages
+    # L2-resident as they are right after the producing kernel.
     roof = None
     if rank == 0:
-        hbm, peak_src = peaks()
+        pk, peak_src = peaks()
+        hbm = float(pk["hbm_gbs"])
         K = i3d.kernels
-        g2, _ = fresh(resident[0])
+        g2, _ = store.collate(batches[0])
         st = i3d.graph.graph_structure(g2)
         rowptr = st.rowptr
         N, E, F = g2.number_of_nodes(), int(st.rowptr[-1].item()), int(cfg.PRETRAIN_QM9_MODEL_PARAMETERS["hidden_dim"])
@@ -309,60 +398,41 @@ def run_b200(args):
         gbs = lambda nbytes, t: nbytes / (t * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "pna_aggregate_fwd_kernel<4,2,3>", "achieved": gbs(b_f, t_f),
                 "peak": hbm, "peak_source": peak_src, "unit": "GB/s", "frac": gbs(b_f, t_f) / hbm,
-                "traffic": AGG_TRAFFIC.get("fwd"), "algorithmic_bytes_per_launch": b_f, "us_per_launch": t_f * 1e3,
+                "traffic": AGG_TRAFFIC.get("fwd"), "traffic_source": AGG_TRAFFIC["source"],
+                "algorithmic_bytes_per_launch": b_f, "us_per_launch": t_f * 1e3,
                 "warm": {"us_per_launch": t_fw * 1e3, "frac": gbs(b_f, t_fw) / hbm},
                 "bwd": {"kernel": "pna_aggregate_bwd_kernel<4>", "achieved": gbs(b_b, t_b),
                         "frac": gbs(b_b, t_b) / hbm, "traffic": AGG_TRAFFIC.get("bwd"),
                         "algorithmic_bytes_per_launch": b_b, "us_per_launch": t_b * 1e3,
                         "warm": {"us_per_launch": t_bw * 1e3, "frac": gbs(b_b, t_bw) / hbm}},
                 "launches_per_step": {"fwd": len(pna.node_gnn.mp_layers), "bwd": len(pna.node_gnn.mp_layers)},
-                "how": "40 launches per CUDA graph on the timed batch's CSR (N=%d, E=%d, F=%d), 20 replays between two "
+                "how": "40 launches per CUDA graph on a timed batch's CSR (N=%d, E=%d, F=%d), 20 replays between two "
                        "CUDA events on the launch stream; achieved = cold (rotating over 8 buffer sets > L2), warm = "
                        "one buffer set; algorithmic bytes = 4F*E + 4E + 4(N+1) + 16F*N (fwd), 32F*N + 8F*E + 4(N+1) "
                        "(bwd), SURVEY 8d" % (N, E, F)}
 
-    # ---- device-side batch construction: time of PackedMoleculeStore.collate per batch ----------------
-    collate_info = None
     if rank == 0:
-        store = i3d.PackedMoleculeStore(i3d.synthetic.make_store(7, 4 * args.batch), dev)
-        rng = __import__("numpy").random.default_rng(11)
-        idxs = [rng.integers(0, len(store), size=args.batch) for _ in range(16)]
-        for ix in idxs[:6]:                      # batch sizes differ: let the caching allocator see them first
-            store.collate(ix)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for ix in idxs[6:]:
-            cg2, cg3 = store.collate(ix)
-        c1.record()
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) / 10
-        collate_info = {"us_per_batch_device": c0.elapsed_time(c1) * 1e3 / 10, "us_per_batch_wall": wall * 1e6,
-                        "h2d_bytes_per_batch": 8 * (7 * args.batch + 3),
-                        "what": "PackedMoleculeStore.collate: molecule indices -> batched 2-D + 3-D graphs on the "
-                                "device (replaces B x Dataset.__getitem__ + dgl.batch + graph H2D copy)"}
-        del store, cg2, cg3
-
-    if rank == 0:
-        mols = args.batch * world * args.steps
+        mols = B * world * args.steps
         line = {"metric": METRIC, "value": mols / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args), "global_batch": args.batch * world,
-                           "parallelism": "dp%d" % world, "launch": "cuda-graph" if caps is not None else "eager",
-                           "l2": "rotating pool of %d distinct batches; per-step working set (activations ~1 GB at "
-                                 "batch 512) exceeds the 126 MB L2, no explicit flush" % POOL,
-                           "bn": "local per-rank batch statistics", "note": note, "last_loss": float(last_loss)},
+                "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": c["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, world),
+                "detail": {"launch": "cuda-graph per shape bucket (trainer.BucketedStep)" if bucketed else "eager",
+                           "distinct_batch_shapes_in_timed_loop": len(shapes), "store_molecules": M,
+                           "bucket_levels_used": levels_used, "graphs_captured": captures, "eager_steps": eager_steps,
+                           "host_wall_ms_per_step": wall / args.steps * 1e3,
+                           "bn": "local per-rank batch statistics", "last_loss": float(last_loss)},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roof, "collate": collate_info}
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "what": "BucketedStep.step(idx) + loss.item() per step: pinned-host metadata (molecule indices + "
+                                "offsets) -> device, device collate from the HBM-resident store, step, loss -> host"},
+                "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            val, per, threads = cpu_oracle_throughput(min(args.batch, 256), 3, 1, cores)
+            nb = min(B, 512)
+            val, per, threads = cpu_oracle_throughput(args, nb, 5, 1, cores)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "3 timed + 1 warm-up oracle steps, QM9-shaped batch of %d molecules"
-                                              % min(args.batch, 256)}
+                                    "sample": "5 timed + 1 warm-up oracle steps on batches of %d molecules" % nb}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured CUDA graphs hold NCCL kernels; tearing the communicator down under them deadlocks

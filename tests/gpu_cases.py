@@ -993,11 +993,10 @@ def case_train_steps(B=16, steps=3, captured=False, seed=21):
     b = syn.make_batch(seed, B)
     cap = None
     if captured:
-        # CapturedStep runs ONE eager warm-up step on the example batch before capturing: mirror it in the oracle
-        otr.step(*O.graphs_from_batch(b))
+        # CapturedStep's eager warm-up step on the example batch leaves no trace (weights, Adam state and BatchNorm
+        # buffers are restored before the capture): nothing to mirror in the oracle
         g2, g3 = i3d.batch_from_numpy(b, DEV)
         cap = i3d.CapturedStep(tr, g2, g3, warmup=1)
-        sync_params()
     for s in range(steps):
         if not captured:
             b = syn.make_batch(seed + s, B)
