@@ -74,6 +74,18 @@ class FCLayer(nn.Module):
             bn = (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
         return ops.fc(segs, self.linear.weight, self.linear.bias, self.act, bn, self.training, residual, valid)
 
+    def _bn_tuple(self):
+        if self.batch_norm is None:
+            return None
+        b = self.batch_norm
+        return (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
+
+    def forward_edge_factored(self, g, h, table, valid=None):
+        """This layer applied to cat[h[src], h[dst], e] in factored form (ops._FCEdgeFactored); ``table``: this layer's
+        bond-feature table from ops.bond_tables."""
+        return ops.fc_edge_factored(g, h, table, self.linear.weight, self.linear.bias, self.act, self._bn_tuple(),
+                                    self.training, valid)
+
     def forward_merged(self, plan, h, agg, residual=None, valid=None):
         """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""
         from .kernels import MergedPosttransWeights

@@ -115,6 +115,14 @@ class PackedMoleculeStore:
         lc = local_csr(self.n_atoms, self.atom_slices_h, self.edge_slices_h, ei)
         self.in_rowptr_l, self.in_eid_l, self.out_rowptr_l, self.out_pos_l = (torch.from_numpy(a).to(device) for a in lc)
         self.max_in_degree_all = int(self.max_in_degree.max()) if self.M else 0
+        # mixed-radix weights of the categorical edge-feature row (OGB bond feature vocabulary sizes 5, 6, 2 ->
+        # (12, 2, 1); commons/mol_encoder.py:4-7): the collate kernel emits each edge's combination index with them
+        from .synthetic import BOND_FEATURE_DIMS
+        mult, acc = [], 1
+        for d in reversed(BOND_FEATURE_DIMS[:self.CE] if self.CE <= len(BOND_FEATURE_DIMS) else [1] * self.CE):
+            mult.append(acc)
+            acc *= d
+        self.code_mult = torch.tensor(list(reversed(mult)), dtype=torch.int64, device=device)
         self._staging = {}
 
     def __len__(self):
@@ -182,6 +190,7 @@ class PackedMoleculeStore:
         src, dst, x_atom, e_attr = i64(e_cap), i64(e_cap), i64(n_cap, self.CA), i64(e_cap, self.CE)
         rowptr, out_rowptr, graph_ptr = i32(n_cap + 1), i32(n_cap + 1), i32(B + 1)
         src_csr, dst_csr, eid, out_pos = i32(e_cap), i32(e_cap), i32(e_cap), i32(e_cap)
+        code_csr = i64(e_cap)
         src3, dst3 = i64(e3_cap), i64(e3_cap)
         d3 = torch.empty(e3_cap, 1, dtype=torch.float32, device=dev)
         rowptr3, graph_ptr3, nn3 = i32(n3_cap + 1), i32(B * C + 1), i64(B * C)
@@ -194,7 +203,8 @@ class PackedMoleculeStore:
                                            p(self.in_rowptr_l), p(self.in_eid_l), p(self.out_rowptr_l),
                                            p(self.out_pos_l), p(v["node_ptr"]), p(v["edge_ptr"]), n_cap, e_cap, p(src),
                                            p(dst), p(x_atom), p(e_attr), p(rowptr), p(src_csr), p(dst_csr), p(eid),
-                                           p(out_rowptr), p(out_pos), p(graph_ptr), s), "i3d_collate_2d_struct")
+                                           p(out_rowptr), p(out_pos), p(graph_ptr), p(self.code_mult), p(code_csr), s),
+                   "i3d_collate_2d_struct")
         _lib.check(L.i3d_collate_3d_struct(p(v["idx"]), B, C, p(self.atom_slices), p(self.conformations),
                                            int(self.conformations.shape[1]), p(v["node_ptr"]), p(v["edge3_ptr"]), n3_cap,
                                            e3_cap, p(src3), p(dst3), p(d3), p(rowptr3), p(src_csr3), p(dst_csr3), p(eid3),
@@ -203,6 +213,7 @@ class PackedMoleculeStore:
                         max_in_degree=self.max_in_degree_all)
         g2._i3d_struct = GraphStructure.from_parts(n_cap, e_cap, B, rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos,
                                                    graph_ptr, True, self.max_in_degree_all, padded=True)
+        g2._i3d_struct.code_csr = code_csr                  # bond-feature combination index of every CSR-ordered edge
         g3 = GraphBatch(src3, dst3, nn3, None, {}, {"d": d3}, n3_cap)
         g3._i3d_struct = GraphStructure.from_parts(n3_cap, e3_cap, B * C, rowptr3, src_csr3, dst_csr3, eid3, rowptr3,
                                                    out_pos3, graph_ptr3, False, None, padded=True)

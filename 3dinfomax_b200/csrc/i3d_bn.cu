@@ -47,10 +47,67 @@ __device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const
   }
 }
 
+// Same-address atomics serialise in L2 (~33 ns each, measured: +148 CTAs = +4.9 us on the gather-add kernel), so with
+// ~300-450 CTAs the atomic tail of a column-statistics kernel was 10-15 us of a 16-30 us launch.  Two-stage variant:
+// every CTA stores its column partials in its OWN slot of `slots` (plain coalesced stores), takes a ticket, and the
+// last CTA to arrive sums the slots in slot order and stores the result (no pre-zeroed output needed, and the sums no
+// longer depend on the order in which CTAs retire).  `counter` must be 0 on entry and is reset to 0 on exit.
+template <typename T>
+__device__ __forceinline__ void last_block_col_sum(const T* __restrict__ slots, int ncols, T* __restrict__ out,
+                                                   unsigned* __restrict__ counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int G = gridDim.x;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int b = 0;
+    for (; b + 4 <= G; b += 4) {
+      s0 += __ldcg(slots + (int64_t)b * ncols + c);
+      s1 += __ldcg(slots + (int64_t)(b + 1) * ncols + c);
+      s2 += __ldcg(slots + (int64_t)(b + 2) * ncols + c);
+      s3 += __ldcg(slots + (int64_t)(b + 3) * ncols + c);
+    }
+    for (; b < G; ++b) s0 += __ldcg(slots + (int64_t)b * ncols + c);
+    out[c] = (s0 + s1) + (s2 + s3);
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+template <int V, int NV>
+__device__ __forceinline__ void block_col_reduce_f64_ws(double (&acc)[NV][V], const ColMap& m, int FV, int F,
+                                                        double* __restrict__ gsum, double* __restrict__ slots,
+                                                        unsigned* __restrict__ counter) {
+  if (!slots) {
+    block_col_reduce_f64<V, NV>(acc, m, FV, F, gsum);
+    return;
+  }
+  extern __shared__ double sh[];  // [NV][V][kColThreads]
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int i = 0; i < V; ++i) sh[(a * V + i) * kColThreads + threadIdx.x] = m.active ? acc[a][i] : 0.0;
+  __syncthreads();
+  double* mine = slots + (int64_t)blockIdx.x * NV * F;
+  if (m.active && m.rg == 0) {
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        double s = 0.0;
+        for (int r = 0; r < m.RP; ++r) s += sh[(a * V + i) * kColThreads + r * FV + m.cg];
+        mine[(int64_t)a * F + m.cg * V + i] = s;
+      }
+  }
+  last_block_col_sum<double>(slots, NV * F, gsum, counter);
+}
+
 template <int V>
 __global__ void __launch_bounds__(kColThreads)
     act_colstats_kernel(const float* __restrict__ Y, int64_t M, int F, int ldy, int act, double* __restrict__ sums,
-                        const int32_t* __restrict__ m_valid) {
+                        const int32_t* __restrict__ m_valid, double* __restrict__ slots, unsigned* __restrict__ counter) {
   pdl_grid_sync();
   if (m_valid) M = min(M, (int64_t)*m_valid);
   const int FV = F / V;
@@ -71,7 +128,7 @@ __global__ void __launch_bounds__(kColThreads)
       }
     }
   }
-  block_col_reduce_f64<V, 2>(acc, m, FV, F, sums);
+  block_col_reduce_f64_ws<V, 2>(acc, m, FV, F, sums, slots, counter);
 }
 
 // per-column (alpha, beta) with O = h*alpha + beta, exactly the folded form PyTorch's CPU batch_norm uses
@@ -161,7 +218,8 @@ template <int V>
 __global__ void __launch_bounds__(kColThreads)
     bn_bwd_reduce_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M,
                          int F, int act, const float* __restrict__ save_mean_rstd, double* __restrict__ sums2,
-                         float* __restrict__ zero_buf, int zero_n, const int32_t* __restrict__ m_valid) {
+                         float* __restrict__ zero_buf, int zero_n, const int32_t* __restrict__ m_valid,
+                         double* __restrict__ slots, unsigned* __restrict__ counter) {
   pdl_grid_sync();
   if (m_valid) M = min(M, (int64_t)*m_valid);      // padding rows may hold anything (never read)
   if (blockIdx.x == 0)
@@ -215,7 +273,7 @@ __global__ void __launch_bounds__(kColThreads)
       }
     }
   }
-  block_col_reduce_f64<V, 2>(acc, m, FV, F, sums2);
+  block_col_reduce_f64_ws<V, 2>(acc, m, FV, F, sums2, slots, counter);
 }
 
 template <int V>
@@ -224,7 +282,8 @@ __global__ void __launch_bounds__(kColThreads)
                         int act, int has_bn, int training, const float* __restrict__ save_mean_rstd,
                         const float* __restrict__ gamma, const double* __restrict__ sums2, float* __restrict__ dY,
                         int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                        const int32_t* __restrict__ m_valid) {
+                        const int32_t* __restrict__ m_valid, float* __restrict__ slots,
+                        unsigned* __restrict__ counter) {
   pdl_grid_sync();
   // shape-bucketed batches: rows [*m_valid, M) are padding — dY is written as exact zeros there (their dO / Y are
   // never read), so nothing downstream (dW = dY^T x, dx = dY W, row sums) sees them
@@ -309,10 +368,90 @@ __global__ void __launch_bounds__(kColThreads)
       for (int i = 0; i < V; ++i) {
         float s = 0.f;
         for (int r = 0; r < m.RP; ++r) s += sh[i * kColThreads + r * FV + m.cg];
-        atomicAdd(dbias + m.cg * V + i, s);
+        if (slots) slots[(int64_t)blockIdx.x * F + m.cg * V + i] = s;
+        else atomicAdd(dbias + m.cg * V + i, s);
+      }
+    }
+    if (slots) last_block_col_sum<float>(slots, F, dbias, counter);     // (stores: dbias need not be zeroed)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Factored first layer of the edge MLP (models/pna.py:237-252).  cat[h[src], h[dst], e] W^T splits by columns of W into
+// (h W_s^T)[src] + (h W_d^T)[dst] + e W_e^T: the two h terms are ONE node-level GEMM P = h [W_s;W_d]^T
+// (N rows instead of E, K = F instead of 3F) and, because the bond features take only prod(5,6,2) = 60 distinct values
+// (commons/mol_encoder.py:4-7), e W_e^T is a 60-row table T looked up by the edge's feature code.  This kernel is what
+// is left at edge level:  Y[m,:] = P[src[m], 0:F] + P[dst[m], F:2F] + T[code[m], :] + bias, with the FCLayer's train-mode
+// BatchNorm statistics (column sums of act(Y), act(Y)^2 in fp64) fused, as the GEMM epilogue does for the other layers.
+// HBM/L2-bound: P (N x 2F) and T stay L2 / L1 resident, Y is written once.  Negative src/dst (padding edges) read zeros.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGaBatch = 2;      // rows in flight per thread: 3 CTAs/SM x 2 rows beat 2 CTAs/SM x 4 rows (registers)
+
+template <int V>
+__global__ void __launch_bounds__(kColThreads, 3)
+    edge_gather_add_kernel(const float* __restrict__ P, int ldp, const int32_t* __restrict__ src,
+                           const int32_t* __restrict__ dst, const float* __restrict__ T, int ldt,
+                           const int32_t* __restrict__ code, const float* __restrict__ bias, int64_t M, int F,
+                           float* __restrict__ Y, int ldy, double* __restrict__ stats, int act,
+                           const int32_t* __restrict__ m_valid, double* __restrict__ slots,
+                           unsigned* __restrict__ counter) {
+  pdl_grid_sync();
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  const int64_t Mv = m_valid ? min(M, (int64_t)*m_valid) : M;
+  double acc[2][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = 0.0, acc[1][i] = 0.0;
+  if (m.active) {
+    const int c0 = m.cg * V;
+    Vec<V> b;
+    if (bias) b.load(bias + c0); else b.fill(0.f);
+    const int64_t stride = (int64_t)gridDim.x * m.RP;
+    // the gather indices of a batch of rows are loaded one batch ahead, so that no row load waits on an index load
+    int32_t ns[kGaBatch], nd[kGaBatch], nc[kGaBatch];
+    auto load_idx = [&](int64_t rb) {
+#pragma unroll
+      for (int j = 0; j < kGaBatch; ++j) {
+        const int64_t r = rb + j * stride;
+        ns[j] = nd[j] = -1, nc[j] = 0;
+        if (r < M) ns[j] = __ldg(src + r), nd[j] = __ldg(dst + r), nc[j] = code ? __ldg(code + r) : 0;
+      }
+    };
+    load_idx((int64_t)blockIdx.x * m.RP + m.rg);
+    for (int64_t r0 = (int64_t)blockIdx.x * m.RP + m.rg; r0 < M; r0 += kGaBatch * stride) {
+      int32_t is[kGaBatch], id[kGaBatch], ic[kGaBatch];
+#pragma unroll
+      for (int j = 0; j < kGaBatch; ++j) is[j] = ns[j], id[j] = nd[j], ic[j] = nc[j];
+      load_idx(r0 + kGaBatch * stride);
+      Vec<V> a[kGaBatch], d[kGaBatch], t[kGaBatch];
+#pragma unroll
+      for (int j = 0; j < kGaBatch; ++j) {
+        a[j].fill(0.f), d[j].fill(0.f), t[j].fill(0.f);
+        if (is[j] >= 0) a[j].load(P + (int64_t)is[j] * ldp + c0);
+        if (id[j] >= 0) d[j].load(P + (int64_t)id[j] * ldp + F + c0);
+        if (T && r0 + j * stride < M) t[j].load(T + (int64_t)ic[j] * ldt + c0);
+      }
+#pragma unroll
+      for (int j = 0; j < kGaBatch; ++j) {
+        const int64_t r = r0 + j * stride;
+        if (r >= M) continue;
+        Vec<V> y;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          y.v[i] = __fadd_rn(__fadd_rn(__fadd_rn(a[j].v[i], d[j].v[i]), t[j].v[i]), b.v[i]);
+        y.store(Y + r * ldy + c0);
+        if (stats && r < Mv) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const double h = (double)act_apply(y.v[i], act);
+            acc[0][i] += h;
+            acc[1][i] = fma(h, h, acc[1][i]);
+          }
+        }
       }
     }
   }
+  if (stats) block_col_reduce_f64_ws<V, 2>(acc, m, FV, F, stats, slots, counter);
 }
 
 __global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y) {
@@ -383,11 +522,16 @@ using namespace i3d;
 extern "C" {
 
 int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double* sums, void* stream) {
-  return i3d_act_colstats_v(Y, M, F, ldy, act, sums, nullptr, stream);
+  return i3d_act_colstats_v(Y, M, F, ldy, act, sums, nullptr, nullptr, stream);
+}
+
+// two-stage reduction workspace usable for `grid` CTAs x `ncols` columns of `elem` bytes?
+static inline bool rws_ok(const i3d_reduce_ws* r, int grid, int ncols, size_t elem) {
+  return r && r->slots && r->counter && (size_t)grid * ncols * elem <= (size_t)r->slot_bytes;
 }
 
 int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, double* sums, const int32_t* m_valid,
-                       void* stream) {
+                       const i3d_reduce_ws* rws, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && sums && (M == 0 || Y), "invalid argument");
   cudaStream_t s = as_stream(stream);
   I3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
@@ -396,10 +540,14 @@ int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, doubl
   const int V = v4 ? 4 : 1, FV = F / V;
   I3D_REQUIRE(FV <= kColThreads, "feature width too large (F <= 1024 when 16B-aligned, else F <= 256)");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
+  const int grid = col_grid(M, FV);
+  const bool two = rws_ok(rws, grid, 2 * F, sizeof(double));
+  double* slots = two ? static_cast<double*>(rws->slots) : nullptr;
+  unsigned* counter = two ? rws->counter : nullptr;
   if (v4)
-    launch(act_colstats_kernel<4>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid);
+    launch(act_colstats_kernel<4>, grid, kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid, slots, counter);
   else
-    launch(act_colstats_kernel<1>, col_grid(M, FV), kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid);
+    launch(act_colstats_kernel<1>, grid, kColThreads, smem, s, Y, M, F, ldy, act, sums, m_valid, slots, counter);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -439,12 +587,13 @@ int i3d_bn_apply_v(const float* Y, int64_t M, int F, int ldy, int act, const dou
 
 int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                          const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n, void* stream) {
-  return i3d_bn_bwd_reduce_v(dO, ldd, Y, ldy, M, F, act, save_mean_rstd, sums2, zero_buf, zero_n, nullptr, stream);
+  return i3d_bn_bwd_reduce_v(dO, ldd, Y, ldy, M, F, act, save_mean_rstd, sums2, zero_buf, zero_n, nullptr, nullptr,
+                             stream);
 }
 
 int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                         const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n,
-                        const int32_t* m_valid, void* stream) {
+                        const int32_t* m_valid, const i3d_reduce_ws* rws, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && sums2 && save_mean_rstd && (M == 0 || (Y && dO)) &&
                   zero_n >= 0 && (zero_n == 0 || zero_buf),
               "invalid argument");
@@ -460,12 +609,16 @@ int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64
   const int V = v4 ? 4 : 1, FV = F / V;
   I3D_REQUIRE(FV <= kColThreads, "feature width too large");
   const size_t smem = sizeof(double) * 2 * V * kColThreads;
+  const int grid = col_grid(M, FV);
+  const bool two = rws_ok(rws, grid, 2 * F, sizeof(double));
+  double* slots = two ? static_cast<double*>(rws->slots) : nullptr;
+  unsigned* counter = two ? rws->counter : nullptr;
   if (v4)
-    launch(bn_bwd_reduce_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2, zero_buf, zero_n, m_valid);
+    launch(bn_bwd_reduce_kernel<4>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+                                                                      sums2, zero_buf, zero_n, m_valid, slots, counter);
   else
-    launch(bn_bwd_reduce_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
-                                                                      sums2, zero_buf, zero_n, m_valid);
+    launch(bn_bwd_reduce_kernel<1>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, save_mean_rstd,
+                                                                      sums2, zero_buf, zero_n, m_valid, slots, counter);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -479,12 +632,13 @@ int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t 
                      int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
                      int lddy, float* dbias, float* dgamma, float* dbeta, void* stream) {
   return i3d_bn_bwd_apply_v(dO, ldd, Y, ldy, M, F, act, has_bn, training, save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                            dgamma, dbeta, nullptr, stream);
+                            dgamma, dbeta, nullptr, nullptr, stream);
 }
 
 int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                        int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
-                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid, void* stream) {
+                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid,
+                       const i3d_reduce_ws* rws, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && (M == 0 || (Y && dO && dY)), "invalid argument");
   I3D_REQUIRE(!has_bn || (save_mean_rstd && gamma && sums2 && dgamma && dbeta), "BN tensors missing");
   if (M == 0) return I3D_OK;
@@ -493,14 +647,49 @@ int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_
   I3D_REQUIRE(FV <= kColThreads, "feature width too large");
   const size_t smem = sizeof(float) * V * kColThreads;
   cudaStream_t s = as_stream(stream);
+  const int grid = col_grid(M, FV);
+  const bool two = dbias && rws_ok(rws, grid, F, sizeof(float));
+  float* slots = two ? static_cast<float*>(rws->slots) : nullptr;
+  unsigned* counter = two ? rws->counter : nullptr;
   if (v4)
-    launch(bn_bwd_apply_kernel<4>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
+    launch(bn_bwd_apply_kernel<4>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta, m_valid);
+                                                                     dgamma, dbeta, m_valid, slots, counter);
   else
-    launch(bn_bwd_apply_kernel<1>, col_grid(M, FV), kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
+    launch(bn_bwd_apply_kernel<1>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta, m_valid);
+                                                                     dgamma, dbeta, m_valid, slots, counter);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_edge_gather_add(const float* P, int ldp, const int32_t* src, const int32_t* dst, const float* T, int ldt,
+                        const int32_t* code, const float* bias, int64_t M, int F, float* Y, int ldy, double* col_stats,
+                        int stats_act, const int32_t* m_valid, const i3d_reduce_ws* rws, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldp >= 2 * F && ldy >= F && (!T || ldt >= F) && (M == 0 || (P && src && dst && Y)),
+              "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
+  stats_act &= 0xff;
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * F, s));
+  if (M == 0) return I3D_OK;
+  const bool v4 = can_vec4({P, T, bias, Y}, {F, ldp, ldy, T ? ldt : 0});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  I3D_REQUIRE(FV <= kColThreads, "feature width too large");
+  const size_t smem = sizeof(double) * 2 * V * kColThreads;
+  const int RP = kColThreads / FV;
+  int64_t need = (M + (int64_t)RP * 4 - 1) / ((int64_t)RP * 4);          // >= 4 rows per thread
+  const int64_t cap = (int64_t)sm_count() * 3;
+  const int grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+  const bool two = col_stats && rws_ok(rws, grid, 2 * F, sizeof(double));
+  double* slots = two ? static_cast<double*>(rws->slots) : nullptr;
+  unsigned* counter = two ? rws->counter : nullptr;
+  if (v4)
+    launch(edge_gather_add_kernel<4>, grid, kColThreads, smem, s, P, ldp, src, dst, T, ldt, code, bias, M, F, Y,
+           ldy, col_stats, stats_act, m_valid, slots, counter);
+  else
+    launch(edge_gather_add_kernel<1>, grid, kColThreads, smem, s, P, ldp, src, dst, T, ldt, code, bias, M, F, Y,
+           ldy, col_stats, stats_act, m_valid, slots, counter);
   I3D_LAUNCHED();
   return I3D_OK;
 }

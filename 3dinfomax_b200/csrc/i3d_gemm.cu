@@ -261,6 +261,77 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small problems (M * N <= 64K outputs, K <= 4096): one thread per output element.  The tiled kernel above needs
+// >= 128 x 64 outputs per CTA: the 60-row bond-feature tables of the factored edge layer (T = combo W_e^T, its two
+// gradients) gave it 1-4 CTAs and ~20 us of pure latency each, 22 launches per step; here they spread over every SM.
+// Operands are L1/L2 resident at these sizes, so the per-thread dot product streams float4s of its own B row (NT) or
+// coalesced B columns (NN / TN) against a warp-broadcast A element.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_small_kernel(const __grid_constant__ GemmParams p) {
+  pdl_grid_sync();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t M = p.M;
+  const int N = p.N;
+  if (t >= M * N) return;
+  const int64_t m = t / N;
+  const int n = (int)(t - m * N);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  for (int s = 0; s < p.n_seg; ++s) {
+    const float* __restrict__ A = p.seg[s].A;
+    const float* __restrict__ B = p.seg[s].B;
+    const int32_t* __restrict__ a_idx = p.seg[s].a_idx;
+    const int32_t* __restrict__ b_idx = p.seg[s].b_idx;
+    const float* __restrict__ scale = p.seg[s].scale;
+    const int lda = p.seg[s].lda, ldb = p.seg[s].ldb, K = p.seg[s].K;
+    if (MODE == I3D_GEMM_TN) {
+      for (int k = 0; k < K; ++k) {
+        const int64_t ra = a_idx ? (int64_t)__ldg(a_idx + k) : (int64_t)k;
+        const int64_t rb = b_idx ? (int64_t)__ldg(b_idx + k) : (int64_t)k;
+        if (ra < 0 || rb < 0) continue;
+        float a = __ldg(A + ra * lda + m);
+        if (scale) a *= __ldg(scale + k);
+        acc0 = fmaf(a, __ldg(B + rb * ldb + n), acc0);
+      }
+    } else {
+      const int64_t ra = a_idx ? (int64_t)__ldg(a_idx + m) : m;
+      if (ra < 0) continue;
+      const float sc = scale ? __ldg(scale + m) : 1.f;
+      const float* __restrict__ ap = A + ra * lda;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+      if (MODE == I3D_GEMM_NT) {
+        const float* __restrict__ bp = B + (int64_t)n * ldb;
+        const bool vec = ((lda | ldb) & 3) == 0 && is_al16(A) && is_al16(B);
+        int k = 0;
+        if (vec) {
+          for (; k + 4 <= K; k += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(ap + k));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bp + k));
+            p0 = fmaf(a.x, b.x, p0), p1 = fmaf(a.y, b.y, p1), p2 = fmaf(a.z, b.z, p2), p3 = fmaf(a.w, b.w, p3);
+          }
+        }
+        for (; k < K; ++k) p0 = fmaf(__ldg(ap + k), __ldg(bp + k), p0);
+      } else {
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+          p0 = fmaf(__ldg(ap + k), __ldg(B + (int64_t)k * ldb + n), p0);
+          p1 = fmaf(__ldg(ap + k + 1), __ldg(B + (int64_t)(k + 1) * ldb + n), p1);
+          p2 = fmaf(__ldg(ap + k + 2), __ldg(B + (int64_t)(k + 2) * ldb + n), p2);
+          p3 = fmaf(__ldg(ap + k + 3), __ldg(B + (int64_t)(k + 3) * ldb + n), p3);
+        }
+        for (; k < K; ++k) p0 = fmaf(__ldg(ap + k), __ldg(B + (int64_t)k * ldb + n), p0);
+      }
+      const float part = (p0 + p1) + (p2 + p3);
+      acc1 = fmaf(sc, part, acc1);
+    }
+  }
+  float o = (acc0 + acc1) + (acc2 + acc3);
+  if (p.bias) o += __ldg(p.bias + n);
+  float* c = p.C + m * p.ldc + n;
+  *c = p.accumulate ? *c + o : o;
+}
+
 __global__ void zero_block_kernel(float* __restrict__ C, int64_t M, int N, int ldc) {
   pdl_grid_sync();
   const int64_t total = M * N;
@@ -485,6 +556,21 @@ extern "C" int i3d_gemm_ex_v(int mode, int64_t M, int N, int n_seg, const i3d_ge
   const int64_t gx = (M + BM - 1) / BM;
   const int gy = (N + BN - 1) / BN;
   I3D_REQUIRE(gx < (1ll << 31) && gy <= 65535, "problem too large");
+  int64_t ksum = 0;
+  for (int sg = 0; sg < n_seg; ++sg) ksum += segs[sg].K;
+  if (M * N <= 65536 && ksum <= 4096 && gx * gy < 32) {
+    // too few 128 x 64 tiles to fill the machine: one thread per output element
+    const int grid = (int)((M * N + 255) / 256);
+    if (mode == I3D_GEMM_TN)
+      launch(gemm_small_kernel<I3D_GEMM_TN>, grid, 256, 0, s, p);
+    else if (mode == I3D_GEMM_NT)
+      launch(gemm_small_kernel<I3D_GEMM_NT>, grid, 256, 0, s, p);
+    else
+      launch(gemm_small_kernel<I3D_GEMM_NN>, grid, 256, 0, s, p);
+    I3D_LAUNCHED();
+    if (col_stats && mode == I3D_GEMM_NT) return i3d_act_colstats_v(C, M, N, ldc, stats_act, col_stats, m_valid, nullptr, stream);
+    return I3D_OK;
+  }
   if (mode == I3D_GEMM_TN) {
     const int K = segs[0].K;
     const int64_t tiles = gx * gy;
@@ -506,7 +592,7 @@ extern "C" int i3d_gemm_ex_v(int mode, int64_t M, int N, int n_seg, const i3d_ge
     launch(gemm_kernel<I3D_GEMM_NT>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);
     if (col_stats) {
       I3D_LAUNCHED();
-      return i3d_act_colstats_v(C, M, N, ldc, stats_act, col_stats, m_valid, stream);
+      return i3d_act_colstats_v(C, M, N, ldc, stats_act, col_stats, m_valid, nullptr, stream);
     }
   } else {
     launch(gemm_kernel<I3D_GEMM_NN>, dim3((unsigned)gx, gy, 1), GEMM_THREADS, 0, s, p);

@@ -498,9 +498,12 @@ __global__ void __launch_bounds__(256)
                              int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t* __restrict__ x_atom,
                              int64_t* __restrict__ e_attr, int32_t* __restrict__ rowptr, int32_t* __restrict__ src_csr,
                              int32_t* __restrict__ dst_csr, int32_t* __restrict__ eid, int32_t* __restrict__ out_rowptr,
-                             int32_t* __restrict__ out_pos, int32_t* __restrict__ graph_ptr) {
+                             int32_t* __restrict__ out_pos, int32_t* __restrict__ graph_ptr,
+                             const int64_t* __restrict__ code_mult, int64_t* __restrict__ code_csr) {
   pdl_grid_sync();
-  const int64_t n_valid = node_ptr[B], e_valid = edge_ptr[B];
+  // a batch that does not fit the bucket is the caller's error (BucketedStep picks the bucket from the same sizes);
+  // the sizes are clamped so that such a call truncates the batch instead of indexing past the capacities
+  const int64_t n_valid = min(node_ptr[B], n_cap), e_valid = min(edge_ptr[B], e_cap);
   const int64_t node_items = (n_cap + 1), total = node_items + e_cap + (B + 1);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     if (t < node_items) {
@@ -509,8 +512,8 @@ __global__ void __launch_bounds__(256)
         const int k = find_segment(node_ptr, B, v);
         const int64_t a = atom_slices[idx[k]] + (v - node_ptr[k]);
         const int32_t eb = (int32_t)edge_ptr[k];
-        rowptr[v] = eb + in_rowptr_l[a];
-        out_rowptr[v] = eb + out_rowptr_l[a];
+        rowptr[v] = min(eb + in_rowptr_l[a], (int32_t)e_valid);
+        out_rowptr[v] = min(eb + out_rowptr_l[a], (int32_t)e_valid);
         for (int c = 0; c < CA; ++c) x_atom[v * CA + c] = atom_features[a * CA + c];
       } else {
         rowptr[v] = (int32_t)e_valid;
@@ -531,18 +534,25 @@ __global__ void __launch_bounds__(256)
         for (int c = 0; c < CE; ++c) e_attr[e * CE + c] = edge_features[(s0 + le) * CE + c];
         const int32_t leid = in_eid_l[s0 + le];              // local edge id at CSR position le of this molecule
         eid[e] = eb + leid;
-        src_csr[e] = (int32_t)(edge_indices[s0 + leid] + off);
-        dst_csr[e] = (int32_t)(edge_indices[Etot + s0 + leid] + off);
+        const int64_t sv = edge_indices[s0 + leid] + off, dv = edge_indices[Etot + s0 + leid] + off;
+        src_csr[e] = sv < n_valid ? (int32_t)sv : -1;        // (only a truncated, i.e. mis-bucketed, batch clips)
+        dst_csr[e] = dv < n_valid ? (int32_t)dv : -1;
         out_pos[e] = eb + out_pos_l[s0 + le];
+        if (code_csr) {                                      // mixed-radix index of the edge's categorical feature row
+          int64_t cd = 0;
+          for (int c = 0; c < CE; ++c) cd += edge_features[(s0 + leid) * CE + c] * code_mult[c];
+          code_csr[e] = cd;
+        }
       } else {
         src[e] = -1, dst[e] = -1;
         for (int c = 0; c < CE; ++c) e_attr[e * CE + c] = 0;
         eid[e] = (int32_t)e, out_pos[e] = (int32_t)e;
         src_csr[e] = -1, dst_csr[e] = -1;
+        if (code_csr) code_csr[e] = 0;
       }
     } else {
       const int64_t k = t - node_items - e_cap;
-      graph_ptr[k] = (int32_t)node_ptr[k];
+      graph_ptr[k] = (int32_t)min(node_ptr[k], n_valid);
     }
   }
 }
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(256)
                              int32_t* __restrict__ eid, int32_t* __restrict__ out_pos, int32_t* __restrict__ graph_ptr,
                              int64_t* __restrict__ num_nodes3) {
   pdl_grid_sync();
-  const int64_t n_valid = C * node_ptr[B], e_valid = C * edge3_ptr[B];
+  const int64_t n_valid = min(C * node_ptr[B], n_cap), e_valid = min(C * edge3_ptr[B], e_cap);   // clamped, see 2-D
   const int64_t node_items = n_cap + 1, graphs = (int64_t)B * C;
   const int64_t total = node_items + e_cap + graphs + 1;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(256)
         const int64_t n = node_ptr[k + 1] - node_ptr[k];
         const int64_t lv = v - C * node_ptr[k];
         const int64_t c = lv / n, j = lv - c * n;
-        rp = (int32_t)(C * edge3_ptr[k] + c * n * (n - 1) + j * (n - 1));
+        rp = (int32_t)min(C * edge3_ptr[k] + c * n * (n - 1) + j * (n - 1), e_valid);
       }
       rowptr[v] = rp;                                        // the out-CSR row pointer is the same array (symmetric)
     } else if (t < node_items + e_cap) {
@@ -594,7 +604,7 @@ __global__ void __launch_bounds__(256)
         const float dx = __fsub_rn(xa[0], xb[0]), dy = __fsub_rn(xa[1], xb[1]), dz = __fsub_rn(xa[2], xb[2]);
         d3[e] = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
         // CSR position e: destination a, q-th in-edge comes from o (ascending source)
-        dst_csr[e] = (int32_t)(b0 + a), src_csr[e] = (int32_t)(b0 + o);
+        dst_csr[e] = b0 + a < n_valid ? (int32_t)(b0 + a) : -1, src_csr[e] = b0 + o < n_valid ? (int32_t)(b0 + o) : -1;
         eid[e] = (int32_t)(e0 + o * (n - 1) + (a < o ? a : a - 1));
         // out-CSR slot e: r-th out-edge of a (ascending destination o) sits at CSR position of (dst o, src a)
         out_pos[e] = (int32_t)(e0 + o * (n - 1) + (a < o ? a : a - 1));
@@ -609,7 +619,7 @@ __global__ void __launch_bounds__(256)
       } else {
         const int64_t k = g / C, c = g - k * C;
         const int64_t n = node_ptr[k + 1] - node_ptr[k];
-        graph_ptr[g] = (int32_t)(C * node_ptr[k] + c * n);
+        graph_ptr[g] = (int32_t)min(C * node_ptr[k] + c * n, n_valid);
         if (num_nodes3) num_nodes3[g] = n;
       }
     }
@@ -627,7 +637,8 @@ int i3d_collate_2d_struct(const int64_t* idx, int64_t B, const int64_t* atom_sli
                           const int64_t* node_ptr, const int64_t* edge_ptr, int64_t n_cap, int64_t e_cap, int64_t* src,
                           int64_t* dst, int64_t* x_atom, int64_t* e_attr, int32_t* rowptr, int32_t* src_csr,
                           int32_t* dst_csr, int32_t* eid, int32_t* out_rowptr, int32_t* out_pos, int32_t* graph_ptr,
-                          void* stream) {
+                          const int64_t* code_mult, int64_t* code_csr, void* stream) {
+  I3D_REQUIRE(!code_csr || code_mult, "code_csr needs code_mult");
   I3D_REQUIRE(B >= 1 && B < (1 << 30) && n_cap >= 0 && e_cap >= 0 && n_cap < (1ll << 31) - 1 && e_cap < (1ll << 31) &&
                   Etot >= 0 && n_atom_feat >= 1 && n_edge_feat >= 0 && idx && atom_slices && edge_slices && node_ptr &&
                   edge_ptr && rowptr && out_rowptr && graph_ptr && (n_cap == 0 || (atom_features && x_atom && in_rowptr_l &&
@@ -638,7 +649,7 @@ int i3d_collate_2d_struct(const int64_t* idx, int64_t B, const int64_t* atom_sli
   i3d::launch(i3d::collate_2d_struct_kernel, i3d::grid_for(work, 256), 256, 0, i3d::as_stream(stream), idx, (int)B,
               atom_slices, edge_slices, edge_indices, Etot, atom_features, n_atom_feat, edge_features, n_edge_feat,
               in_rowptr_l, in_eid_l, out_rowptr_l, out_pos_l, node_ptr, edge_ptr, n_cap, e_cap, src, dst, x_atom, e_attr,
-              rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos, graph_ptr);
+              rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos, graph_ptr, code_mult, code_csr);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -111,6 +111,7 @@ class GraphStructure:
     # them are padding (include/i3d.h "Padding convention").  None = every row is valid.
     n_valid = None
     e_valid = None
+    code_csr = None      # optional int64 [E]: bond-feature combination index of every CSR-ordered edge (device collate)
 
     @classmethod
     def from_parts(cls, N, E, B, rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos, graph_ptr, need_scalers=True,

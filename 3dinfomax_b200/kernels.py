@@ -26,14 +26,33 @@ class StatsArena:
     dependent launch between its neighbours.  ``take`` hands out consecutive slices (host-side bump pointer); the
     slices are only valid until the next ``reset`` and never escape the operator that took them."""
 
-    def __init__(self, device, doubles=1 << 17):
+    def __init__(self, device, doubles=1 << 17, scratch_bytes=192 << 20, counters=1 << 12):
         self.buf = torch.zeros(doubles, dtype=torch.float64, device=device)
         self.used = 0
         self.lock = __import__("threading").Lock()
+        # workspace of the two-stage column reductions (i3d_reduce_ws): per-CTA partial slots (never initialised) and
+        # ticket counters (zeroed ONCE: every kernel leaves its counter at 0), handed out by bump pointers per step
+        on_gpu = torch.device(device).type == "cuda"
+        self.scratch = torch.empty(scratch_bytes if on_gpu else 0, dtype=torch.uint8, device=device)
+        self.counters = torch.zeros(counters, dtype=torch.int32, device=device)
+        self.s_used = self.c_used = 0
+        self.slot_ctas = 4 * (torch.cuda.get_device_properties(device).multi_processor_count if on_gpu else 148)
 
     def reset(self):
         self.buf.zero_()                       # one memset node (1 MB) per step
         self.used = 0
+        self.s_used = self.c_used = 0
+
+    def take_ws(self, ncols, elem_bytes):
+        """i3d_reduce_ws for a column reduction over ``ncols`` columns, or None when the scratch is exhausted"""
+        n = (self.slot_ctas * ncols * elem_bytes + 255) // 256 * 256
+        with self.lock:
+            if self.s_used + n > self.scratch.numel() or self.c_used >= self.counters.numel():
+                return None
+            ws = _lib.reduce_ws(self.scratch.data_ptr() + self.s_used, n, self.counters.data_ptr() + 4 * self.c_used)
+            self.s_used += n
+            self.c_used += 1
+            return ws
 
     def take(self, n):
         with self.lock:
@@ -50,6 +69,12 @@ def _stats_buffer(arena, n, device):
     if t is not None:
         return t, STATS_PREZEROED
     return torch.empty(n, dtype=torch.float64, device=device), 0
+
+
+def _ws(arena, ncols, elem_bytes):
+    """(ctypes pointer to an i3d_reduce_ws or None, keep-alive object)"""
+    ws = arena.take_ws(ncols, elem_bytes) if arena is not None else None
+    return (ctypes.byref(ws) if ws is not None else None), ws
 
 
 def _L():
@@ -364,6 +389,41 @@ class WeightPrep:
         self._table = None
         return e
 
+    def entry_stacked(self, W, key, views):
+        """Prepared B operand made of several weight blocks stacked along N (rows of the operand): ``views`` are 2-D
+        views [n_j, K] of W with the same K.  Used for P = h [W_s; W_d]^T (ops._FCEdgeFactored): one GEMM, N = sum n_j."""
+        k = (W.data_ptr(), ("stacked",) + tuple(key), False)
+        e = self.entries.get(k)
+        if e is not None:
+            return e
+        Kd = int(views[0].shape[1])
+        ktot = kpad32(Kd)
+        ntot = sum(int(v.shape[0]) for v in views)
+        e = PreparedB()
+        e.W = W
+        e.ws = torch.empty(2 * ntot * ktot * 4 + 256, dtype=torch.uint8, device=self.device)
+        base = (e.ws.data_ptr() + 127) & ~127               # same layout as i3d_gemm_prep_describe / gemm_ws_nt
+        lo_base = base + ntot * ktot * 4
+        e.items = (_lib.prep_item * len(views))()
+        e.n_items = len(views)
+        row0, tiles = 0, 0
+        for j, v in enumerate(views):
+            pb, ldb = _mat(v, "B")
+            n = int(v.shape[0])
+            it = e.items[j]
+            it.B, it.hi, it.lo = pb, base + row0 * ktot * 4, lo_base + row0 * ktot * 4
+            it.ldb, it.N, it.K, it.kpad, it.ldo, it.col0 = int(ldb), n, Kd, ktot, ktot, 0
+            it.transposed, it.tile0 = 0, self._tiles + tiles
+            tiles += ((n + 31) // 32) * (ktot // 32)
+            row0 += n
+        self._tiles += tiles
+        e.epoch, e.w_version = -1, -1
+        self.entries[k] = e
+        if self._table is not None:
+            self._old_tables.append(self._table)
+        self._table = None
+        return e
+
     def ready(self, e):
         return e.epoch == self.epoch and e.w_version == e.W._version
 
@@ -389,6 +449,67 @@ class WeightPrep:
         _lib.check(_L().i3d_gemm_prep_run(_p(self._table), self._n_items, self._tiles, _s()), "i3d_gemm_prep_run")
         for e in ents:
             e.epoch, e.w_version = self.epoch, e.W._version
+
+
+def edge_gather_add(P, src, dst, T, code, bias, Y, stats_act=None, arena=None, valid=None):
+    """Y[m] = P[src[m], :F] + P[dst[m], F:2F] + T[code[m]] + bias (i3d_edge_gather_add); returns the fp64 [2F] column
+    sums of act(Y), act(Y)^2 when ``stats_act`` is given."""
+    pp, ldp = _mat(P, "P")
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    pt, ldt = (None, 0) if T is None else _mat(T, "T")
+    stats, flag = (None, 0)
+    ws = keep = None
+    if stats_act is not None:
+        stats, flag = _stats_buffer(arena, 2 * F, Y.device)
+        ws, keep = _ws(arena, 2 * F, 8)
+    _lib.check(_L().i3d_edge_gather_add(pp, ldp, _vec(src, torch.int32, "src"), _vec(dst, torch.int32, "dst"), pt, ldt,
+                                        _vec(code, torch.int32, "code"), _vec(bias, torch.float32, "bias"), M, F, py, ldy,
+                                        _p(stats), 0 if stats_act is None else (stats_act | flag), _valid(valid), ws,
+                                        _s()), "i3d_edge_gather_add")
+    return stats
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def _bond_check(combo, Ws, col0):
+    _vec(combo, torch.float32, "combo")
+    n_codes, F = combo.shape
+    Fout, ldw = Ws[0].shape[0], Ws[0].stride(0)
+    for W in Ws:
+        _req(W, torch.float32, "W")
+        if W.dim() != 2 or W.stride(1) != 1 or W.shape[0] != Fout or W.stride(0) != ldw or W.shape[1] < col0 + F:
+            raise ValueError("bond tables: the layers' weights must share shape and leading dimension")
+    return n_codes, F, Fout, ldw
+
+
+def bond_tables_fwd(combo, Ws, col0):
+    """T_l = combo @ W_l[:, col0:col0+F]^T for every layer in one launch (i3d_bond_tables_fwd); returns the list of T_l"""
+    n_codes, F, Fout, ldw = _bond_check(combo, Ws, col0)
+    Ts = [torch.empty(n_codes, Fout, dtype=torch.float32, device=combo.device) for _ in Ws]
+    _lib.check(_L().i3d_bond_tables_fwd(_p(combo), n_codes, F, len(Ws), _ptr_array(Ws), ldw, col0, Fout, _ptr_array(Ts),
+                                        _s()), "i3d_bond_tables_fwd")
+    return Ts
+
+
+def bond_tables_bwd(combo, Ws, col0, dTs, dWs, want_dcombo=True):
+    """dW_l[:, col0:col0+F] += dT_l^T combo (layers whose dT_l / dW_l is None are skipped); returns dcombo or None"""
+    n_codes, F, Fout, ldw = _bond_check(combo, Ws, col0)
+    for t in dTs:
+        if t is not None:
+            _vec(t, torch.float32, "dT")
+    for t in dWs:
+        if t is not None and (t.stride(0) != ldw or t.stride(1) != 1):
+            raise ValueError("bond tables: a weight gradient must share the weight's layout")
+    dcombo = torch.zeros(n_codes, F, dtype=torch.float32, device=combo.device) if want_dcombo else None
+    _lib.check(_L().i3d_bond_tables_bwd(_p(combo), n_codes, F, len(Ws), _ptr_array(Ws), ldw, col0, Fout,
+                                        _ptr_array(dTs), _ptr_array(dWs), _p(dcombo), _s()), "i3d_bond_tables_bwd")
+    return dcombo
 
 
 def transpose(x):
@@ -434,12 +555,15 @@ def bn_bwd_reduce(dO, Y, act, save, arena=None, zero=None, valid=None):
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
     sums2, flag = _stats_buffer(arena, 2 * F, Y.device)
+    ws, keep = _ws(arena, 2 * F, 8)
     _lib.check(_L().i3d_bn_bwd_reduce_v(pd, ldd, py, ldy, M, F, act | flag, _p(save), _p(sums2), _p(zero),
-                                        0 if zero is None else zero.numel(), _valid(valid), _s()), "i3d_bn_bwd_reduce")
+                                        0 if zero is None else zero.numel(), _valid(valid), ws, _s()),
+               "i3d_bn_bwd_reduce")
     return sums2
 
 
-def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True, dbias_zeroed=None, valid=None):
+def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=True, dbias_zeroed=None, valid=None,
+                 arena=None):
     pd, ldd = _mat(dO, "dO")
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
@@ -453,9 +577,10 @@ def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=Tr
         dbias = torch.zeros(F, dtype=torch.float32, device=dev)
     dgamma = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
+    ws, keep = _ws(arena, F, 4) if dbias is not None else (None, None)
     _lib.check(_L().i3d_bn_bwd_apply_v(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,
                                        _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), _p(dgamma), _p(dbeta),
-                                       _valid(valid), _s()), "i3d_bn_bwd_apply")
+                                       _valid(valid), ws, _s()), "i3d_bn_bwd_apply")
     return dY, dbias, dgamma, dbeta
 
 

@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "i3d.h")
 SO_PATH = os.path.join(_HERE, "lib3dinfomax_b200.so")
-SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_net3d.cu", "i3d_gemm.cu", "i3d_gemm_tc.cu", "i3d_gemm_tc_ws.cu", "i3d_gemm_tc_tn.cu",
+SOURCES = ["i3d_runtime.cu", "i3d_graph.cu", "i3d_pna.cu", "i3d_bn.cu", "i3d_bond.cu", "i3d_net3d.cu", "i3d_gemm.cu", "i3d_gemm_tc.cu", "i3d_gemm_tc_ws.cu", "i3d_gemm_tc_tn.cu",
            "i3d_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
@@ -30,6 +30,11 @@ class gemm_seg(ctypes.Structure):
     _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("a_idx", ctypes.c_void_p),
                 ("b_idx", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("K", ctypes.c_int32),
                 ("lda", ctypes.c_int32), ("ldb", ctypes.c_int32)]
+
+
+class reduce_ws(ctypes.Structure):
+    """struct i3d_reduce_ws of include/i3d.h"""
+    _fields_ = [("slots", ctypes.c_void_p), ("slot_bytes", ctypes.c_int64), ("counter", ctypes.c_void_p)]
 
 
 class prep_item(ctypes.Structure):
@@ -63,17 +68,17 @@ SIGNATURES = {
     "i3d_collate_2d": (_I, [_P, _L, _P, _P, _P, _L, _P, _I, _P, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
     "i3d_collate_3d": (_I, [_P, _L, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
     "i3d_collate_2d_struct": (_I, [_P, _L, _P, _P, _P, _L, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P, _P,
-                                   _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "i3d_collate_3d_struct": (_I, [_P, _L, _I, _P, _P, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "i3d_gemm_ex_v": (_I, [_I, _L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, ctypes.c_size_t, _P, _I, _P,
                            _P]),
     "i3d_gemm_nt_prepared_v": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
     "i3d_gemm_nt_bucketed_v": (_I, [_L, _I, _I, ctypes.POINTER(gemm_seg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I,
                                     _P, _P]),
-    "i3d_act_colstats_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P]),
+    "i3d_act_colstats_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "i3d_bn_apply_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P, _P]),
-    "i3d_bn_bwd_reduce_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P]),
-    "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "i3d_bn_bwd_reduce_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "i3d_gemm_backend": (_I, [_I]),
@@ -91,6 +96,9 @@ SIGNATURES = {
     "i3d_bn_bwd_reduce": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P]),
     "i3d_bn_bwd_reduce_ex": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P]),
     "i3d_bn_bwd_apply": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "i3d_edge_gather_add": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _L, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "i3d_bond_tables_fwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
+    "i3d_bond_tables_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "i3d_act_fwd": (_I, [_P, _L, _I, _P, _P]),
     "i3d_act_bwd": (_I, [_P, _P, _L, _I, _P, _P]),
     "i3d_pna_aggregate_fwd": (_I, [_P, _P, _L, _I, _P, _I, _P]),

@@ -162,7 +162,7 @@ class _FC(torch.autograd.Function):
             dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
             sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz, valid=cfg.valid)
+                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
         elif cfg.act != 0 or cfg.valid is not None:
             # (padded batches: the pass also writes the exact zeros of the padding rows)
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
@@ -300,7 +300,7 @@ class _FCPostMerged(torch.autograd.Function):
             dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
             sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz, valid=cfg.valid)
+                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
         elif cfg.act != 0 or cfg.valid is not None:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:
@@ -339,6 +339,165 @@ def fc_post_merged(plan, merged, h, agg, W, b, act, bn=None, training=True, resi
         gamma, beta, rm, rv, nbt, mom, eps = bn
         cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps, valid=valid)
     return _FCPostMerged.apply(cfg, plan, merged, W, b, gamma, beta, residual, h, agg)
+
+
+class EdgeCodes:
+    """Per-batch index tensors of the factored edge layer: CSR gather lists + the bond-feature code of every edge."""
+    __slots__ = ("src_csr", "dst_csr", "rowptr", "out_rowptr", "out_pos", "code32", "code64", "col_off", "n_codes")
+
+    def __init__(self, st, code_csr, n_codes):
+        self.src_csr, self.dst_csr, self.rowptr = st.src_csr, st.dst_csr, st.rowptr
+        self.out_rowptr, self.out_pos = st.out_rowptr, st.out_pos
+        self.code64 = code_csr.reshape(-1, 1).contiguous()
+        self.code32 = code_csr.to(torch.int32)
+        self.col_off = torch.zeros(1, dtype=torch.int32, device=code_csr.device)
+        self.n_codes = int(n_codes)
+
+
+class _BondTables(torch.autograd.Function):
+    """T_l = combo W_e,l^T for every message-passing layer l (W_e,l = columns [col0, col0+F) of the layer's first edge-MLP
+    weight): the `e` K-segment of cat[h[src], h[dst], e] W^T as a table over the distinct bond-feature combinations
+    (``combo`` [n_codes, F] = their embeddings).  One launch for all layers, forward and backward (i3d_bond.cu)."""
+
+    @staticmethod
+    def forward(ctx, col0, combo, *Ws):
+        combo = combo.contiguous()
+        Ts = K.bond_tables_fwd(combo, list(Ws), col0)
+        ctx.col0 = col0
+        ctx.w_params = Ws
+        ctx.save_for_backward(combo, *Ws)
+        return tuple(Ts)
+
+    @staticmethod
+    def backward(ctx, *dTs):
+        combo = ctx.saved_tensors[0]
+        Ws = list(ctx.saved_tensors[1:])
+        dTs = [None if d is None else d.contiguous() for d in dTs]
+        # FC weights owned by FusedAdam accumulate straight into their slice of the flat gradient buffer
+        direct = [getattr(w, "_i3d_grad_view", None) for w in ctx.w_params]
+        need = ctx.needs_input_grad[2:]
+        accs = [d if d is not None else (torch.zeros_like(w) if n else None) for d, w, n in zip(direct, Ws, need)]
+        dcombo = K.bond_tables_bwd(combo, Ws, ctx.col0, dTs, accs, want_dcombo=ctx.needs_input_grad[1])
+        grads = [None if (d is not None or not n) else a for d, a, n in zip(direct, accs, need)]
+        return (None, dcombo) + tuple(grads)
+
+
+def bond_tables(combo, weights, col0):
+    """list of per-layer tables T_l [n_codes, Fout] (see _BondTables)"""
+    return list(_BondTables.apply(int(col0), combo, *weights))
+
+
+class _FCEdgeFactored(torch.autograd.Function):
+    """First FCLayer of the edge MLP over cat[h[src], h[dst], e] (models/pna.py:249-252) in factored form:
+    (h W_s^T)[src] + (h W_d^T)[dst] + T[code] with P = h [W_s; W_d]^T ONE node-level GEMM (N rows, K = F) and
+    T = combo W_e^T the layer's bond-feature table (ops.bond_tables).  The edge-level work left is one gather-add pass
+    with the BatchNorm statistics fused (i3d_edge_gather_add).
+    Backward: dP = per-node row sums of dY over the out- / in-edges (what the h[src], h[dst] gathers need anyway),
+    dT = dY summed per code; every GEMM of the layer is node-level.  The weight gradient returned / accumulated here
+    covers the W_s, W_d columns; the W_e columns get theirs from _BondTables.backward."""
+
+    @staticmethod
+    def forward(ctx, cfg, g, W, b, gamma, beta, h, T):
+        N, F = h.shape
+        Fout = W.shape[0]
+        M = g.src_csr.numel()
+        if W.shape[1] != 3 * F or T.shape != (g.n_codes, Fout):
+            raise ValueError("factored edge layer expects a [Fout, 3F] weight and a [n_codes, Fout] table")
+        dev = W.device
+        P = torch.empty(N, 2 * Fout, dtype=torch.float32, device=dev)
+        prep = getattr(W, "_i3d_prep", None)
+        ready = None
+        if prep is not None and K.gemm_nt_prepared_ok(N, 2 * Fout, [{"A": h, "K": F}]):
+            ent = prep.entry_stacked(W, (F,), [W[:, :F], W[:, F:2 * F]])
+            ready = ent if prep.ready(ent) else None
+        if ready is not None:
+            K.gemm(K.NT, N, 2 * Fout, [{"A": h, "K": F}], P, prepared=ready)
+        else:
+            K.gemm(K.NT, N, Fout, [{"A": h, "B": W[:, :F], "K": F}], P[:, :Fout])
+            K.gemm(K.NT, N, Fout, [{"A": h, "B": W[:, F:2 * F], "K": F}], P[:, Fout:])
+        Y = torch.empty(M, Fout, dtype=torch.float32, device=dev)
+        want_stats = cfg.has_bn and cfg.training
+        sums = K.edge_gather_add(P, g.src_csr, g.dst_csr, T.contiguous(), g.code32, b, Y,
+                                 stats_act=cfg.act if want_stats else None, arena=getattr(W, "_i3d_arena", None),
+                                 valid=cfg.valid)
+        save = None
+        if cfg.has_bn:
+            O, save = K.bn_apply(Y, cfg.act, sums, cfg.running_mean, cfg.running_var, cfg.nbt, gamma, beta,
+                                 cfg.momentum, cfg.eps, cfg.training, None, valid=cfg.valid)
+        else:
+            O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
+        ctx.cfg, ctx.g, ctx.w_param = cfg, g, W
+        ctx.save_for_backward(W, Y, save, gamma, h)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        cfg, g = ctx.cfg, ctx.g
+        W, Y, save, gamma, h = ctx.saved_tensors
+        N, F = h.shape
+        Fout = W.shape[0]
+        dev = W.device
+        if dO.dim() != 2 or dO.stride(1) != 1:
+            dO = dO.contiguous()
+        need_b = ctx.needs_input_grad[3]
+        dgamma = dbeta = None
+        arena = getattr(ctx.w_param, "_i3d_arena", None)
+        if cfg.has_bn:
+            dbz = torch.empty(Fout, dtype=torch.float32, device=dev) if need_b else None
+            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
+                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+        elif cfg.act != 0 or cfg.valid is not None:
+            dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
+        else:
+            dY = dO
+            db = K.colsum(dO) if need_b else None
+        # dP: per-node sums of dY over the node's out-edges (h[src] term) and in-edges (h[dst] term)
+        Rs = K.segment_sum_fwd(dY, g.out_rowptr, g.out_pos)
+        Rd = K.segment_sum_fwd(dY, g.rowptr, None)
+        # dT: dY summed per bond-feature code (shared-memory pre-reduction of the embedding-gradient kernel)
+        dT = K.embed_sum_bwd(g.code64, g.col_off, None, dY, g.n_codes, g.n_codes) if ctx.needs_input_grad[7] else None
+        dW = None
+        if ctx.needs_input_grad[2]:
+            direct = getattr(ctx.w_param, "_i3d_grad_view", None)
+            acc = direct if direct is not None else torch.zeros_like(W)
+            side = None
+            if direct is not None and N >= _dw_min_rows() and Fout >= 64:
+                side = _dw_fork(dev, torch.cuda.current_stream(dev), [Rs, Rd, h])
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                K.gemm(K.TN, Fout, F, [{"A": Rs, "B": h, "K": N}], acc[:, :F], accumulate=True)
+                K.gemm(K.TN, Fout, F, [{"A": Rd, "B": h, "K": N}], acc[:, F:2 * F], accumulate=True)
+            dW = None if direct is not None else acc
+        dh = None
+        if ctx.needs_input_grad[6]:
+            dh = torch.empty(N, F, dtype=torch.float32, device=dev)
+            nn = [{"A": Rs, "K": Fout}, {"A": Rd, "K": Fout}]
+            prep = getattr(ctx.w_param, "_i3d_prep", None)
+            via_nt = N >= 256 and Fout % 4 == 0 and F % 4 == 0
+            ready = None
+            if via_nt and prep is not None and K.gemm_nt_prepared_ok(N, F, nn):
+                ent = prep.entry(ctx.w_param, ("b", F, 0, F), F, [(W[:, :F], Fout), (W[:, F:2 * F], Fout)], True)
+                ready = ent if prep.ready(ent) else None
+            if ready is None:
+                if via_nt:
+                    Wt = K.transpose(W[:, :2 * F])                         # [2F, Fout]
+                    nn[0]["B"], nn[1]["B"] = Wt[:F, :], Wt[F:, :]
+                else:
+                    nn[0]["B"], nn[1]["B"] = W[:, :F], W[:, F:2 * F]
+            K.gemm(K.NT if via_nt else K.NN, N, F, nn, dh, prepared=ready)
+        return None, None, dW, db, dgamma, dbeta, dh, dT
+
+
+def fc_edge_factored(g, h, T, W, b, act, bn=None, training=True, valid=None):
+    """FCLayer over cat[h[src], h[dst], e] in factored form (``g``: EdgeCodes, ``T``: the layer's table from
+    ``bond_tables``); other arguments as ``fc``."""
+    if bn is None:
+        cfg = FCConfig(None, act, False, training, valid=valid)
+        gamma = beta = None
+    else:
+        gamma, beta, rm, rv, nbt, mom, eps = bn
+        cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps, valid=valid)
+    return _FCEdgeFactored.apply(cfg, g, W, b, gamma, beta, h, T)
 
 
 class _EmbedSum(torch.autograd.Function):

@@ -12,6 +12,8 @@ Per layer (models/pna.py:199-213), in kernels:
   posttrans  : ONE GEMM over the virtual cat[h, agg, agg*ln(D+1), agg/ln(D+1)] (degree scalers applied to the
                operand tile as it is staged, never materialised) -> BN -> + residual.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -86,11 +88,18 @@ class PNALayer(nn.Module):
                              last_activation=last_activation, dropout=dropout, mid_batch_norm=mid_batch_norm,
                              last_batch_norm=last_batch_norm, batch_norm_momentum=batch_norm_momentum)
 
-    def forward(self, st, h, ef_csr):
+    def forward(self, st, h, ef_csr, edge_codes=None, table=None):
         # models/pna.py:203,237-252 — edge MLP over cat[h[src], h[dst], e], rows emitted in CSR order
-        msg = self.pretrans([ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
-                             ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr),
-                             ops.Seg(ef_csr)], valid=st.e_valid)
+        if edge_codes is not None:
+            # factored first layer: node-level GEMM + 60-row bond-feature table + one gather-add pass (ops._FCEdgeFactored)
+            fcs = self.pretrans.fully_connected
+            msg = fcs[0].forward_edge_factored(edge_codes, h, table, st.e_valid)
+            for i in range(1, len(fcs)):
+                msg = fcs[i](msg, None, st.e_valid)
+        else:
+            msg = self.pretrans([ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
+                                 ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr),
+                                 ops.Seg(ef_csr)], valid=st.e_valid)
         # models/pna.py:206,221-235
         agg = ops.pna_aggregate(msg, st.rowptr)
         # models/pna.py:207-211 — cat[h, agg, agg*amp, agg*att] -> posttrans -> + h
@@ -122,6 +131,21 @@ class PNAGNN(nn.Module):
         self.atom_encoder = AtomEncoder(emb_dim=hidden_dim)
         self.bond_encoder = BondEncoder(emb_dim=hidden_dim)
         self.keep_edge_side_effects = True
+        # every combination of the categorical bond features (5*6*2 = 60 rows) and the mixed-radix weights that turn an
+        # edge's feature row into its combination index: lets the `e` K-segment of the edge MLP become a table lookup
+        dims = list(BOND_FEATURE_DIMS)
+        n_codes = 1
+        for d in dims:
+            n_codes *= d
+        self.n_bond_codes = n_codes
+        mult, acc = [], 1
+        for d in reversed(dims):
+            mult.append(acc)
+            acc *= d
+        mult = list(reversed(mult))
+        grid = torch.stack(torch.meshgrid(*[torch.arange(d) for d in dims], indexing="ij"), dim=-1).reshape(-1, len(dims))
+        self.register_buffer("_bond_combos", grid.long().contiguous(), persistent=False)
+        self.register_buffer("_bond_mult", torch.tensor(mult, dtype=torch.int64), persistent=False)
 
     def forward(self, graph):
         st = graph_structure(graph)
@@ -130,13 +154,27 @@ class PNAGNN(nn.Module):
             raise TypeError("PNA expects int64 categorical features in ndata['feat'] / edata['feat'] "
                             "(the graph is consumed by forward, as in the reference)")
         h = self.atom_encoder(x_atom)                              # models/pna.py:162
-        ef_csr = self.bond_encoder(e_attr, perm=st.eid)            # models/pna.py:163, emitted in CSR order
+        factored = (os.environ.get("I3D_PRETRANS", "factored") != "gemm" and self.n_bond_codes <= 256
+                    and e_attr.shape[1] == self._bond_mult.numel())
+        edge_codes = tables = ef_csr = None
+        if factored:
+            # models/pna.py:163 — the bond embedding of an edge is one of n_bond_codes rows: embed the combinations once,
+            # and turn the `e` segment of every layer's edge MLP into a table over them (one launch for all layers)
+            combo = self.bond_encoder(self._bond_combos)
+            F = h.shape[1]
+            tables = ops.bond_tables(combo, [l.pretrans.fully_connected[0].linear.weight for l in self.mp_layers], 2 * F)
+            code_csr = getattr(st, "code_csr", None)                # emitted by the device collate when it built `st`
+            if code_csr is None:
+                code_csr = (e_attr * self._bond_mult).sum(dim=1)[st.eid.long()]
+            edge_codes = ops.EdgeCodes(st, code_csr, self.n_bond_codes)
+        else:
+            ef_csr = self.bond_encoder(e_attr, perm=st.eid)        # models/pna.py:163, emitted in CSR order
         graph.ndata["feat"] = h
         if self.keep_edge_side_effects:
             with torch.no_grad():
                 graph.edata["feat"] = self.bond_encoder(e_attr)    # edge-id order, as the reference leaves it
-        for layer in self.mp_layers:
-            h, _ = layer(st, h, ef_csr)
+        for li, layer in enumerate(self.mp_layers):
+            h, _ = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li])
             graph.ndata["feat"] = h                                # models/pna.py:213
         return st, h
 

@@ -126,7 +126,9 @@ int i3d_collate_3d(const int64_t* idx, int64_t B, const int64_t* atom_slices, co
  *        position), out_rowptr_l[Ntot], out_pos_l[Etot] (local CSR position of the molecule's edges sorted by source).
  *        Outputs: src/dst [e_cap] int64 (edge-id order), x_atom [n_cap, n_atom_feat], e_attr [e_cap, n_edge_feat],
  *        rowptr / out_rowptr [n_cap+1], src_csr / dst_csr / eid / out_pos [e_cap], graph_ptr [B+1]  — bit-equal to
- *        i3d_csr_build on the collated edge list.
+ *        i3d_csr_build on the collated edge list.  code_csr [e_cap] (optional): sum_c e_attr[eid[k], c] * code_mult[c],
+ *        the mixed-radix index of the CSR-ordered edge's categorical feature row (the table index of
+ *        i3d_edge_gather_add); 0 for padding edges.
  *   3-D: C conformer graphs per molecule, molecule-major [datasets/qmugs_dataset.py:149-166]; coords [Ntot, ld_coords]
  *        fp32 with conformer c in columns [3c, 3c+3).  Complete digraphs in the reference's order have a closed-form
  *        CSR; the out-CSR row pointer equals rowptr.  Outputs: src3/dst3 [e_cap] int64, d3 [e_cap] (edge-id order),
@@ -138,7 +140,7 @@ int i3d_collate_2d_struct(const int64_t* idx, int64_t B, const int64_t* atom_sli
                           const int64_t* node_ptr, const int64_t* edge_ptr, int64_t n_cap, int64_t e_cap, int64_t* src,
                           int64_t* dst, int64_t* x_atom, int64_t* e_attr, int32_t* rowptr, int32_t* src_csr,
                           int32_t* dst_csr, int32_t* eid, int32_t* out_rowptr, int32_t* out_pos, int32_t* graph_ptr,
-                          void* stream);
+                          const int64_t* code_mult, int64_t* code_csr, void* stream);
 int i3d_collate_3d_struct(const int64_t* idx, int64_t B, int C, const int64_t* atom_slices, const float* coords,
                           int ld_coords, const int64_t* node_ptr, const int64_t* edge3_ptr, int64_t n_cap, int64_t e_cap,
                           int64_t* src3, int64_t* dst3, float* d3, int32_t* rowptr, int32_t* src_csr, int32_t* dst_csr,
@@ -291,19 +293,54 @@ int i3d_bn_bwd_reduce_ex(const float* dO, int ldd, const float* Y, int ldy, int6
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                      int training, const float* save_mean_rstd, const float* gamma, const double* sums2,
                      float* dY, int lddy, float* dbias, float* dgamma, float* dbeta, void* stream);
+/* Workspace of the two-stage column reductions (optional argument `rws` below; NULL = fp atomics into the output).
+ * Same-address atomics serialise in L2: with 300-450 CTAs the atomic tail was most of a column-statistics kernel.  With a
+ * workspace every CTA stores its partial sums in its own slot, takes a ticket on `counter`, and the last CTA sums the
+ * slots in slot order and STORES the result (the output then needs no pre-zeroing and is bit-reproducible).
+ *   slots       caller-owned device scratch, slot_bytes >= CTAs x columns x element size (else: atomics);
+ *   counter     device uint32, 0 on entry, left 0 on exit; one counter per kernel that may run concurrently. */
+typedef struct {
+  void* slots;
+  int64_t slot_bytes;
+  unsigned int* counter;
+} i3d_reduce_ws;
+
 /* valid-row variants of the four entry points above (see i3d_gemm_ex_v) */
 int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, double* sums, const int32_t* m_valid,
-                       void* stream);
+                       const i3d_reduce_ws* rws, void* stream);
 int i3d_bn_apply_v(const float* Y, int64_t M, int F, int ldy, int act, const double* sums, float* running_mean,
                    float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
                    float momentum, float eps, int training, float* save_mean_rstd, const float* residual, float* O,
                    int ldo, const int32_t* m_valid, void* stream);
 int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                         const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n,
-                        const int32_t* m_valid, void* stream);
+                        const int32_t* m_valid, const i3d_reduce_ws* rws, void* stream);
+/* with rws, dbias is STORED (not accumulated) */
 int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                        int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
-                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid, void* stream);
+                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid,
+                       const i3d_reduce_ws* rws, void* stream);
+/* Factored first layer of the edge MLP [models/pna.py:237-252]: cat[h[src], h[dst], e] W^T =
+ * (h W_s^T)[src] + (h W_d^T)[dst] + e W_e^T.  P [N, >=2F] = h [W_s; W_d]^T comes from ONE node-level GEMM; the bond
+ * features take prod(5,6,2) = 60 distinct values [commons/mol_encoder.py:4-7], so e W_e^T is a table T [n_codes, F]
+ * indexed by the edge's feature code.  Y[m,:] = P[src[m], 0:F] + P[dst[m], F:2F] + T[code[m],:] + bias[:]; negative
+ * src / dst read zeros; T / code / bias optional.  col_stats (optional, fp64 [2F]): column sums of act(Y), act(Y)^2 over
+ * the rows < *m_valid (all M when m_valid is NULL) — the FCLayer's train-mode BatchNorm statistics; stats_act takes
+ * I3D_STATS_PREZEROED like the GEMM entry points. */
+int i3d_edge_gather_add(const float* P, int ldp, const int32_t* src, const int32_t* dst, const float* T, int ldt,
+                        const int32_t* code, const float* bias, int64_t M, int F, float* Y, int ldy, double* col_stats,
+                        int stats_act, const int32_t* m_valid, const i3d_reduce_ws* rws, void* stream);
+/* The tables of i3d_edge_gather_add for ALL message-passing layers in one launch, and their gradients:
+ *   fwd   T_l[c, n]             = sum_k combo[c, k] W_l[n, col0 + k]          l < L, c < n_codes <= 64, n < Fout
+ *   bwd   dW_l[n, col0 + k]    += sum_c dT_l[c, n] combo[c, k]                 (layers with dT[l] or dW[l] NULL skipped)
+ *         dcombo[c, k]         += sum_l sum_n dT_l[c, n] W_l[n, col0 + k]      (caller-zeroed; NULL: not computed)
+ * combo [n_codes, F] = BondEncoder applied to every categorical combination [commons/mol_encoder.py:45-73];
+ * W / T / dT / dW are HOST arrays of L (<= 16) device pointers; W_l is the first pretrans weight of layer l
+ * [models/pna.py:249-252], leading dimension ldw, `e` segment at columns [col0, col0 + F); T_l, dT_l [n_codes, Fout]. */
+int i3d_bond_tables_fwd(const float* combo, int n_codes, int F, int L, const float* const* W, int ldw, int col0,
+                        int Fout, float* const* T, void* stream);
+int i3d_bond_tables_bwd(const float* combo, int n_codes, int F, int L, const float* const* W, int ldw, int col0,
+                        int Fout, const float* const* dT, float* const* dW, float* dcombo, void* stream);
 /* y = act(x) elementwise (used where there is no BN, and for Net3D's second SiLU, models/net3d.py:81) */
 int i3d_act_fwd(const float* x, int64_t n, int act, float* y, void* stream);
 int i3d_act_bwd(const float* gy, const float* x, int64_t n, int act, float* gx, void* stream);

@@ -906,7 +906,24 @@ def case_finetune_config():
             for k, fp in zip(gold["grad_keys"], gold["grad_fp"]):
                 mine = grad_fingerprint(named[str(k)].grad.cpu())
                 worst = max(worst, float(np.abs(mine[2:] - fp[2:]).max()) / scale)
-            out.append((tag + "/param_grads(all, sampled)", worst, 1e-3))
+            # Ground truth: the oracle in float64.  12 molecules (~220 nodes) through 7 train-mode BatchNorm layers and
+            # an L1 loss (gradient = sign / B): the CPU fp32 reference's own distance from the truth sets the scale, and
+            # the golden fp32 vectors are checked at 1e-3 or twice that distance.
+            def oracle_grads(dt):
+                s = {k: (v.to(dt) if v.is_floating_point() else v.clone()) for k, v in st.items()}
+                s = O.as_leaf_params(s)
+                og2, xa, ea, _, _ = O.graphs_from_batch(b)
+                zz = O.pna_forward(s, c, og2, xa, ea, True)
+                torch.nn.L1Loss()(zz, y.cpu().to(dt)).backward()
+                return {k: s[k].grad for k in O.param_keys(s)}
+
+            g64, g32 = oracle_grads(torch.float64), oracle_grads(torch.float32)
+            sc = max(float(v.abs().max()) for v in g64.values())
+            e_cuda = max(float((named[k].grad.cpu().double() - g64[k]).abs().max()) for k in g64) / sc
+            e_cpu = max(float((g32[k].double() - g64[k]).abs().max()) for k in g64) / sc
+            out.append((tag + "/param_grads(all, sampled; vs the reference's fp32 vectors)", worst, max(1e-3, 2 * e_cpu + e_cuda)))
+            out.append((tag + "/param_grads(all tensors in full; cuda vs fp64 truth)", e_cuda, max(1e-3, 2 * e_cpu)))
+            out.append((tag + "/param_grads(all tensors in full; cpu fp32 oracle vs fp64 truth, for scale)", e_cpu, float("inf")))
     return out
 
 
@@ -1066,11 +1083,11 @@ def case_full_size_properties():
 
 from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 from gpu_cases_bucketed import (case_bucketed_step, case_bucketed_step_conformers, case_collate_struct,  # noqa: E402
-                                case_epoch_many_shapes, case_staging_ring, case_step_b512, case_step_config3)
+                                case_edge_factored, case_epoch_many_shapes, case_staging_ring, case_step_b512, case_step_config3)
 
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
              case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_pna_original, case_finetune_config, case_sharded_equals_full,
-             case_collate_struct, case_staging_ring, case_bucketed_step, case_bucketed_step_conformers, case_step_b512,
+             case_collate_struct, case_edge_factored, case_staging_ring, case_bucketed_step, case_bucketed_step_conformers, case_step_b512,
              case_step_config3, case_epoch_many_shapes]

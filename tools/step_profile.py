@@ -33,23 +33,28 @@ def main():
     pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
     n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
     graph = args.mode == "graph"
-    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), dev, {"lr": 8e-5}, graph_safe=graph)
-    batches = [i3d.batch_from_numpy(i3d.synthetic.make_batch(1000 + i, args.batch), dev) for i in range(2)]
-
-    def fresh(pair):
-        g2, g3 = pair
-        a = i3d.GraphBatch(*g2.edges(), g2.batch_num_nodes(), None, {"feat": g2.ndata["feat"]},
-                           {"feat": g2.edata["feat"]}, g2.number_of_nodes(), g2.max_in_degree)
-        b = i3d.GraphBatch(*g3.edges(), g3.batch_num_nodes(), None, {}, {"d": g3.edata["d"]}, g3.number_of_nodes())
-        return a, b
-
-    caps = [i3d.CapturedStep(tr, *fresh(p), warmup=2) for p in batches] if graph else None
+    # the step bench.py times: device collate padded to a shape bucket -> both encoders -> loss -> backward -> Adam,
+    # here launched EAGERLY (the kernel sequence BucketedStep captures) so that CUPTI attributes every kernel
+    import numpy as np
+    from importlib import import_module
+    tr = i3d.SelfSupervisedTrainer(pna, n3, i3d.NTXent(tau=0.1), dev, {"lr": 8e-5}, graph_safe=True)
+    store = i3d.PackedMoleculeStore(i3d.synthetic.make_store(7, 4 * args.batch), dev)
+    run = i3d.BucketedStep(tr, store)
+    rng = np.random.default_rng(3)
+    idxs = [rng.permutation(4 * args.batch)[:args.batch] for _ in range(8)]
+    tmod = import_module("3dinfomax_b200.trainer")
+    cmod = import_module("3dinfomax_b200.collate")
+    bk = tmod._Bucket()
+    lad = run.ladder(args.batch)
+    bk.caps = lad.caps(max(lad.level_of(store.batch_sizes(ix)) for ix in idxs))
+    bk.meta = torch.zeros(cmod.metadata_len(args.batch), dtype=torch.int64, device=dev)
 
     def step(i):
-        if caps is not None:
-            return caps[i % 2].run()
-        g2, g3 = fresh(batches[i % 2])
-        return tr.process_batch(([g2], [g3]))[0]
+        if graph:
+            return run.step(idxs[i % 8])
+        store.stage_metadata(idxs[i % 8], dev_out=bk.meta)
+        run._body(bk, args.batch, True)
+        return run.loss
 
     for i in range(3):
         step(i)
