@@ -42,7 +42,7 @@ __device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const
       for (int i = 0; i < V; ++i) {
         double s = 0.0;
         for (int r = 0; r < m.RP; ++r) s += sh[(a * V + i) * kColThreads + r * FV + m.cg];
-        atomicAdd(gsum + (int64_t)a * F + m.cg * V + i, s);
+        atomicAdd(gsum + ((int64_t)a * F + m.cg * V + i) * I3D_STATS_STRIDE, s);
       }
   }
 }
@@ -54,7 +54,7 @@ __device__ __forceinline__ void block_col_reduce_f64(double (&acc)[NV][V], const
 // longer depend on the order in which CTAs retire).  `counter` must be 0 on entry and is reset to 0 on exit.
 template <typename T>
 __device__ __forceinline__ void last_block_col_sum(const T* __restrict__ slots, int ncols, T* __restrict__ out,
-                                                   unsigned* __restrict__ counter) {
+                                                   unsigned* __restrict__ counter, int out_stride = 1) {
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
@@ -73,7 +73,7 @@ __device__ __forceinline__ void last_block_col_sum(const T* __restrict__ slots, 
       s3 += __ldcg(slots + (int64_t)(b + 3) * ncols + c);
     }
     for (; b < G; ++b) s0 += __ldcg(slots + (int64_t)b * ncols + c);
-    out[c] = (s0 + s1) + (s2 + s3);
+    out[(int64_t)c * out_stride] = (s0 + s1) + (s2 + s3);
   }
   if (threadIdx.x == 0) *counter = 0u;
 }
@@ -101,7 +101,7 @@ __device__ __forceinline__ void block_col_reduce_f64_ws(double (&acc)[NV][V], co
         mine[(int64_t)a * F + m.cg * V + i] = s;
       }
   }
-  last_block_col_sum<double>(slots, NV * F, gsum, counter);
+  last_block_col_sum<double>(slots, NV * F, gsum, counter, I3D_STATS_STRIDE);
 }
 
 template <int V>
@@ -140,8 +140,8 @@ __device__ __forceinline__ void bn_column_terms(int c, int64_t M, int F, const d
                                                 double* var_biased) {
   double mean, var;
   if (training) {
-    mean = sums[c] / (double)M;
-    var = sums[F + c] / (double)M - mean * mean;
+    mean = sums[(int64_t)c * I3D_STATS_STRIDE] / (double)M;
+    var = sums[(int64_t)(F + c) * I3D_STATS_STRIDE] / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
   } else {
     mean = (double)running_mean[c];
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kColThreads)
                         const float* __restrict__ gamma, const double* __restrict__ sums2, float* __restrict__ dY,
                         int lddy, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         const int32_t* __restrict__ m_valid, float* __restrict__ slots,
-                        unsigned* __restrict__ counter) {
+                        unsigned* __restrict__ counter, int db_stride) {
   pdl_grid_sync();
   // shape-bucketed batches: rows [*m_valid, M) are padding — dY is written as exact zeros there (their dO / Y are
   // never read), so nothing downstream (dW = dY^T x, dx = dY W, row sums) sees them
@@ -301,13 +301,14 @@ __global__ void __launch_bounds__(kColThreads)
       mean[i] = save_mean_rstd[c];
       rstd[i] = save_mean_rstd[F + c];
       gr[i] = gamma[c] * rstd[i];
+      const double s_do = sums2[(int64_t)c * I3D_STATS_STRIDE], s_dx = sums2[(int64_t)(F + c) * I3D_STATS_STRIDE];
       if (training) {
-        k1[i] = (float)(sums2[c] / (double)M);
-        k2[i] = (float)(sums2[F + c] / (double)M);
+        k1[i] = (float)(s_do / (double)M);
+        k2[i] = (float)(s_dx / (double)M);
       }
       if (blockIdx.x == 0 && m.rg == 0) {
-        dbeta[c] = (float)sums2[c];
-        dgamma[c] = (float)sums2[F + c];
+        dbeta[c] = (float)s_do;
+        dgamma[c] = (float)s_dx;
       }
     }
   }
@@ -369,10 +370,10 @@ __global__ void __launch_bounds__(kColThreads)
         float s = 0.f;
         for (int r = 0; r < m.RP; ++r) s += sh[i * kColThreads + r * FV + m.cg];
         if (slots) slots[(int64_t)blockIdx.x * F + m.cg * V + i] = s;
-        else atomicAdd(dbias + m.cg * V + i, s);
+        else atomicAdd(dbias + (int64_t)(m.cg * V + i) * db_stride, s);      // db_stride 8: one float per 32-byte sector
       }
     }
-    if (slots) last_block_col_sum<float>(slots, F, dbias, counter);     // (stores: dbias need not be zeroed)
+    if (slots) last_block_col_sum<float>(slots, F, dbias, counter, db_stride);     // (stores: dbias need not be zeroed)
   }
 }
 
@@ -534,7 +535,7 @@ int i3d_act_colstats_v(const float* Y, int64_t M, int F, int ldy, int act, doubl
                        const i3d_reduce_ws* rws, void* stream) {
   I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && sums && (M == 0 || Y), "invalid argument");
   cudaStream_t s = as_stream(stream);
-  I3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
+  I3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F * I3D_STATS_STRIDE, s));
   if (M == 0) return I3D_OK;
   const bool v4 = can_vec4({Y}, {F, ldy});
   const int V = v4 ? 4 : 1, FV = F / V;
@@ -600,7 +601,7 @@ int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64
   cudaStream_t s = as_stream(stream);
   const bool prezeroed = (act & I3D_STATS_PREZEROED) != 0;
   act &= 0xff;
-  if (!prezeroed) I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F, s));
+  if (!prezeroed) I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F * I3D_STATS_STRIDE, s));
   if (M == 0) {
     if (zero_n > 0) I3D_CUDA(cudaMemsetAsync(zero_buf, 0, sizeof(float) * zero_n, s));
     return I3D_OK;
@@ -631,15 +632,16 @@ int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t
 int i3d_bn_bwd_apply(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                      int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
                      int lddy, float* dbias, float* dgamma, float* dbeta, void* stream) {
-  return i3d_bn_bwd_apply_v(dO, ldd, Y, ldy, M, F, act, has_bn, training, save_mean_rstd, gamma, sums2, dY, lddy, dbias,
+  return i3d_bn_bwd_apply_v(dO, ldd, Y, ldy, M, F, act, has_bn, training, save_mean_rstd, gamma, sums2, dY, lddy, dbias, 1,
                             dgamma, dbeta, nullptr, nullptr, stream);
 }
 
 int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                        int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
-                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid,
+                       int lddy, float* dbias, int dbias_stride, float* dgamma, float* dbeta, const int32_t* m_valid,
                        const i3d_reduce_ws* rws, void* stream) {
-  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && (M == 0 || (Y && dO && dY)), "invalid argument");
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && (M == 0 || (Y && dO && dY)) && dbias_stride >= 1,
+              "invalid argument");
   I3D_REQUIRE(!has_bn || (save_mean_rstd && gamma && sums2 && dgamma && dbeta), "BN tensors missing");
   if (M == 0) return I3D_OK;
   const bool v4 = can_vec4({Y, dO, dY}, {F, ldy, ldd, lddy});
@@ -654,11 +656,11 @@ int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_
   if (v4)
     launch(bn_bwd_apply_kernel<4>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta, m_valid, slots, counter);
+                                                                     dgamma, dbeta, m_valid, slots, counter, dbias_stride);
   else
     launch(bn_bwd_apply_kernel<1>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
-                                                                     dgamma, dbeta, m_valid, slots, counter);
+                                                                     dgamma, dbeta, m_valid, slots, counter, dbias_stride);
   I3D_LAUNCHED();
   return I3D_OK;
 }
@@ -671,7 +673,7 @@ int i3d_edge_gather_add(const float* P, int ldp, const int32_t* src, const int32
   cudaStream_t s = as_stream(stream);
   const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
   stats_act &= 0xff;
-  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * F, s));
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * F * I3D_STATS_STRIDE, s));
   if (M == 0) return I3D_OK;
   const bool v4 = can_vec4({P, T, bias, Y}, {F, ldp, ldy, T ? ldt : 0});
   const int V = v4 ? 4 : 1, FV = F / V;

@@ -447,7 +447,7 @@ extern "C" int i3d_gemm_nt_bucketed_v(int64_t Mv, int N, int n_seg, const i3d_ge
                 "segments must be 16-byte aligned, unscaled, with K a multiple of 4");
   const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
   stats_act &= 0xff;
-  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N * I3D_STATS_STRIDE, as_stream(stream)));
   return gemm_ws_nt_bucketed(Mv, N, n_seg, segs, C, ldc, bias, b_hi, b_lo, b_pitch, n_buckets, tile_bucket, row_map,
                              col_stats, stats_act, as_stream(stream), m_valid);
 }
@@ -499,7 +499,7 @@ extern "C" int i3d_gemm_nt_prepared_v(int64_t M, int N, int n_seg, const i3d_gem
   I3D_REQUIRE(i3d_gemm_nt_prepared_ok(M, N, n_seg, segs), "shape not eligible for prepared operands");
   const bool prezeroed = (stats_act & I3D_STATS_PREZEROED) != 0;
   stats_act &= 0xff;
-  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+  if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N * I3D_STATS_STRIDE, as_stream(stream)));
   return gemm_ws_nt(M, N, n_seg, segs, C, ldc, bias, accumulate, const_cast<void*>(ws), col_stats, stats_act,
                     as_stream(stream), true, m_valid);
 }
@@ -532,7 +532,7 @@ extern "C" int i3d_gemm_ex_v(int mode, int64_t M, int N, int n_seg, const i3d_ge
     I3D_REQUIRE(mode == I3D_GEMM_TN || segs[s].b_idx == nullptr, "b_idx is only valid in TN mode");
   }
   if (g_gemm_backend != 1 && gemm_tc_eligible(mode, M, N, n_seg, segs)) {
-    if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N, as_stream(stream)));
+    if (col_stats && !prezeroed) I3D_CUDA(cudaMemsetAsync(col_stats, 0, sizeof(double) * 2 * N * I3D_STATS_STRIDE, as_stream(stream)));
     return gemm_tc(mode, M, N, n_seg, segs, C, ldc, bias, accumulate, ws, ws_bytes, col_stats, stats_act,
                    as_stream(stream), m_valid);
   }

@@ -172,15 +172,17 @@ __global__ void add_i64_kernel(int64_t* x, int64_t d) {
   pdl_grid_sync(); x[0] += d; }
 
 __global__ void multi_copy_kernel(const uint64_t* __restrict__ ptrs, const int64_t* __restrict__ off,
-                                  const int64_t* __restrict__ len, float* __restrict__ flat, int to_flat) {
+                                  const int64_t* __restrict__ len, const int64_t* __restrict__ stride,
+                                  float* __restrict__ flat, int to_flat) {
   pdl_grid_sync();
   const int t = blockIdx.y;
   float* tp = reinterpret_cast<float*>(ptrs[t]);
   float* fp = flat + off[t];
   const int64_t n = len[t];
+  const int64_t st = stride ? stride[t] : 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (to_flat) fp[i] = tp[i];
-    else tp[i] = fp[i];
+    if (to_flat) fp[i] = tp[i * st];
+    else tp[i * st] = fp[i];
   }
 }
 
@@ -336,9 +338,14 @@ int i3d_add_i64(int64_t* x, int64_t delta, void* stream) {
 
 int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len, int T, float* flat, int to_flat,
                    void* stream) {
+  return i3d_multi_copy_strided(ptrs, off, len, nullptr, T, flat, to_flat, stream);
+}
+
+int i3d_multi_copy_strided(const uint64_t* ptrs, const int64_t* off, const int64_t* len, const int64_t* stride, int T,
+                           float* flat, int to_flat, void* stream) {
   I3D_REQUIRE(T >= 0 && T <= 65535 && (T == 0 || (ptrs && off && len && flat)), "invalid argument");
   if (T == 0) return I3D_OK;
-  launch(multi_copy_kernel, dim3(16, T, 1), 256, 0, as_stream(stream), ptrs, off, len, flat, to_flat);
+  launch(multi_copy_kernel, dim3(16, T, 1), 256, 0, as_stream(stream), ptrs, off, len, stride, flat, to_flat);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -218,8 +218,8 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
         s1[0] += h;
         s2[0] = fma(h, h, s2[0]);
       }
-      atomicAdd(stats + n0 + c, (s1[0] + s1[1]) + (s1[2] + s1[3]));
-      atomicAdd(stats + N + n0 + c, (s2[0] + s2[1]) + (s2[2] + s2[3]));
+      atomicAdd(stats + (int64_t)(n0 + c) * I3D_STATS_STRIDE, (s1[0] + s1[1]) + (s1[2] + s1[3]));
+      atomicAdd(stats + (int64_t)(N + n0 + c) * I3D_STATS_STRIDE, (s2[0] + s2[1]) + (s2[2] + s2[3]));
     }
   }
   const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);

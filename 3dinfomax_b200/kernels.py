@@ -16,6 +16,7 @@ NT, NN, TN = 0, 1, 2
 
 
 STATS_PREZEROED = 0x100      # I3D_STATS_PREZEROED (include/i3d.h)
+STATS_STRIDE = 16            # I3D_STATS_STRIDE: one fp64 accumulator per 128-byte line
 
 
 class StatsArena:
@@ -26,7 +27,7 @@ class StatsArena:
     dependent launch between its neighbours.  ``take`` hands out consecutive slices (host-side bump pointer); the
     slices are only valid until the next ``reset`` and never escape the operator that took them."""
 
-    def __init__(self, device, doubles=1 << 17, scratch_bytes=192 << 20, counters=1 << 12):
+    def __init__(self, device, doubles=1 << 20, scratch_bytes=192 << 20, counters=1 << 12):
         self.buf = torch.zeros(doubles, dtype=torch.float64, device=device)
         self.used = 0
         self.lock = __import__("threading").Lock()
@@ -39,7 +40,7 @@ class StatsArena:
         self.slot_ctas = 4 * (torch.cuda.get_device_properties(device).multi_processor_count if on_gpu else 148)
 
     def reset(self):
-        self.buf.zero_()                       # one memset node (1 MB) per step
+        self.buf.zero_()                       # one memset node (8 MB) per step
         self.used = 0
         self.s_used = self.c_used = 0
 
@@ -64,7 +65,9 @@ class StatsArena:
 
 
 def _stats_buffer(arena, n, device):
-    """(buffer, flag): a pre-zeroed arena slice when there is one, else a fresh tensor the library zeroes itself"""
+    """(buffer, flag) for ``n`` column statistics in the library's strided layout (n * STATS_STRIDE doubles): a pre-zeroed
+    arena slice when there is one, else a fresh tensor the library zeroes itself"""
+    n = n * STATS_STRIDE
     t = arena.take(n) if arena is not None else None
     if t is not None:
         return t, STATS_PREZEROED
@@ -73,7 +76,11 @@ def _stats_buffer(arena, n, device):
 
 def _ws(arena, ncols, elem_bytes):
     """(ctypes pointer to an i3d_reduce_ws or None, keep-alive object)"""
-    ws = arena.take_ws(ncols, elem_bytes) if arena is not None else None
+    # measured on B200 (batch 512): the single-CTA second stage pulls ~1 MB of slots through one SM (~10 us) and costs
+    # more than the atomic tail it removes (bn_bwd_reduce 16.3 -> 26.3 us), so the workspace is opt-in (I3D_TWO_STAGE=1)
+    if arena is None or os.environ.get("I3D_TWO_STAGE", "0") != "1":
+        return None, None
+    ws = arena.take_ws(ncols, elem_bytes)
     return (ctypes.byref(ws) if ws is not None else None), ws
 
 
@@ -525,7 +532,7 @@ def transpose(x):
 def act_colstats(Y, act):
     py, ldy = _mat(Y, "Y")
     M, F = Y.shape
-    sums = torch.empty(2 * F, dtype=torch.float64, device=Y.device)
+    sums = torch.empty(2 * F * STATS_STRIDE, dtype=torch.float64, device=Y.device)
     _lib.check(_L().i3d_act_colstats(py, M, F, ldy, act, _p(sums), _s()), "i3d_act_colstats")
     return sums
 
@@ -549,6 +556,14 @@ def bn_apply(Y, act, sums, running_mean, running_var, nbt, gamma, beta, momentum
     return O, save
 
 
+DBIAS_STRIDE = 8       # bias-gradient accumulators: one float per 32-byte sector (see i3d_bn_bwd_apply_v)
+
+
+def dbias_buffer(F, device):
+    """accumulator for the bias gradient of an FC layer in the spread layout; zeroed by bn_bwd_reduce(zero=...)"""
+    return torch.empty(F * DBIAS_STRIDE, dtype=torch.float32, device=device)
+
+
 def bn_bwd_reduce(dO, Y, act, save, arena=None, zero=None, valid=None):
     """zero: optional fp32 tensor the kernel clears on the way (the dbias accumulator of the following bn_bwd_apply)"""
     pd, ldd = _mat(dO, "dO")
@@ -569,18 +584,22 @@ def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=Tr
     M, F = Y.shape
     dev = Y.device
     dY = torch.empty(M, F, dtype=torch.float32, device=dev)
+    db_stride = 1
     if not want_dbias:
         dbias = None
     elif dbias_zeroed is not None:
         dbias = dbias_zeroed                     # cleared by the preceding bn_bwd_reduce
+        db_stride = dbias.numel() // F           # DBIAS_STRIDE floats per column when it comes from dbias_buffer()
     else:
         dbias = torch.zeros(F, dtype=torch.float32, device=dev)
     dgamma = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_bn else None
     ws, keep = _ws(arena, F, 4) if dbias is not None else (None, None)
     _lib.check(_L().i3d_bn_bwd_apply_v(pd, ldd, py, ldy, M, F, act, 1 if has_bn else 0, 1 if training else 0,
-                                       _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), _p(dgamma), _p(dbeta),
-                                       _valid(valid), ws, _s()), "i3d_bn_bwd_apply")
+                                       _p(save), _p(gamma), _p(sums2), _p(dY), F, _p(dbias), db_stride, _p(dgamma),
+                                       _p(dbeta), _valid(valid), ws, _s()), "i3d_bn_bwd_apply")
+    if dbias is not None and db_stride > 1:
+        dbias = dbias.view(F, db_stride)[:, 0]   # strided view: FusedAdam's gradient pack reads it with its stride
     return dY, dbias, dgamma, dbeta
 
 
@@ -771,6 +790,6 @@ def add_i64(x, delta):
     _lib.check(_L().i3d_add_i64(_p(x), int(delta), _s()), "i3d_add_i64")
 
 
-def multi_copy(ptrs, off, length, flat, to_flat):
-    _lib.check(_L().i3d_multi_copy(_p(ptrs), _p(off), _p(length), ptrs.numel(), _p(flat), 1 if to_flat else 0, _s()),
-               "i3d_multi_copy")
+def multi_copy(ptrs, off, length, flat, to_flat, stride=None):
+    _lib.check(_L().i3d_multi_copy_strided(_p(ptrs), _p(off), _p(length), _p(stride), ptrs.numel(), _p(flat),
+                                           1 if to_flat else 0, _s()), "i3d_multi_copy")

@@ -78,7 +78,7 @@ SIGNATURES = {
     "i3d_act_colstats_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "i3d_bn_apply_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_bn_bwd_reduce_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
-    "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "i3d_gemm_backend": (_I, [_I]),
@@ -123,6 +123,7 @@ SIGNATURES = {
     "i3d_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _D, _L, _P, _P, _P]),
     "i3d_add_i64": (_I, [_P, _L, _P]),
     "i3d_multi_copy": (_I, [_P, _P, _P, _I, _P, _I, _P]),
+    "i3d_multi_copy_strided": (_I, [_P, _P, _P, _P, _I, _P, _I, _P]),
 }
 
 

@@ -159,10 +159,16 @@ class _FC(torch.autograd.Function):
         dgamma = dbeta = None
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
-            dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
+            dbz = K.dbias_buffer(Fout, W.device) if need_b else None
             sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
+            # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
+            # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
+            zero_db = need_b and cfg.training and cfg.act == 0
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
+                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            if zero_db:
+                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
         elif cfg.act != 0 or cfg.valid is not None:
             # (padded batches: the pass also writes the exact zeros of the padding rows)
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
@@ -297,10 +303,16 @@ class _FCPostMerged(torch.autograd.Function):
         dgamma = dbeta = None
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
-            dbz = torch.empty(Fout, dtype=torch.float32, device=W.device) if need_b else None
+            dbz = K.dbias_buffer(Fout, W.device) if need_b else None
             sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
+            # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
+            # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
+            zero_db = need_b and cfg.training and cfg.act == 0
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
+                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            if zero_db:
+                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
         elif cfg.act != 0 or cfg.valid is not None:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:
@@ -443,10 +455,16 @@ class _FCEdgeFactored(torch.autograd.Function):
         dgamma = dbeta = None
         arena = getattr(ctx.w_param, "_i3d_arena", None)
         if cfg.has_bn:
-            dbz = torch.empty(Fout, dtype=torch.float32, device=dev) if need_b else None
+            dbz = K.dbias_buffer(Fout, dev) if need_b else None
             sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2, need_b,
-                                                   dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
+            # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
+            # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
+            zero_db = need_b and cfg.training and cfg.act == 0
+            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
+                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            if zero_db:
+                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
         elif cfg.act != 0 or cfg.valid is not None:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:

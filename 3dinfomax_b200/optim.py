@@ -107,25 +107,42 @@ class FusedAdam:
             grads = [None if (d or p.grad is None or p.grad.data_ptr() == gbase + 4 * o) else p.grad
                      for p, d, o in zip(params, fl["direct"], fl["offs"])]
             self._needs_zero = self._needs_zero or any(fl["direct"])
+            def elem_stride(x):
+                """element stride of a gradient the pack kernel can read: contiguous (1) or a 1-D strided view (the
+                bias gradients of the FC layers live one per 32-byte sector, kernels.DBIAS_STRIDE)"""
+                if x.is_contiguous():
+                    return 1
+                if x.dim() == 1 and x.stride(0) > 0:
+                    return x.stride(0)
+                raise RuntimeError("gradients must be contiguous (or 1-D strided) fp32")
+
             key = tuple(0 if x is None else x.data_ptr() for x in grads)
             if key != fl["ptr_key"]:
                 for x in grads:
-                    if x is not None and (not x.is_contiguous() or x.dtype != torch.float32):
-                        raise RuntimeError("gradients must be contiguous fp32")
+                    if x is not None and x.dtype != torch.float32:
+                        raise RuntimeError("gradients must be fp32")
                 live = [i for i, x in enumerate(grads) if x is not None]
                 # one pinned table (pointers, offsets, lengths) + async copy: legal inside CUDA-graph capture (the
                 # graph re-reads the pinned host memory on replay, so it is kept alive)
                 host = torch.tensor([[key[i] for i in live], [fl["offs"][i] for i in live],
-                                     [fl["sizes"][i] for i in live]], dtype=torch.int64).reshape(3, len(live))
+                                     [fl["sizes"][i] for i in live], [elem_stride(grads[i]) for i in live]],
+                                    dtype=torch.int64).reshape(4, len(live))
                 if live:
                     host = host.pin_memory()
-                fl["ptrs_host"] = fl.get("ptrs_host", []) + [host]
-                table = torch.empty(3, len(live), dtype=torch.int64, device=fl["p"].device)
+                # a captured graph re-reads its pinned table on every replay, so tables created during a capture are
+                # kept for good; in eager mode the copy below is stream-ordered and the previous table is only kept
+                # until this one replaces it (no unbounded growth when gradient addresses change every step)
+                if torch.cuda.is_current_stream_capturing():
+                    fl.setdefault("ptrs_host_captured", []).append(host)
+                else:
+                    fl["ptrs_host_prev"] = fl.get("ptrs_host_eager")
+                    fl["ptrs_host_eager"] = host
+                table = torch.empty(4, len(live), dtype=torch.int64, device=fl["p"].device)
                 table.copy_(host, non_blocking=True)
-                fl["ptrs"], fl["poff"], fl["plen"] = table[0], table[1], table[2]
+                fl["ptrs"], fl["poff"], fl["plen"], fl["pstride"] = table[0], table[1], table[2], table[3]
                 fl["ptr_key"] = key
             if fl["ptrs"].numel():
-                K.multi_copy(fl["ptrs"], fl["poff"], fl["plen"], fl["g"], True)
+                K.multi_copy(fl["ptrs"], fl["poff"], fl["plen"], fl["g"], True, fl["pstride"])
             if self.process_group is not None:
                 torch.distributed.all_reduce(fl["g"], group=self.process_group)
             b1, b2 = g["betas"]

@@ -195,7 +195,13 @@ size_t i3d_gemm_ws_bytes(int mode, int64_t M, int N, int n_seg, const i3d_gemm_s
  * ~50 memset nodes per training step this way (each one also breaks programmatic dependent launch between its
  * neighbours). */
 #define I3D_STATS_PREZEROED 0x100
-/* col_stats (optional, NT without accumulate): fp64 [2N] = column sums of act(C) and act(C)^2, i.e. the train-mode
+/* Layout of every fp64 column-statistics buffer of this library (col_stats, sums, sums2): statistic j of column c lives
+ * at element (j * F + c) * I3D_STATS_STRIDE, i.e. one accumulator per 128-byte line; a buffer for F columns holds
+ * 2 * F * I3D_STATS_STRIDE doubles.  Hundreds of CTAs add their partial sums into these with atomics; with 4 doubles
+ * per 32-byte sector the L2 serialised them (measured on B200, 296 CTAs x 400 columns: 27.5 us packed -> 16.3 us
+ * spread for the same kernel). */
+#define I3D_STATS_STRIDE 16
+/* col_stats (optional, NT without accumulate): fp64 [2N * I3D_STATS_STRIDE] = column sums of act(C) and act(C)^2, i.e. the train-mode
  * BatchNorm statistics of the FCLayer tail, produced by the GEMM epilogue instead of a separate pass over C. */
 int i3d_gemm_ex(int mode, int64_t M, int N, int n_seg, const i3d_gemm_seg* segs, float* C, int ldc,
                 const float* bias, int accumulate, void* ws, size_t ws_bytes, double* col_stats, int stats_act,
@@ -272,7 +278,7 @@ int i3d_posttrans_unmerge(const float* dWb, int n_buckets, int Fout, int F, floa
  * FCLayer tail: activation -> BatchNorm1d (train: batch statistics)  [models/base_layers.py:102-110]
  *   h = act(Y);  O = gamma*(h-mean)*rstd + beta (+ residual)
  * ---------------------------------------------------------------------------------------------- */
-/* sums[0:F]=sum_rows act(Y), sums[F:2F]=sum_rows act(Y)^2 (fp64; zeroed inside) */
+/* sums[(0:F) * S]=sum_rows act(Y), sums[(F:2F) * S]=sum_rows act(Y)^2, S = I3D_STATS_STRIDE (fp64; zeroed inside) */
 int i3d_act_colstats(const float* Y, int64_t M, int F, int ldy, int act, double* sums, void* stream);
 /* training!=0: statistics from `sums` (biased var for normalisation), running stats updated with
  * `momentum` (unbiased var), *num_batches_tracked += 1;  else running stats are used.
@@ -281,7 +287,7 @@ int i3d_bn_apply(const float* Y, int64_t M, int F, int ldy, int act, const doubl
                  float* running_var, int64_t* num_batches_tracked, const float* gamma, const float* beta,
                  float momentum, float eps, int training, float* save_mean_rstd, const float* residual,
                  float* O, int ldo, void* stream);
-/* sums2[0:F]=sum dO, sums2[F:2F]=sum dO*xhat (fp64; zeroed inside) */
+/* sums2[(0:F) * S]=sum dO, sums2[(F:2F) * S]=sum dO*xhat, S = I3D_STATS_STRIDE (fp64; zeroed inside) */
 int i3d_bn_bwd_reduce(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                       const float* save_mean_rstd, double* sums2, void* stream);
 /* same; additionally sets zero_buf[0:zero_n] = 0 (fp32) — the bias-gradient accumulator the following
@@ -315,10 +321,11 @@ int i3d_bn_apply_v(const float* Y, int64_t M, int F, int ldy, int act, const dou
 int i3d_bn_bwd_reduce_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act,
                         const float* save_mean_rstd, double* sums2, float* zero_buf, int zero_n,
                         const int32_t* m_valid, const i3d_reduce_ws* rws, void* stream);
-/* with rws, dbias is STORED (not accumulated) */
+/* dbias_stride: element stride of dbias (column c accumulates into dbias[c * dbias_stride]); 8 puts every accumulator in
+ * its own 32-byte sector, which the L2 needs to run the ~300 CTAs' atomics in parallel.  With rws, dbias is STORED. */
 int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int has_bn,
                        int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
-                       int lddy, float* dbias, float* dgamma, float* dbeta, const int32_t* m_valid,
+                       int lddy, float* dbias, int dbias_stride, float* dgamma, float* dbeta, const int32_t* m_valid,
                        const i3d_reduce_ws* rws, void* stream);
 /* Factored first layer of the edge MLP [models/pna.py:237-252]: cat[h[src], h[dst], e] W^T =
  * (h W_s^T)[src] + (h W_d^T)[dst] + e W_e^T.  P [N, >=2F] = h [W_s; W_d]^T comes from ONE node-level GEMM; the bond
@@ -441,6 +448,9 @@ int i3d_add_i64(int64_t* x, int64_t delta, void* stream);
 /* flat[off[t] : off[t]+len[t]] = src_t (to_flat!=0) or the reverse.  ptrs/off/len: DEVICE arrays of T entries */
 int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len, int T, float* flat, int to_flat,
                    void* stream);
+/* same with a per-tensor element stride on the tensor side (stride[t] >= 1; NULL = all 1): strided bias gradients */
+int i3d_multi_copy_strided(const uint64_t* ptrs, const int64_t* off, const int64_t* len, const int64_t* stride, int T,
+                           float* flat, int to_flat, void* stream);
 
 #ifdef __cplusplus
 }

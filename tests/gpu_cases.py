@@ -829,6 +829,21 @@ def case_contrastive_metrics():
     # the two threshold-free metrics share one fused evaluation, the three thresholded ones another (6 launches each:
     # 2 row norms, weight split, GEMM, row pass, final reduction) — instead of five separate [B,B] einsum chains
     out.append(("metrics/five_metrics_two_evaluations(launches<=12)", float(max(0, launches - 12)), 0))
+    # a NEW batch of embeddings at the SAME address (what the caching allocator hands the trainer for the next batch's
+    # predictions) must not be served the previous batch's cached metrics
+    m = i3d.PositiveSimilarity()
+    ya, yb = embeddings(10, 256, 64, 0)
+    ta, tb = ya.to(DEV), yb.to(DEV)
+    first = float(m(ta, tb))
+    pa, pb = ta.data_ptr(), tb.data_ptr()
+    del ta, tb
+    za, zb = embeddings(11, 256, 64, 0)
+    ua, ub = za.to(DEV), zb.to(DEV)
+    same_addr = ua.data_ptr() == pa and ub.data_ptr() == pb
+    second = float(m(ua, ub))
+    want = float(O.contrastive_metrics(za, zb, 0.5)[0])
+    out.append(("metrics/next_batch_at_the_same_address_is_recomputed(same address: %s)" % same_addr, abs(second - want), 1e-5))
+    out.append(("metrics/and_differs_from_the_previous_batch", float(abs(first - second) < 1e-7), 0))
     return out
 
 

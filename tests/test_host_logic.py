@@ -138,10 +138,12 @@ def test_stats_arena_bump_allocator():
     s1.fill_(3.0)
     a.reset()
     assert a.used == 0 and float(a.buf.abs().sum()) == 0.0
-    buf, flag = K._stats_buffer(a, 400, "cpu")
-    assert flag == K.STATS_PREZEROED and buf.data_ptr() == a.buf.data_ptr()
-    buf2, flag2 = K._stats_buffer(None, 400, "cpu")
-    assert flag2 == 0 and buf2.numel() == 400
+    # statistics buffers use the library's strided layout: one accumulator per 128-byte line (I3D_STATS_STRIDE doubles)
+    buf, flag = K._stats_buffer(a, 40, "cpu")
+    assert flag == K.STATS_PREZEROED and buf.data_ptr() == a.buf.data_ptr() and buf.numel() == 40 * K.STATS_STRIDE
+    buf2, flag2 = K._stats_buffer(None, 40, "cpu")
+    assert flag2 == 0 and buf2.numel() == 40 * K.STATS_STRIDE
+    assert K.StatsArena("cpu").take_ws(400, 8) is None      # no reduction scratch off the GPU
 
 
 def test_graph_batch_carries_the_degree_hint():
