@@ -80,11 +80,11 @@ class FCLayer(nn.Module):
         b = self.batch_norm
         return (b.weight, b.bias, b.running_mean, b.running_var, b.num_batches_tracked, b.momentum, b.eps)
 
-    def forward_edge_factored(self, g, h, table, valid=None):
+    def forward_edge_factored(self, g, h, table, valid=None, combo=None):
         """This layer applied to cat[h[src], h[dst], e] in factored form (ops._FCEdgeFactored); ``table``: this layer's
         bond-feature table from ops.bond_tables."""
         return ops.fc_edge_factored(g, h, table, self.linear.weight, self.linear.bias, self.act, self._bn_tuple(),
-                                    self.training, valid)
+                                    self.training, valid, combo)
 
     def forward_merged(self, plan, h, agg, residual=None, valid=None):
         """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""

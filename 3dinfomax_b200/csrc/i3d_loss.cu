@@ -168,6 +168,77 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data-parallel optimizer step as ONE kernel over NVLink/NVSwitch multicast memory: gradient all-reduce + Adam +
+// parameter broadcast (replaces NCCL all-reduce(s) followed by the Adam kernel; trainer/trainer.py:119-123 under DDP).
+// The flat buffers [p | g | m | v] (n floats each) of every rank live in ONE symmetric allocation bound to a multicast
+// address.  Rank r owns the slice [r*per, (r+1)*per) of the elements:
+//   g_sum  = multimem.ld_reduce.add  over the slice of g     (the switch adds the 8 ranks' values: 1/8 of the buffer
+//                                                             crosses this GPU's links instead of 2x the whole buffer)
+//   Adam on the slice with the local copies of p, m, v       (replicas are identical)
+//   multimem.st of the new p, m, v                           (the switch writes them into every rank's buffers)
+// Cross-rank ordering (gradients complete before, stores landed after) is the caller's: a signal-pad barrier on the
+// stream before and after this kernel (FusedAdam.step).  fp32 throughout; the sum order is the switch's.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+    adam_nvls_kernel(float* __restrict__ mc, float* __restrict__ local, int64_t n, int rank, int world, AdamHyper h,
+                     int64_t step, const double* __restrict__ hyper_dev, const int64_t* __restrict__ step_dev) {
+  pdl_grid_sync();
+  __shared__ float sc[7];
+  if (threadIdx.x == 0) {
+    if (hyper_dev) {
+      h.lr = hyper_dev[0], h.beta1 = hyper_dev[1], h.beta2 = hyper_dev[2];
+      h.eps = hyper_dev[3], h.weight_decay = hyper_dev[4], h.grad_scale = hyper_dev[5];
+    }
+    if (step_dev) step = step_dev[0];
+    const double bc1 = 1.0 - pow(h.beta1, (double)step);
+    const double bc2 = 1.0 - pow(h.beta2, (double)step);
+    sc[0] = (float)(h.lr / bc1), sc[1] = (float)sqrt(bc2), sc[2] = (float)h.beta1, sc[3] = (float)h.beta2;
+    sc[4] = (float)h.eps, sc[5] = (float)h.weight_decay, sc[6] = (float)h.grad_scale;
+  }
+  __syncthreads();
+  const float step_size = sc[0], bc2_sqrt = sc[1], beta1 = sc[2], beta2 = sc[3], eps = sc[4], wd = sc[5], gs = sc[6];
+  const int64_t q = n >> 2;                                   // float4 elements per array (n is a multiple of 4)
+  const int64_t per = (q + world - 1) / world;
+  const int64_t lo = (int64_t)rank * per, hi = lo + per < q ? lo + per : q;
+  const float4* p4 = reinterpret_cast<const float4*>(local);
+  const float4* m4 = reinterpret_cast<const float4*>(local + 2 * n);
+  const float4* v4 = reinterpret_cast<const float4*>(local + 3 * n);
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gsum = multimem_ld_reduce_add(mc + n + 4 * i);
+    const float4 pv = p4[i], mv = m4[i], vv = v4[i];
+    const float g[4] = {gsum.x, gsum.y, gsum.z, gsum.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w};
+    const float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vvv[4] = {vv.x, vv.y, vv.z, vv.w};
+    float po[4], mo[4], vo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gi = g[j] * gs;
+      if (wd != 0.f) gi = fmaf(wd, pp[j], gi);
+      mo[j] = mm[j] + (1.f - beta1) * (gi - mm[j]);
+      vo[j] = vvv[j] * beta2 + (1.f - beta2) * gi * gi;
+      const float denom = sqrtf(vo[j]) / bc2_sqrt + eps;
+      po[j] = pp[j] - step_size * (mo[j] / denom);
+    }
+    multimem_st(mc + 4 * i, make_float4(po[0], po[1], po[2], po[3]));
+    multimem_st(mc + 2 * n + 4 * i, make_float4(mo[0], mo[1], mo[2], mo[3]));
+    multimem_st(mc + 3 * n + 4 * i, make_float4(vo[0], vo[1], vo[2], vo[3]));
+  }
+}
+
 __global__ void add_i64_kernel(int64_t* x, int64_t d) {
   pdl_grid_sync(); x[0] += d; }
 
@@ -325,6 +396,22 @@ int i3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, doubl
   if (n == 0) return I3D_OK;
   AdamHyper h{lr, beta1, beta2, eps, weight_decay, grad_scale};
   launch(adam_kernel, grid_for(n, 256), 256, 0, as_stream(stream), p, g, m, v, n, h, step, hyper_dev, step_dev);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_adam_step_nvls(float* mc_base, float* local_base, int64_t n, int rank, int world, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, double grad_scale, int64_t step,
+                       const double* hyper_dev, const int64_t* step_dev, void* stream) {
+  I3D_REQUIRE(n >= 0 && (n & 3) == 0 && world >= 1 && rank >= 0 && rank < world && (step_dev || step >= 1) &&
+                  (n == 0 || (mc_base && local_base)) && (reinterpret_cast<uintptr_t>(mc_base) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(local_base) & 15u) == 0,
+              "invalid argument");
+  if (n == 0) return I3D_OK;
+  AdamHyper h{lr, beta1, beta2, eps, weight_decay, grad_scale};
+  const int64_t per = ((n >> 2) + world - 1) / world;
+  launch(adam_nvls_kernel, grid_for(per, 256, 4), 256, 0, as_stream(stream), mc_base, local_base, n, rank, world, h, step,
+         hyper_dev, step_dev);
   I3D_LAUNCHED();
   return I3D_OK;
 }

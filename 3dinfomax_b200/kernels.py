@@ -786,6 +786,15 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
                                   _p(step_dev), _s()), "i3d_adam_step")
 
 
+def adam_step_nvls(mc_ptr, local, n, rank, world, lr, beta1, beta2, eps, weight_decay, grad_scale, step, hyper_dev=None,
+                   step_dev=None):
+    """fused all-reduce + Adam + broadcast over multicast memory (i3d_adam_step_nvls); ``local``: the [4n] symmetric
+    tensor [p | g | m | v], ``mc_ptr``: its multicast address"""
+    _lib.check(_L().i3d_adam_step_nvls(int(mc_ptr), _p(local), int(n), int(rank), int(world), float(lr), float(beta1),
+                                       float(beta2), float(eps), float(weight_decay), float(grad_scale), int(step),
+                                       _p(hyper_dev), _p(step_dev), _s()), "i3d_adam_step_nvls")
+
+
 def add_i64(x, delta):
     _lib.check(_L().i3d_add_i64(_p(x), int(delta), _s()), "i3d_add_i64")
 

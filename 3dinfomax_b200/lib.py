@@ -121,6 +121,7 @@ SIGNATURES = {
     "i3d_ntxent_rows_bwd": (_I, [_P, _L, _L, _I, _P, _P, _I, _F, _F, _L, _P, _P, _F, _P, _P, _P]),
     "i3d_norm_bwd_accum": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "i3d_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _D, _L, _P, _P, _P]),
+    "i3d_adam_step_nvls": (_I, [_P, _P, _L, _I, _I, _D, _D, _D, _D, _D, _D, _L, _P, _P, _P]),
     "i3d_add_i64": (_I, [_P, _L, _P]),
     "i3d_multi_copy": (_I, [_P, _P, _P, _I, _P, _I, _P]),
     "i3d_multi_copy_strided": (_I, [_P, _P, _P, _P, _I, _P, _I, _P]),

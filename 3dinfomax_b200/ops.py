@@ -63,6 +63,21 @@ def _dw_fork(device, main, used):
     return side
 
 
+def _grad_ready(param, stream):
+    """tell the optimizer that ``param``'s weight-gradient kernels have been issued on ``stream`` (FusedAdam overlaps the
+    data-parallel all-reduce of a layer's gradients with the backward of the layers below it)"""
+    opt = getattr(param, "_i3d_optim", None)
+    if opt is not None and opt.process_group is not None:
+        dev = param.device
+        streams = [torch.cuda.current_stream(dev)]
+        side = _dw_streams.get(dev.index)          # earlier weights of the group may have gone to the side stream
+        if side is not None:
+            streams.append(side)
+        if stream is not None and stream not in streams:
+            streams.append(stream)
+        opt.notify_grad_ready(param, streams)
+
+
 class Seg:
     """One K-segment of an FC input.
 
@@ -209,6 +224,8 @@ class _FC(torch.autograd.Function):
                                acc[:, off:off + k], accumulate=True)
                     off += k
             dW = None if direct is not None else acc
+            if direct is not None:
+                _grad_ready(ctx.w_param, side)
         # input gradients, one NN GEMM per distinct input tensor (segments sharing a tensor are K-segments of it)
         dxs = [None] * len(xs)
         groups = {}
@@ -331,6 +348,8 @@ class _FCPostMerged(torch.autograd.Function):
                 K.gemm_tn_chunked(plan, dY, agg, dWb)
                 K.posttrans_unmerge(dWb, acc, F)
             dW = None if direct is not None else acc
+            if direct is not None:
+                _grad_ready(ctx.w_param, side)
         dh = dagg = None
         if ctx.needs_input_grad[8] or ctx.needs_input_grad[9]:
             # d[h | agg] = dY Wm_D, rows scattered back to node order by the epilogue
@@ -372,10 +391,10 @@ class _BondTables(torch.autograd.Function):
     (``combo`` [n_codes, F] = their embeddings).  One launch for all layers, forward and backward (i3d_bond.cu)."""
 
     @staticmethod
-    def forward(ctx, col0, combo, *Ws):
+    def forward(ctx, col0, weight_grads, combo, *Ws):
         combo = combo.contiguous()
         Ts = K.bond_tables_fwd(combo, list(Ws), col0)
-        ctx.col0 = col0
+        ctx.col0, ctx.weight_grads = col0, weight_grads
         ctx.w_params = Ws
         ctx.save_for_backward(combo, *Ws)
         return tuple(Ts)
@@ -387,16 +406,17 @@ class _BondTables(torch.autograd.Function):
         dTs = [None if d is None else d.contiguous() for d in dTs]
         # FC weights owned by FusedAdam accumulate straight into their slice of the flat gradient buffer
         direct = [getattr(w, "_i3d_grad_view", None) for w in ctx.w_params]
-        need = ctx.needs_input_grad[2:]
-        accs = [d if d is not None else (torch.zeros_like(w) if n else None) for d, w, n in zip(direct, Ws, need)]
-        dcombo = K.bond_tables_bwd(combo, Ws, ctx.col0, dTs, accs, want_dcombo=ctx.needs_input_grad[1])
+        need = [n and ctx.weight_grads for n in ctx.needs_input_grad[3:]]
+        accs = [d if (d is not None and n) else (torch.zeros_like(w) if n else None) for d, w, n in zip(direct, Ws, need)]
+        dcombo = K.bond_tables_bwd(combo, Ws, ctx.col0, dTs, accs, want_dcombo=ctx.needs_input_grad[2])
         grads = [None if (d is not None or not n) else a for d, a, n in zip(direct, accs, need)]
-        return (None, dcombo) + tuple(grads)
+        return (None, None, dcombo) + tuple(grads)
 
 
-def bond_tables(combo, weights, col0):
-    """list of per-layer tables T_l [n_codes, Fout] (see _BondTables)"""
-    return list(_BondTables.apply(int(col0), combo, *weights))
+def bond_tables(combo, weights, col0, weight_grads=True):
+    """list of per-layer tables T_l [n_codes, Fout] (see _BondTables).  weight_grads=False: the W_e columns of the
+    weight gradients are accumulated by the layers themselves (fc_edge_factored(..., combo=combo))."""
+    return list(_BondTables.apply(int(col0), bool(weight_grads), combo, *weights))
 
 
 class _FCEdgeFactored(torch.autograd.Function):
@@ -409,7 +429,7 @@ class _FCEdgeFactored(torch.autograd.Function):
     covers the W_s, W_d columns; the W_e columns get theirs from _BondTables.backward."""
 
     @staticmethod
-    def forward(ctx, cfg, g, W, b, gamma, beta, h, T):
+    def forward(ctx, cfg, g, W, b, gamma, beta, h, T, combo):
         N, F = h.shape
         Fout = W.shape[0]
         M = g.src_csr.numel()
@@ -439,13 +459,13 @@ class _FCEdgeFactored(torch.autograd.Function):
         else:
             O = K.act_fwd(Y, cfg.act) if cfg.act != 0 else Y
         ctx.cfg, ctx.g, ctx.w_param = cfg, g, W
-        ctx.save_for_backward(W, Y, save, gamma, h)
+        ctx.save_for_backward(W, Y, save, gamma, h, combo)
         return O
 
     @staticmethod
     def backward(ctx, dO):
         cfg, g = ctx.cfg, ctx.g
-        W, Y, save, gamma, h = ctx.saved_tensors
+        W, Y, save, gamma, h, combo = ctx.saved_tensors
         N, F = h.shape
         Fout = W.shape[0]
         dev = W.device
@@ -481,11 +501,17 @@ class _FCEdgeFactored(torch.autograd.Function):
             acc = direct if direct is not None else torch.zeros_like(W)
             side = None
             if direct is not None and N >= _dw_min_rows() and Fout >= 64:
-                side = _dw_fork(dev, torch.cuda.current_stream(dev), [Rs, Rd, h])
+                side = _dw_fork(dev, torch.cuda.current_stream(dev), [Rs, Rd, h, dT, combo])
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 K.gemm(K.TN, Fout, F, [{"A": Rs, "B": h, "K": N}], acc[:, :F], accumulate=True)
                 K.gemm(K.TN, Fout, F, [{"A": Rd, "B": h, "K": N}], acc[:, F:2 * F], accumulate=True)
+                if dT is not None and combo is not None:
+                    # the W_e columns: dT^T combo.  Done here, per layer, so that the layer's whole weight gradient is
+                    # final when this backward returns (the data-parallel all-reduce of the layer starts right away)
+                    K.bond_tables_bwd(combo, [W], 2 * F, [dT], [acc], want_dcombo=False)
             dW = None if direct is not None else acc
+            if direct is not None:
+                _grad_ready(ctx.w_param, side)
         dh = None
         if ctx.needs_input_grad[6]:
             dh = torch.empty(N, F, dtype=torch.float32, device=dev)
@@ -503,19 +529,21 @@ class _FCEdgeFactored(torch.autograd.Function):
                 else:
                     nn[0]["B"], nn[1]["B"] = W[:, :F], W[:, F:2 * F]
             K.gemm(K.NT if via_nt else K.NN, N, F, nn, dh, prepared=ready)
-        return None, None, dW, db, dgamma, dbeta, dh, dT
+        return None, None, dW, db, dgamma, dbeta, dh, dT, None
 
 
-def fc_edge_factored(g, h, T, W, b, act, bn=None, training=True, valid=None):
+def fc_edge_factored(g, h, T, W, b, act, bn=None, training=True, valid=None, combo=None):
     """FCLayer over cat[h[src], h[dst], e] in factored form (``g``: EdgeCodes, ``T``: the layer's table from
-    ``bond_tables``); other arguments as ``fc``."""
+    ``bond_tables``); other arguments as ``fc``.  ``combo``: the combination embeddings the tables were built from —
+    when given, this layer's backward also accumulates the W_e columns of the weight gradient (dT^T combo) and
+    ``bond_tables`` must be called with ``weight_grads=False``."""
     if bn is None:
         cfg = FCConfig(None, act, False, training, valid=valid)
         gamma = beta = None
     else:
         gamma, beta, rm, rv, nbt, mom, eps = bn
         cfg = FCConfig(None, act, True, training, rm, rv, nbt, mom, eps, valid=valid)
-    return _FCEdgeFactored.apply(cfg, g, W, b, gamma, beta, h, T)
+    return _FCEdgeFactored.apply(cfg, g, W, b, gamma, beta, h, T, None if combo is None else combo.detach())
 
 
 class _EmbedSum(torch.autograd.Function):

@@ -14,6 +14,8 @@ memset per group and must be called between steps (the reference loop does, trai
 ``param_groups`` keeps torch's layout (list of dicts with 'params', 'lr', 'betas', 'eps', 'weight_decay'), so the
 reference's ``WarmUpWrapper`` (trainer/lr_schedulers.py), which rewrites ``group['lr']`` every step, drives it as is.
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -30,12 +32,18 @@ class FusedAdam:
         self.process_group = process_group
         self.graph_safe = graph_safe
         self._flat = []
+        # data parallel on NVSwitch: the flat buffers live in symmetric (multicast) memory and the step is ONE kernel that
+        # reduces the gradients through the switch, applies Adam to this rank's slice and multicast-stores the result
+        # (i3d_adam_step_nvls); I3D_NVLS_ADAM=0 or no multicast support -> NCCL all-reduce + the local Adam kernel
+        self.nvls = process_group is not None and os.environ.get("I3D_NVLS_ADAM", "1") != "0"
         for g in groups:
             pg = dict(self.defaults)
             pg.update(g)
             pg["params"] = [p for p in pg["params"]]
             self.param_groups.append(pg)
-            self._flat.append(self._flatten(pg["params"]))
+            self._flat.append(self._flatten(pg["params"], process_group if self.nvls else None))
+        if self.nvls and not all(fl is None or fl.get("mc") for fl in self._flat):
+            self.nvls = False
         self._step = 0
         self._needs_zero = False
         self.post_step_hooks = []          # e.g. WeightPrep.invalidate: the Adam kernel bypasses tensor versions
@@ -44,6 +52,12 @@ class FusedAdam:
         self._hyper_dev = [torch.zeros(6, dtype=torch.float64, device=dev) for _ in self.param_groups] \
             if graph_safe else None
         self._hyper_host = [None] * len(self.param_groups)
+        # gradient all-reduce overlapped with backward (data parallel): see set_overlap_groups
+        self._overlap = []            # [(flat index, start, end, [params])]
+        self._overlap_of = {}         # id(param) -> overlap group index
+        self._pending = {}            # overlap group index -> ids of the params whose gradient is not final yet
+        self._reduced = []            # [(flat index, start, end)] ranges already all-reduced in this step
+        self._comm_stream = None
 
     def _device(self):
         for g in self.param_groups:
@@ -52,25 +66,47 @@ class FusedAdam:
         return torch.device("cuda")
 
     @staticmethod
-    def _flatten(params):
+    def _symmetric(n, dev, group):
+        """[4n] fp32 in symmetric memory bound to a multicast address, or (None, None, None) when unavailable"""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(4 * n, dtype=torch.float32, device=dev)
+            h = symm.rendezvous(t, group)
+            if not h.has_multicast_support or not h.multicast_ptr:
+                return None, None, None
+            t.zero_()
+            return t, h, int(h.multicast_ptr)
+        except Exception:                     # no symmetric-memory support in this build / topology: NCCL path
+            return None, None, None
+
+    @staticmethod
+    def _flatten(params, symm_group=None):
         if not params:
             return None
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FusedAdam needs CUDA parameters: the 3dinfomax_b200 path has no CPU fallback")
         sizes = [p.numel() for p in params]
-        offs, acc = [], 0
-        for n in sizes:
-            offs.append(acc)
-            acc += (n + 3) // 4 * 4          # keep every view 16-byte aligned for the vectorised kernels
-        flat = torch.zeros(acc, dtype=torch.float32, device=dev)
+        # flat layout: the directly-accumulated FC weights first (in parameter order, so the weights of one message-
+        # passing layer are ONE contiguous range that can be all-reduced as soon as that layer's backward is done), the
+        # packed small tensors (biases, BatchNorm, embeddings) behind them.  Offsets are kept per parameter index.
+        order = [i for i, p in enumerate(params) if getattr(p, "_i3d_direct_grad", False)] + \
+                [i for i, p in enumerate(params) if not getattr(p, "_i3d_direct_grad", False)]
+        offs, acc = [0] * len(params), 0
+        for i in order:
+            offs[i] = acc
+            acc += (sizes[i] + 3) // 4 * 4   # keep every view 16-byte aligned for the vectorised kernels
+        sym, handle, mc = (None, None, None)
+        if symm_group is not None:
+            sym, handle, mc = FusedAdam._symmetric(acc, dev, symm_group)
+        flat = torch.zeros(acc, dtype=torch.float32, device=dev) if sym is None else sym[:acc]
         with torch.no_grad():
             for p, o, n in zip(params, offs, sizes):
                 if p.dtype != torch.float32:
                     raise TypeError("fp32 parameters only")
                 flat[o:o + n].copy_(p.data.reshape(-1))
                 p.data = flat[o:o + n].view(p.shape)
-        gflat = torch.zeros_like(flat)
+        gflat = torch.zeros_like(flat) if sym is None else sym[acc:2 * acc]
         direct = []
         for p, o, n in zip(params, offs, sizes):
             d = bool(getattr(p, "_i3d_direct_grad", False))
@@ -78,7 +114,9 @@ class FusedAdam:
             if d:
                 p._i3d_grad_view = gflat[o:o + n].view(p.shape)
                 p.grad = p._i3d_grad_view
-        return {"p": flat, "g": gflat, "m": torch.zeros_like(flat), "v": torch.zeros_like(flat), "direct": direct,
+        mflat = torch.zeros_like(flat) if sym is None else sym[2 * acc:3 * acc]
+        vflat = torch.zeros_like(flat) if sym is None else sym[3 * acc:4 * acc]
+        return {"p": flat, "g": gflat, "m": mflat, "v": vflat, "direct": direct, "sym": sym, "handle": handle, "mc": mc,
                 "off": torch.tensor(offs, dtype=torch.int64, device=dev),
                 "len": torch.tensor(sizes, dtype=torch.int64, device=dev), "offs": offs, "sizes": sizes,
                 "ptr_key": None, "ptrs": None}
@@ -90,15 +128,100 @@ class FusedAdam:
                 raise RuntimeError("a parameter was re-allocated after FusedAdam was built (e.g. module.to()); "
                                    "rebuild the optimizer")
 
+    # --- overlapping the gradient all-reduce with backward ------------------------------------------------------
+    def set_overlap_groups(self, groups):
+        """``groups``: lists of directly-accumulated FC weights (one list per message-passing layer).  When every weight
+        of a group has reported its gradient final (``notify_grad_ready``, called by the backward operators right
+        after they issue the weight-gradient GEMMs), the group's contiguous range of the flat gradient buffer is
+        all-reduced on a communication stream, while backward goes on with the layers below.  ``step()`` joins that
+        stream and all-reduces whatever was not covered.  No-op without a process group."""
+        self._overlap, self._overlap_of = [], {}
+        if self.process_group is None or self.nvls or os.environ.get("I3D_AR_OVERLAP", "1") == "0":
+            return                           # (the fused NVLS step reduces inside the optimizer kernel)
+        for params in groups:
+            where = {}
+            for fi, (g, fl) in enumerate(zip(self.param_groups, self._flat)):
+                if fl is None:
+                    continue
+                for k, p in enumerate(g["params"]):
+                    where[id(p)] = (fi, fl["offs"][k], fl["offs"][k] + (fl["sizes"][k] + 3) // 4 * 4, fl["direct"][k])
+            locs = [where.get(id(p)) for p in params]
+            if not locs or any(l is None or not l[3] or l[0] != locs[0][0] for l in locs):
+                continue                                           # not all direct / not in one flat buffer
+            locs.sort(key=lambda l: l[1])
+            if any(a[2] != b[1] for a, b in zip(locs, locs[1:])):
+                continue                                           # not contiguous
+            gi = len(self._overlap)
+            self._overlap.append((locs[0][0], locs[0][1], locs[-1][2], list(params)))
+            for p in params:
+                self._overlap_of[id(p)] = gi
+        self._reset_pending()
+
+    def _reset_pending(self):
+        self._pending = {gi: {id(p) for p in grp[3]} for gi, grp in enumerate(self._overlap)}
+        self._reduced = []
+
+    def notify_grad_ready(self, param, streams=None):
+        """The weight-gradient kernels of ``param`` have been issued on ``streams`` (default: the current stream)."""
+        gi = self._overlap_of.get(id(param))
+        if gi is None:
+            return
+        pend = self._pending.get(gi)
+        if not pend:
+            return
+        pend.discard(id(param))
+        if pend:
+            return
+        fi, s, e, _ = self._overlap[gi]
+        fl = self._flat[fi]
+        dev = fl["g"].device
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        comm = self._comm_stream
+        for st in (streams or [torch.cuda.current_stream(dev)]):
+            comm.wait_stream(st)
+        with torch.cuda.stream(comm):
+            if os.environ.get("I3D_EXP_SKIP_AR", "0") != "1":        # (timing experiment only: wrong results)
+                torch.distributed.all_reduce(fl["g"][s:e], group=self.process_group)
+        self._reduced.append((fi, s, e))
+
+    def _allreduce_rest(self, fi, fl):
+        """all-reduce the parts of flat gradient buffer ``fi`` that no overlap group has covered"""
+        done = sorted((s, e) for f, s, e in self._reduced if f == fi)
+        pos, n = 0, fl["g"].numel()
+        for s, e in done + [(n, n)]:
+            if s > pos and os.environ.get("I3D_EXP_SKIP_AR", "0") != "1":
+                torch.distributed.all_reduce(fl["g"][pos:s], group=self.process_group)
+            pos = max(pos, e)
+
     @torch.no_grad()
     def step(self, grad_scale=1.0):
         if self._needs_zero:
             raise RuntimeError("FusedAdam: call optimizer.zero_grad() between steps — FC weight gradients accumulate "
                                "in place in the flat buffer (module.zero_grad() does not clear it)")
         self._step += 1
+        if self.nvls:
+            # pack every group's small gradients first, then ONE cross-rank barrier, the fused kernels, ONE barrier
+            for gi, (g, fl) in enumerate(zip(self.param_groups, self._flat)):
+                if fl is not None:
+                    self._pack(g, fl)
+            first = next(fl for fl in self._flat if fl is not None)
+            first["handle"].barrier()
         for gi, (g, fl) in enumerate(zip(self.param_groups, self._flat)):
             if fl is None:
                 continue
+            if not self.nvls:
+                self._pack(g, fl)
+            self._finish_group(gi, g, fl, grad_scale)
+        if self.nvls:
+            first["handle"].barrier()
+        if self.graph_safe:
+            K.add_i64(self._step_dev, 1)
+        for hook in self.post_step_hooks:
+            hook()
+
+    def _pack(self, g, fl):
+        if True:
             params = g["params"]
             self._check_views(params, fl)
             # directly-accumulated weights already live in fl["g"]; parameters that took no part in the step keep
@@ -143,9 +266,31 @@ class FusedAdam:
                 fl["ptr_key"] = key
             if fl["ptrs"].numel():
                 K.multi_copy(fl["ptrs"], fl["poff"], fl["plen"], fl["g"], True, fl["pstride"])
-            if self.process_group is not None:
-                torch.distributed.all_reduce(fl["g"], group=self.process_group)
+
+    def _finish_group(self, gi, g, fl, grad_scale):
+        if True:
             b1, b2 = g["betas"]
+            if self.nvls:
+                # one kernel: switch-side gradient reduction + Adam on this rank's slice + multicast store of p, m, v.
+                # The signal-pad barriers order the ranks: every gradient written before (taken once, after the LAST
+                # group's pack, see below), every store landed after.
+                rank = torch.distributed.get_rank(self.process_group)
+                world = torch.distributed.get_world_size(self.process_group)
+                if self.graph_safe:
+                    hyper = (float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                             float(grad_scale))
+                    if hyper != self._hyper_host[gi]:
+                        self._upload_hyper(gi, hyper)
+                    K.adam_step_nvls(fl["mc"], fl["sym"], fl["p"].numel(), rank, world, 0, b1, b2, g["eps"],
+                                     g["weight_decay"], grad_scale, 1, self._hyper_dev[gi], self._step_dev)
+                else:
+                    K.adam_step_nvls(fl["mc"], fl["sym"], fl["p"].numel(), rank, world, g["lr"], b1, b2, g["eps"],
+                                     g["weight_decay"], grad_scale, self._step)
+                return
+            if self.process_group is not None:
+                if self._reduced and self._comm_stream is not None:
+                    torch.cuda.current_stream(fl["g"].device).wait_stream(self._comm_stream)    # early layer all-reduces
+                self._allreduce_rest(gi, fl)
             if self.graph_safe:
                 hyper = (float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
                          float(grad_scale))
@@ -156,10 +301,6 @@ class FusedAdam:
             else:
                 K.adam_step(fl["p"], fl["g"], fl["m"], fl["v"], g["lr"], b1, b2, g["eps"], g["weight_decay"],
                             grad_scale, self._step)
-        if self.graph_safe:
-            K.add_i64(self._step_dev, 1)
-        for hook in self.post_step_hooks:
-            hook()
 
     def _upload_hyper(self, gi, hyper):
         host = torch.tensor(hyper, dtype=torch.float64).pin_memory()
@@ -189,6 +330,8 @@ class FusedAdam:
 
     def zero_grad(self, set_to_none=True):
         self._needs_zero = False
+        if self._overlap:
+            self._reset_pending()
         for g, fl in zip(self.param_groups, self._flat):
             if fl is None:
                 continue

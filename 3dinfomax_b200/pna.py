@@ -88,12 +88,12 @@ class PNALayer(nn.Module):
                              last_activation=last_activation, dropout=dropout, mid_batch_norm=mid_batch_norm,
                              last_batch_norm=last_batch_norm, batch_norm_momentum=batch_norm_momentum)
 
-    def forward(self, st, h, ef_csr, edge_codes=None, table=None):
+    def forward(self, st, h, ef_csr, edge_codes=None, table=None, combo=None):
         # models/pna.py:203,237-252 — edge MLP over cat[h[src], h[dst], e], rows emitted in CSR order
         if edge_codes is not None:
             # factored first layer: node-level GEMM + 60-row bond-feature table + one gather-add pass (ops._FCEdgeFactored)
             fcs = self.pretrans.fully_connected
-            msg = fcs[0].forward_edge_factored(edge_codes, h, table, st.e_valid)
+            msg = fcs[0].forward_edge_factored(edge_codes, h, table, st.e_valid, combo)
             for i in range(1, len(fcs)):
                 msg = fcs[i](msg, None, st.e_valid)
         else:
@@ -156,13 +156,14 @@ class PNAGNN(nn.Module):
         h = self.atom_encoder(x_atom)                              # models/pna.py:162
         factored = (os.environ.get("I3D_PRETRANS", "factored") != "gemm" and self.n_bond_codes <= 256
                     and e_attr.shape[1] == self._bond_mult.numel())
-        edge_codes = tables = ef_csr = None
+        edge_codes = tables = ef_csr = combo = None
         if factored:
             # models/pna.py:163 — the bond embedding of an edge is one of n_bond_codes rows: embed the combinations once,
             # and turn the `e` segment of every layer's edge MLP into a table over them (one launch for all layers)
             combo = self.bond_encoder(self._bond_combos)
             F = h.shape[1]
-            tables = ops.bond_tables(combo, [l.pretrans.fully_connected[0].linear.weight for l in self.mp_layers], 2 * F)
+            tables = ops.bond_tables(combo, [l.pretrans.fully_connected[0].linear.weight for l in self.mp_layers], 2 * F,
+                                     weight_grads=False)
             code_csr = getattr(st, "code_csr", None)                # emitted by the device collate when it built `st`
             if code_csr is None:
                 code_csr = (e_attr * self._bond_mult).sum(dim=1)[st.eid.long()]
@@ -174,7 +175,7 @@ class PNAGNN(nn.Module):
             with torch.no_grad():
                 graph.edata["feat"] = self.bond_encoder(e_attr)    # edge-id order, as the reference leaves it
         for li, layer in enumerate(self.mp_layers):
-            h, _ = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li])
+            h, _ = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li], combo if factored else None)
             graph.ndata["feat"] = h                                # models/pna.py:213
         return st, h
 

@@ -56,7 +56,15 @@ class SelfSupervisedTrainer:
             if getattr(v, "_i3d_direct_grad", False):
                 v._i3d_prep = self.prep
                 v._i3d_arena = self.arena
+                v._i3d_optim = self.optim
         self.optim.post_step_hooks.append(self.prep.invalidate)
+        # data parallel: the FC weights of one message-passing layer form one contiguous range of the flat gradient
+        # buffer, all-reduced as soon as that layer's backward has issued its weight-gradient kernels
+        layers = {}
+        for k, v in self.model.named_parameters():
+            if getattr(v, "_i3d_direct_grad", False) and ".mp_layers." in k:
+                layers.setdefault(k.split(".mp_layers.")[1].split(".")[0], []).append(v)
+        self.optim.set_overlap_groups(list(layers.values()))
 
     # --- state that a step mutates (used to make CUDA-graph warm-up runs side-effect free) ---------------------
     def snapshot_state(self):
@@ -87,21 +95,29 @@ class SelfSupervisedTrainer:
         self.arena.reset()
         self.prep.refresh()
         info2d, info3d, *rest = tuple(batch)
+        view3d_all = None
         if self.stream3d is not None:
             main = torch.cuda.current_stream(self.device)
             self.stream3d.wait_stream(main)
             with torch.cuda.stream(self.stream3d):
                 view3d = self.model3d(*info3d)
+                if self.world > 1:
+                    # the 3-D encoder is done long before the 2-D one: its all-gather (and, in backward, the
+                    # reduce-scatter autograd replays on this stream) hides behind the 2-D encoder
+                    view3d_all = D.all_gather_rows(view3d, self.process_group)
             view2d = self.model(*info2d, *rest)      # *snorm_n of PNAOriginal (self_supervised_trainer.py:25-26)
             main.wait_stream(self.stream3d)
             view3d.record_stream(main)
+            if view3d_all is not None:
+                view3d_all.record_stream(main)
         else:
             view2d = self.model(*info2d, *rest)
             view3d = self.model3d(*info3d)
         if self.world > 1:
             # global negative set: every rank's 3-D embeddings; the local rows sit at row_offset in column space
             b_local = view2d.shape[0]
-            view3d_all = D.all_gather_rows(view3d, self.process_group)
+            if view3d_all is None:
+                view3d_all = D.all_gather_rows(view3d, self.process_group)
             loss = self.loss_func(view2d, view3d_all, row_offset=self.rank * b_local,
                                   total_rows=self.world * b_local)
         else:

@@ -444,6 +444,16 @@ int i3d_norm_bwd_accum(const float* z, const float* norms, const float* dn, int6
 int i3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, double grad_scale, int64_t step, const double* hyper_dev,
                   const int64_t* step_dev, void* stream);
+/* Data-parallel step fused over NVLink/NVSwitch multicast memory: gradient all-reduce + Adam + parameter broadcast in
+ * ONE kernel (replaces NCCL all-reduce + i3d_adam_step; the DDP form of trainer/trainer.py:119-123).
+ * local_base: this rank's symmetric allocation holding [p | g | m | v], n floats each (n % 4 == 0); mc_base: the
+ * multicast address bound to the same allocation on all `world` ranks.  Rank r reduces slice r of g through the switch
+ * (multimem.ld_reduce.add), applies Adam to that slice and multicast-stores the new p, m, v into every rank's buffers.
+ * The caller orders the ranks: a cross-rank barrier on the stream before (all gradients written) and after (all
+ * stores landed) this call.  Other arguments as i3d_adam_step. */
+int i3d_adam_step_nvls(float* mc_base, float* local_base, int64_t n, int rank, int world, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, double grad_scale, int64_t step,
+                       const double* hyper_dev, const int64_t* step_dev, void* stream);
 int i3d_add_i64(int64_t* x, int64_t delta, void* stream);
 /* flat[off[t] : off[t]+len[t]] = src_t (to_flat!=0) or the reverse.  ptrs/off/len: DEVICE arrays of T entries */
 int i3d_multi_copy(const uint64_t* ptrs, const int64_t* off, const int64_t* len, int T, float* flat, int to_flat,

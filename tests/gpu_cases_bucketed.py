@@ -195,8 +195,11 @@ def case_edge_factored():
         h2, c2, W2, b2, g2, be2 = Q
         rm, rv = torch.zeros(F, device=DEV), torch.ones(F, device=DEV)
         nbt = torch.zeros((), dtype=torch.long, device=DEV)
-        (T2,) = ops.bond_tables(c2, [W2], 2 * F)
-        O2 = ops.fc_edge_factored(codes, h2, T2, W2, b2, K.ACT[act], (g2, be2, rm, rv, nbt, 0.1, 1e-5), True, valid)
+        # (first and last case: the layer accumulates the W_e columns of dW itself, as the product path does)
+        own = tag in ("small_relu", "narrow_silu")
+        (T2,) = ops.bond_tables(c2, [W2], 2 * F, weight_grads=not own)
+        O2 = ops.fc_edge_factored(codes, h2, T2, W2, b2, K.ACT[act], (g2, be2, rm, rv, nbt, 0.1, 1e-5), True, valid,
+                                  c2 if own else None)
         Rp = torch.cat([R[order], torch.randn(pad, F, generator=g)]).to(DEV)       # garbage upstream gradient on padding
         (O2 * Rp).sum().backward()
         torch.cuda.synchronize()
