@@ -569,6 +569,14 @@ static int ws_dispatch(WsParams& p, float* hi, float* lo, int ktot, cudaStream_t
     // half the SMs idle (node-level GEMMs: 72 row tiles at batch 512).
     if (2 * gx <= sms) return launch_ws<112>(p, hi, lo, ktot, stream);
     if (gx > sms) return launch_ws<208, 2>(p, hi, lo, ktot, stream);          // more tiles than SMs: co-resident pairs
+    // between half and all of the SMs (node-level GEMMs at batch 512: 77 row tiles): 208-wide tiles would leave half the
+    // machine idle, 112-wide ones need two waves at one CTA per SM -> two co-resident 112-wide CTAs per SM, one wave
+    static int split = -1;
+    if (split < 0) {
+      const char* e = getenv("I3D_WS_SPLIT_MID");
+      split = e ? atoi(e) : 0;      // measured neutral at batch 512 (4.390 vs 4.392 ms per step): off by default
+    }
+    if (split && 4 * gx <= 3 * (int64_t)sms + sms) return launch_ws<112, 2>(p, hi, lo, ktot, stream);
     return launch_ws<208>(p, hi, lo, ktot, stream);
   }
   if ((N + 207) / 208 <= (N + 255) / 256) {                                  // same tile count, less padding
