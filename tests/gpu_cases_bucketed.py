@@ -16,6 +16,9 @@ fp32 2.9e-5).  Gradients: every tensor in full, 1e-3 of the global gradient scal
 (measured 1.16e-3 with tensor cores, 1.10e-3 with the fp32 SIMT backend, CPU fp32 3.8e-4: the maximum sits on a bias in
 front of a BatchNorm, whose true gradient is zero, and on the weights of one layer with near-dead ReLU columns, i.e.
 1/sqrt(var + eps) ~ 300 — tools/accuracy_probe.py), plus 2e-2 of each tensor's OWN norm (measured 5.5e-3, CPU 1.5e-3).
+Relative L2 error over ALL parameters at B = 512: 5e-3 (measured 2.9e-3; the CPU fp32 oracle is 1.05e-3 from the truth —
+both are dominated by ReLU sign flips of pre-activations within rounding distance of zero, whose number grows with the
+forward error: 7.5e-5 here vs 2.9e-5 on the CPU, same with the fp32 SIMT GEMM backend, i.e. not a tensor-core effect).
 Net3D's BatchNorms (mean^2 >> var) are where fp64 statistics pay: at config 3 the CUDA gradients are 2.6e-4 from the
 truth, the CPU fp32 oracle 6.7e-3.
 """
@@ -486,7 +489,7 @@ def case_step_b512():
         pg = tr.optim.packed_grads()
         res = [(tag + "/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
         res += _vs_truth(tag, "z2d", z2, oz2, tz2, ztol) + _vs_truth(tag, "z3d", z3, oz3, tz3, 1e-4)
-        res += _grad_checks(tag, {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3)
+        res += _grad_checks(tag, {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3, tol_l2=5e-3)
         res += _buffer_checks(tag, pna, n3, otr)
         return res
 
@@ -511,7 +514,8 @@ def case_step_b512():
     named = _named(pna, n3)
     pg = tr.optim.packed_grads()
     out += [("step_b512/captured/loss(vs fp64 truth)", abs(l.item() - tl.item()), 2e-5)]
-    out += _grad_checks("step_b512/captured", {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3)
+    out += _grad_checks("step_b512/captured", {k: pg[p] for k, p in named.items()}, ograds, tgrads, tol_global=2e-3,
+                        tol_l2=5e-3)
     out += _buffer_checks("step_b512/captured", pna, n3, otr)
     # bucketed (padded) captured step fed by the device collate
     pna, n3, tr = fresh(True)
