@@ -12,6 +12,7 @@ Everything computes through lib3dinfomax_b200.so (hand-written sm_100a kernels, 
 There is no CPU fallback: constructing modules works anywhere, running them needs a CUDA device.
 """
 from .collate import PackedMoleculeStore  # noqa: F401
+from .inference import Fingerprinter, fold_batch_norm  # noqa: F401
 from .graph import GraphBatch, GraphStructure, annotate_max_in_degree, batch_from_numpy, graph_structure  # noqa: F401
 from .losses import NTXent, NTXentMultiplePositives  # noqa: F401
 from .metrics import (ContrastiveAccuracy, NegativeSimilarity, PositiveSimilarity, TrueNegativeRate,  # noqa: F401
@@ -25,5 +26,5 @@ from . import lib, synthetic  # noqa: F401
 
 __all__ = ["PNA", "PNAOriginal", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
            "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "SelfSupervisedTrainer", "CapturedStep", "BucketedStep", "BucketLadder", "FusedAdam",
-           "GraphBatch", "GraphStructure", "PackedMoleculeStore", "annotate_max_in_degree", "batch_from_numpy",
+           "GraphBatch", "GraphStructure", "PackedMoleculeStore", "Fingerprinter", "fold_batch_norm", "annotate_max_in_degree", "batch_from_numpy",
            "graph_structure", "lib", "synthetic"]

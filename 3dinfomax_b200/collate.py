@@ -175,7 +175,7 @@ class PackedMoleculeStore:
         g3 = GraphBatch(src3, dst3, v["num_nodes"], v["num_edges3"], {}, {"d": d3}, N)
         return g2, g3
 
-    def collate_padded(self, meta, B, n_cap, e_cap, e3_cap, conformers=1):
+    def collate_padded(self, meta, B, n_cap, e_cap, e3_cap, conformers=1, need_3d=True):
         """Kernel-only part of a shape-bucketed batch (CUDA-graph capturable): from the DEVICE metadata buffer ``meta``
         (stage_metadata) emit both graphs padded to the bucket capacities, together with their CSR structures
         (i3d_collate_2d_struct / i3d_collate_3d_struct: no sort, no atomics).  Valid sizes stay on the device."""
@@ -191,6 +191,8 @@ class PackedMoleculeStore:
         rowptr, out_rowptr, graph_ptr = i32(n_cap + 1), i32(n_cap + 1), i32(B + 1)
         src_csr, dst_csr, eid, out_pos = i32(e_cap), i32(e_cap), i32(e_cap), i32(e_cap)
         code_csr = i64(e_cap)
+        if not need_3d:                                     # forward-only 2-D use (inference.Fingerprinter)
+            e3_cap = 0
         src3, dst3 = i64(e3_cap), i64(e3_cap)
         d3 = torch.empty(e3_cap, 1, dtype=torch.float32, device=dev)
         rowptr3, graph_ptr3, nn3 = i32(n3_cap + 1), i32(B * C + 1), i64(B * C)
@@ -205,15 +207,17 @@ class PackedMoleculeStore:
                                            p(dst), p(x_atom), p(e_attr), p(rowptr), p(src_csr), p(dst_csr), p(eid),
                                            p(out_rowptr), p(out_pos), p(graph_ptr), p(self.code_mult), p(code_csr), s),
                    "i3d_collate_2d_struct")
-        _lib.check(L.i3d_collate_3d_struct(p(v["idx"]), B, C, p(self.atom_slices), p(self.conformations),
-                                           int(self.conformations.shape[1]), p(v["node_ptr"]), p(v["edge3_ptr"]), n3_cap,
-                                           e3_cap, p(src3), p(dst3), p(d3), p(rowptr3), p(src_csr3), p(dst_csr3), p(eid3),
-                                           p(out_pos3), p(graph_ptr3), p(nn3), s), "i3d_collate_3d_struct")
         g2 = GraphBatch(src, dst, v["num_nodes"], v["num_edges"], {"feat": x_atom}, {"feat": e_attr}, n_cap,
                         max_in_degree=self.max_in_degree_all)
         g2._i3d_struct = GraphStructure.from_parts(n_cap, e_cap, B, rowptr, src_csr, dst_csr, eid, out_rowptr, out_pos,
                                                    graph_ptr, True, self.max_in_degree_all, padded=True)
         g2._i3d_struct.code_csr = code_csr                  # bond-feature combination index of every CSR-ordered edge
+        if not need_3d:
+            return g2, None
+        _lib.check(L.i3d_collate_3d_struct(p(v["idx"]), B, C, p(self.atom_slices), p(self.conformations),
+                                           int(self.conformations.shape[1]), p(v["node_ptr"]), p(v["edge3_ptr"]), n3_cap,
+                                           e3_cap, p(src3), p(dst3), p(d3), p(rowptr3), p(src_csr3), p(dst_csr3), p(eid3),
+                                           p(out_pos3), p(graph_ptr3), p(nn3), s), "i3d_collate_3d_struct")
         g3 = GraphBatch(src3, dst3, nn3, None, {}, {"d": d3}, n3_cap)
         g3._i3d_struct = GraphStructure.from_parts(n3_cap, e3_cap, B * C, rowptr3, src_csr3, dst_csr3, eid3, rowptr3,
                                                    out_pos3, graph_ptr3, False, None, padded=True)

@@ -174,9 +174,17 @@ class PNAGNN(nn.Module):
         if self.keep_edge_side_effects:
             with torch.no_grad():
                 graph.edata["feat"] = self.bond_encoder(e_attr)    # edge-id order, as the reference leaves it
+        msg = None
         for li, layer in enumerate(self.mp_layers):
-            h, _ = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li], combo if factored else None)
+            h, msg = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li], combo if factored else None)
             graph.ndata["feat"] = h                                # models/pna.py:213
+        if self.keep_edge_side_effects and msg is not None:
+            # models/pna.py:203,252: apply_edges leaves the last layer's messages in edata['e'] (edge-id order; ours
+            # are in CSR order: position k holds edge eid[k]).  A pure permutation copy, outside the autograd graph.
+            with torch.no_grad():
+                e = torch.zeros_like(msg)
+                e[st.eid.long()] = msg
+                graph.edata["e"] = e
         return st, h
 
 

@@ -553,6 +553,62 @@ def case_step_config3():
     return out
 
 
+def case_inference():
+    """SURVEY 8f N4 (inference.py:208-214): eval-mode forward with every BatchNorm folded into a Linear, and the
+    fingerprint loop (batch size 2) on forward-only bucketed graphs — against the reference-generated golden eval
+    embeddings, the unfolded eval forward, and (mode 'reference') the train-mode per-batch forward the reference
+    script actually runs."""
+    from oracle.make_golden import CASES
+    out = []
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "qm9_b8.npz"))
+    bseed, B, shape, C, loss_name, (s2, s3) = CASES["qm9_b8"]
+    b = syn.make_batch(bseed, B, shape=shape, conformers=C)
+    c2, c3, st2, st3, pna, n3 = _models(s2, s3)
+    pna.eval()
+    folded = i3d.fold_batch_norm(pna)
+    with torch.no_grad():
+        g2, _ = i3d.batch_from_numpy(b, DEV)
+        z_fold = folded(g2)
+        g2, _ = i3d.batch_from_numpy(b, DEV)
+        z_eval = pna(g2)
+    out += [("inference/folded_batchnorms(22)", float(folded.folded_batch_norms != 22), 0),
+            ("inference/folded_eval_vs_reference_golden_z2d_eval", rel(z_fold, gold["z2d_eval"]), 1e-4),
+            ("inference/folded_eval_vs_unfolded_eval", rel(z_fold, z_eval), 2e-5)]
+    # fingerprint loop over a store, batch size 2 (odd molecule count: a last batch of 1)
+    M = 31
+    store = syn.make_store(63, M, "qm9")
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    fp = i3d.Fingerprinter(pna, ps, batch_size=2, mode="eval")
+    got = fp()
+    want = []
+    with torch.no_grad():
+        for i in range(0, M, 2):
+            h2, _ = ps.collate(np.arange(i, min(i + 2, M)))
+            want.append(pna(h2))
+    want = torch.cat(want)
+    out += [("inference/fingerprints_eval(31 molecules, batch 2)_vs_unfolded_eval_forward", rel(got, want), 1e-4),
+            ("inference/fingerprints_shape", float(tuple(got.shape) != (M, 256)), 0)]
+    # what the reference script literally computes: train-mode BatchNorm on every batch of 2
+    c2, c3, st2, st3, pna_t, _ = _models(s2, s3)
+    fpr = i3d.Fingerprinter(pna_t, ps, batch_size=2, mode="reference")
+    got_r = fpr(np.arange(30))
+    c2, c3, st2, st3, pna_u, _ = _models(s2, s3)
+    pna_u.train()
+    want_r = []
+    with torch.no_grad():
+        for i in range(0, 30, 2):
+            h2, _ = ps.collate(np.arange(i, i + 2))
+            want_r.append(pna_u(h2))
+    want_r = torch.cat(want_r)
+    # ~36 rows per train-mode BatchNorm: fp32 summation order moves the result at the 1e-3 level (both are product paths)
+    out.append(("inference/fingerprints_reference_mode(train-mode BN per batch of 2)_vs_unpadded_forward",
+                rel(got_r, want_r), 2e-3))
+    out.append(("inference/reference_mode_updates_running_stats_like_the_unpadded_loop",
+                rel(pna_t.state_dict()["output.fully_connected.0.batch_norm.running_mean"],
+                    pna_u.state_dict()["output.fully_connected.0.batch_norm.running_mean"]), 2e-3))
+    return out
+
+
 def case_epoch_many_shapes():
     """An 'epoch' of 40 distinct random batches through BucketedStep: every step replays a captured graph (no eager
     fallback), few buckets get captured, and the padded run tracks an unpadded eager run of the same batches (loss per

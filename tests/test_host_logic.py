@@ -183,3 +183,56 @@ def test_degree_plan_reference_layout():
         if n:
             assert r0 % 128 == 0 and n % 128 == 0 and n <= 4 * 128
             assert set(tile_bucket[r0 // 128:(r0 + n) // 128].tolist()) == {bk}
+
+
+def test_fold_batch_norm_algebra():
+    """inference.fold_batch_norm: eval-mode FCLayer stacks (Linear -> activation -> BatchNorm,
+    models/base_layers.py:100-111) with the BatchNorm affine folded into the layer's own Linear (activation 'none') or
+    into the next Linear (behind an activation) compute the same function.  Plain torch on the CPU: the parameters of the
+    product modules, evaluated with torch ops (the kernels need a GPU; tests/gpu_cases_bucketed.py::case_inference runs
+    the folded modules themselves)."""
+    import importlib
+    import torch
+    import torch.nn.functional as F
+    i3d = importlib.import_module("3dinfomax_b200")
+    inf = importlib.import_module("3dinfomax_b200.inference")
+    bl = importlib.import_module("3dinfomax_b200.base_layers")
+    torch.manual_seed(0)
+
+    def torch_eval(mlp, x):
+        for fc in mlp.fully_connected:
+            x = F.linear(x, fc.linear.weight, fc.linear.bias)
+            x = {0: lambda t: t, 1: torch.relu, 2: F.silu, 3: lambda t: F.leaky_relu(t, 0.01)}[fc.act](x)
+            if fc.batch_norm is not None:
+                b = fc.batch_norm
+                x = F.batch_norm(x, b.running_mean, b.running_var, b.weight, b.bias, False, 0.0, b.eps)
+        return x
+
+    for kw, kept in ((dict(in_dim=24, hidden_size=16, out_dim=16, layers=2, mid_activation="relu", last_activation="none",
+                           mid_batch_norm=True, last_batch_norm=True), 0),      # PNA pretrans: 0 -> 1, 1 -> itself
+                     (dict(in_dim=24, out_dim=16, layers=1, last_activation="none", last_batch_norm=True), 0),  # posttrans
+                     (dict(in_dim=24, hidden_size=16, out_dim=8, layers=2, mid_activation="relu", mid_batch_norm=True), 0),
+                     (dict(in_dim=24, out_dim=16, layers=1, last_activation="SiLU", last_batch_norm=True), 1)):  # kept
+        m = bl.MLP(**kw).double()
+        with torch.no_grad():
+            for fc in m.fully_connected:
+                fc.linear.weight.normal_(0, 0.3), fc.linear.bias.normal_(0, 0.3)
+                if fc.batch_norm is not None:
+                    b = fc.batch_norm
+                    b.weight.uniform_(0.5, 1.5), b.bias.normal_(0, 0.3), b.running_mean.normal_(0, 0.5)
+                    b.running_var.uniform_(0.1, 2.0)
+        x = torch.randn(50, 24, dtype=torch.float64)
+        want = torch_eval(m, x)
+        n_bn = sum(fc.batch_norm is not None for fc in m.fully_connected)
+        folded = inf.fold_batch_norm(m)
+        assert folded.folded_batch_norms == n_bn - kept
+        assert sum(fc.batch_norm is not None for fc in folded.fully_connected) == kept
+        got = torch_eval(folded, x)
+        assert float((got - want).abs().max()) < 1e-12 * float(want.abs().max() + 1)
+        assert all(fc.batch_norm is not None for fc in m.fully_connected if True) == (n_bn == len(m.fully_connected))
+    # the shipped PNA: every BatchNorm folds away
+    cfg = importlib.import_module("3dinfomax_b200.configs")
+    pna = i3d.PNA(avg_d=1, device="cpu", **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
+    f = inf.fold_batch_norm(pna)
+    assert f.folded_batch_norms == 22 and not any("batch_norm" in k for k in f.state_dict())
+    assert any("batch_norm" in k for k in pna.state_dict())          # the original is untouched
