@@ -15,8 +15,9 @@ from .collate import PackedMoleculeStore  # noqa: F401
 from .inference import Fingerprinter, fold_batch_norm  # noqa: F401
 from .graph import GraphBatch, GraphStructure, annotate_max_in_degree, batch_from_numpy, graph_structure  # noqa: F401
 from .losses import NTXent, NTXentMultiplePositives  # noqa: F401
-from .metrics import (ContrastiveAccuracy, NegativeSimilarity, PositiveSimilarity, TrueNegativeRate,  # noqa: F401
-                      TruePositiveRate, contrastive_metrics)
+from .metrics import (Alignment, BatchVariance, ContrastiveAccuracy, DimensionCovariance,  # noqa: F401
+                      NegativeSimilarity, PositiveSimilarity, TrueNegativeRate, TruePositiveRate, Uniformity,
+                      contrastive_metrics, embedding_metrics)
 from .net3d import Net3D  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .pna import PNA  # noqa: F401
@@ -25,6 +26,6 @@ from .trainer import BucketedStep, BucketLadder, CapturedStep, SelfSupervisedTra
 from . import lib, synthetic  # noqa: F401
 
 __all__ = ["PNA", "PNAOriginal", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
-           "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "SelfSupervisedTrainer", "CapturedStep", "BucketedStep", "BucketLadder", "FusedAdam",
+           "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "DimensionCovariance", "BatchVariance", "Alignment", "Uniformity", "embedding_metrics", "SelfSupervisedTrainer", "CapturedStep", "BucketedStep", "BucketLadder", "FusedAdam",
            "GraphBatch", "GraphStructure", "PackedMoleculeStore", "Fingerprinter", "fold_batch_norm", "annotate_max_in_degree", "batch_from_numpy",
            "graph_structure", "lib", "synthetic"]

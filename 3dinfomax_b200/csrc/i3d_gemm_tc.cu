@@ -20,6 +20,7 @@
 // 256 threads: all threads stage A, thread 0 issues TMA + MMAs, 8 warps drain TMEM through shared memory.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "i3d_tc.cuh"
@@ -310,6 +311,16 @@ static int launch_generic(TcParams& p, cudaStream_t s) {
   if (MODE == I3D_GEMM_TN) {
     const int K = p.seg[0].K;
     int64_t want = (sm_count() + gx * gy - 1) / (gx * gy);          // ~one CTA per SM
+    {
+      // I3D_TN_SPLIT_DIV=d: 1/d of that (fewer, longer CTAs: less atomic traffic, SMs left to the main stream)
+      static int div = -1;
+      if (div < 0) {
+        const char* e = getenv("I3D_TN_SPLIT_DIV");
+        div = e ? atoi(e) : 1;
+        if (div < 1) div = 1;
+      }
+      want = (want + div - 1) / div;
+    }
     const int64_t max_splits = (K + 4 * TC_BK - 1) / (4 * TC_BK);   // at least 4 k-blocks per CTA
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;

@@ -332,6 +332,154 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The other four metrics the pre-training configs log (configs_clean/pre-train_QM9.yml): DimensionCovariance,
+// BatchVariance, Alignment, Uniformity (trainer/metrics.py:161-176,212-230; cov_loss / uniformity_loss of
+// commons/losses.py:946-964).  The reference builds a [D,D] covariance and a B(B-1)/2 pdist vector per metric and
+// tensor; here tiles of those are reduced on the fly into a handful of fp64 accumulators:
+//   acc[0],acc[1]  sum of squared off-diagonal covariance entries of x1, x2      (x - mean)^T (x - mean) / (B - 1)
+//   acc[2],acc[3]  sum over columns of the unbiased standard deviation of x1, x2
+//   acc[4]         sum_i ||x1_i - x2_i||^alpha
+//   acc[5],acc[6]  sum_{i<j} exp(-t ||x_i - x_j||^2)   (exp evaluated in fp32 like the reference: it underflows to 0,
+//                  and the metric to -inf, for unnormalised embeddings)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_add_f64(double v, double* __restrict__ target) {
+  __shared__ double sh[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(target, t);
+  }
+  __syncthreads();
+}
+
+// one thread per column: mean (kept for the covariance kernel) and unbiased std, two passes over the B rows
+__global__ void metric_cols_kernel(const float* __restrict__ x, int64_t B, int D, double* __restrict__ mean,
+                                   double* __restrict__ acc_std) {
+  pdl_grid_sync();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double sd = 0.0;
+  if (c < D) {
+    double s = 0.0;
+    for (int64_t b = 0; b < B; ++b) s += (double)x[b * D + c];
+    const double m = s / (double)B;
+    double q = 0.0;
+    for (int64_t b = 0; b < B; ++b) {
+      const double d = (double)x[b * D + c] - m;
+      q = fma(d, d, q);
+    }
+    mean[c] = m;
+    sd = B > 1 ? sqrt(q / (double)(B - 1)) : 0.0;
+  }
+  block_add_f64(sd, acc_std);
+}
+
+// 32 x 32 tile of the covariance matrix per CTA (256 threads, 4 entries each), rows streamed through shared memory
+__global__ void __launch_bounds__(256)
+    metric_cov_kernel(const float* __restrict__ x, int64_t B, int D, const double* __restrict__ mean,
+                      double* __restrict__ acc) {
+  pdl_grid_sync();
+  __shared__ float Xi[32][33], Xj[32][33];
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float mi = i0 + tx < D ? (float)mean[i0 + tx] : 0.f, mj = j0 + tx < D ? (float)mean[j0 + tx] : 0.f;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t b0 = 0; b0 < B; b0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t b = b0 + ty * 4 + q;
+      Xi[ty * 4 + q][tx] = (b < B && i0 + tx < D) ? x[b * D + i0 + tx] - mi : 0.f;
+      Xj[ty * 4 + q][tx] = (b < B && j0 + tx < D) ? x[b * D + j0 + tx] - mj : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < 32; ++r) {
+      const float vj = Xj[r][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = fma((double)Xi[r][ty * 4 + q], (double)vj, a[q]);
+    }
+    __syncthreads();
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int gi = i0 + ty * 4 + q, gj = j0 + tx;
+    if (gi < D && gj < D && gi != gj) {
+      const double c = a[q] / (double)(B - 1);
+      s = fma(c, c, s);
+    }
+  }
+  block_add_f64(s, acc);
+}
+
+// 32 x 32 tile of row pairs per CTA (upper triangle): squared distances accumulated in fp32 in dimension order
+__global__ void __launch_bounds__(256)
+    metric_pair_kernel(const float* __restrict__ x, int64_t B, int D, float t, double* __restrict__ acc) {
+  pdl_grid_sync();
+  if (blockIdx.y < blockIdx.x) return;                        // i-tile <= j-tile only (whole CTA)
+  __shared__ float Xi[32][33], Xj[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float d2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < D; c0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty * 4 + q;
+      Xi[r][tx] = (i0 + r < B && c0 + tx < D) ? x[(i0 + r) * D + c0 + tx] : 0.f;
+      Xj[r][tx] = (j0 + r < B && c0 + tx < D) ? x[(j0 + r) * D + c0 + tx] : 0.f;
+    }
+    __syncthreads();
+    for (int c = 0; c < 32; ++c) {
+      const float vj = Xj[tx][c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float d = Xi[ty * 4 + q][c] - vj;
+        d2[q] = fmaf(d, d, d2[q]);
+      }
+    }
+    __syncthreads();
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t gi = i0 + ty * 4 + q, gj = j0 + tx;
+    if (gi < gj && gj < B) s += (double)expf(-t * d2[q]);
+  }
+  block_add_f64(s, acc);
+}
+
+// one warp per row: ||x1_i - x2_i||_2 ^ alpha
+__global__ void metric_align_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int64_t B, int D,
+                                    float alpha, double* __restrict__ acc) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  double v = 0.0;
+  if (row < B) {
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float d = x1[row * D + c] - x2[row * D + c];
+      s = fmaf(d, d, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) v = (double)powf(sqrtf(s), alpha);
+  }
+  block_add_f64(v, acc);
+}
+
+__global__ void metric_final_kernel(const double* __restrict__ acc, int64_t B1, int64_t B2, int D,
+                                    float* __restrict__ out) {
+  pdl_grid_sync();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out[0] = (float)(acc[0] / D) + (float)(acc[1] / D);                          // DimensionCovariance
+  out[1] = (float)(acc[2] / D) + (float)(acc[3] / D);                          // BatchVariance
+  out[2] = (float)(acc[4] / (double)B1);                                       // Alignment
+  const double p1 = 0.5 * (double)B1 * (double)(B1 - 1), p2 = 0.5 * (double)B2 * (double)(B2 - 1);
+  out[3] = (logf((float)(acc[5] / p1)) + logf((float)(acc[6] / p2))) / 2.f;    // Uniformity
+}
+
 }  // namespace i3d
 
 using namespace i3d;
@@ -433,6 +581,36 @@ int i3d_multi_copy_strided(const uint64_t* ptrs, const int64_t* off, const int64
   I3D_REQUIRE(T >= 0 && T <= 65535 && (T == 0 || (ptrs && off && len && flat)), "invalid argument");
   if (T == 0) return I3D_OK;
   launch(multi_copy_kernel, dim3(16, T, 1), 256, 0, as_stream(stream), ptrs, off, len, stride, flat, to_flat);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_embedding_metrics(const float* x1, int64_t B1, const float* x2, int64_t B2, int D, float alpha, float t,
+                          double* ws, float* out4, void* stream) {
+  I3D_REQUIRE(x1 && x2 && ws && out4 && B1 >= 2 && B2 >= B1 && D >= 2 && D <= 65536, "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  double* acc = ws;
+  double* mean1 = ws + 8;
+  double* mean2 = ws + 8 + D;
+  I3D_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 8, s));
+  const int tiles_d = (D + 31) / 32;
+  launch(metric_cols_kernel, (D + 127) / 128, 128, 0, s, x1, B1, D, mean1, acc + 2);
+  I3D_LAUNCHED();
+  launch(metric_cols_kernel, (D + 127) / 128, 128, 0, s, x2, B2, D, mean2, acc + 3);
+  I3D_LAUNCHED();
+  launch(metric_cov_kernel, dim3(tiles_d, tiles_d), 256, 0, s, x1, B1, D, mean1, acc + 0);
+  I3D_LAUNCHED();
+  launch(metric_cov_kernel, dim3(tiles_d, tiles_d), 256, 0, s, x2, B2, D, mean2, acc + 1);
+  I3D_LAUNCHED();
+  const int t1 = (int)((B1 + 31) / 32), t2 = (int)((B2 + 31) / 32);
+  I3D_REQUIRE(t2 <= 65535, "too many rows");
+  launch(metric_pair_kernel, dim3(t1, t1), 256, 0, s, x1, B1, D, t, acc + 5);
+  I3D_LAUNCHED();
+  launch(metric_pair_kernel, dim3(t2, t2), 256, 0, s, x2, B2, D, t, acc + 6);
+  I3D_LAUNCHED();
+  launch(metric_align_kernel, (int)((B1 * 32 + 255) / 256), 256, 0, s, x1, x2, B1, D, alpha, acc + 4);
+  I3D_LAUNCHED();
+  launch(metric_final_kernel, 1, 32, 0, s, acc, B1, B2, D, out4);
   I3D_LAUNCHED();
   return I3D_OK;
 }

@@ -117,6 +117,7 @@ SIGNATURES = {
     "i3d_row_norms": (_I, [_P, _L, _I, _P, _P]),
     "i3d_ntxent_rows_fwd": (_I, [_P, _L, _L, _I, _P, _P, _I, _F, _F, _L, _P, _P, _P]),
     "i3d_contrastive_metrics": (_I, [_P, _L, _P, _P, _F, _P, _P, _P]),
+    "i3d_embedding_metrics": (_I, [_P, _L, _P, _L, _I, _F, _F, _P, _P, _P]),
     "i3d_sum_scaled": (_I, [_P, _L, _F, _P, _P]),
     "i3d_ntxent_rows_bwd": (_I, [_P, _L, _L, _I, _P, _P, _I, _F, _F, _L, _P, _P, _F, _P, _P, _P]),
     "i3d_norm_bwd_accum": (_I, [_P, _P, _P, _L, _I, _P, _P]),

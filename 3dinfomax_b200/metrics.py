@@ -7,6 +7,9 @@ similarity GEMM and ONE pass over it (``i3d_contrastive_metrics``): the first me
 tensor OBJECTS with a given threshold computes all five, the others read the cached device vector (no host sync anywhere;
 the threshold-free similarities default to 0.5, so a config with threshold 0.5009 costs two fused evaluations).
 
+``DimensionCovariance``, ``BatchVariance``, ``Alignment``, ``Uniformity`` (trainer/metrics.py:161-176,212-230) — the other
+four entries of that metric list — share one ``i3d_embedding_metrics`` evaluation the same way.
+
 Only the global-vs-global case (``pos_mask is None``) that the target configs use has a kernel; a ``pos_mask`` raises.
 """
 import torch
@@ -63,6 +66,71 @@ class _Shared:
     @classmethod
     def clear(cls):
         cls.x1 = cls.x2 = cls.versions = cls.threshold = cls.value = None
+
+
+def embedding_metrics(x1, x2, alpha=2.0, t=2.0):
+    """device fp32 [4]: (dimension_covariance, batch_variance, alignment, uniformity) — trainer/metrics.py:161-176,212-230"""
+    if not x1.is_cuda:
+        raise RuntimeError("embedding_metrics needs CUDA tensors: the 3dinfomax_b200 path has no CPU fallback")
+    x1 = x1.detach().float().contiguous()
+    x2 = x2.detach().float().contiguous()
+    B1, D = x1.shape
+    if x2.shape[0] < B1 or x2.shape[1] != D:
+        raise ValueError("x2 must have at least as many rows as x1 and the same width")
+    ws = torch.empty(8 + 2 * D, dtype=torch.float64, device=x1.device)
+    out = torch.empty(4, dtype=torch.float32, device=x1.device)
+    _lib.check(_lib.load().i3d_embedding_metrics(x1.data_ptr(), B1, x2.data_ptr(), x2.shape[0], D, float(alpha), float(t),
+                                                 ws.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "i3d_embedding_metrics")
+    return out
+
+
+class _Shared4:
+    """one fused evaluation of the four embedding metrics per (x1, x2, alpha) — keyed like _Shared on tensor objects"""
+    x1 = x2 = None
+    key = None
+    value = None
+
+    @classmethod
+    def get(cls, x1, x2, alpha):
+        key = (x1._version, x2._version, float(alpha))
+        if not (cls.x1 is x1 and cls.x2 is x2 and cls.key == key):
+            cls.value = embedding_metrics(x1, x2, alpha)
+            cls.x1, cls.x2, cls.key = x1, x2, key
+        return cls.value
+
+
+class _Metric4(nn.Module):
+    index = 0
+    alpha = 2.0
+
+    def forward(self, x1, x2, pos_mask=None):
+        return _Shared4.get(x1, x2, self.alpha)[self.index]
+
+
+class DimensionCovariance(_Metric4):
+    index = 0
+
+
+class BatchVariance(_Metric4):
+    index = 1
+
+
+class Alignment(_Metric4):
+    index = 2
+
+    def __init__(self, alpha=2):
+        super().__init__()
+        self.alpha = float(alpha)
+
+
+class Uniformity(_Metric4):
+    """(the reference stores ``t`` but evaluates uniformity_loss with its default t = 2, trainer/metrics.py:223-229)"""
+    index = 3
+
+    def __init__(self, t=2):
+        super().__init__()
+        self.t = t
 
 
 class _Metric(nn.Module):

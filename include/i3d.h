@@ -424,6 +424,15 @@ int i3d_ntxent_rows_fwd(float* P, int64_t B, int64_t Bc, int C, const float* n1,
  * true_positive_rate, true_negative_rate, contrastive_accuracy).  One pass instead of five [B,B] einsums.      */
 int i3d_contrastive_metrics(const float* dot, int64_t B, const float* n1, const float* n2, float threshold,
                             float* part, float* out5, void* stream);
+/* The other four metrics of configs_clean/pre-train_QM9.yml [trainer/metrics.py:161-176,212-230 with cov_loss /
+ * uniformity_loss of commons/losses.py:946-964], x1 [B1, D], x2 [B2 >= B1, D] (extra rows of x2 are the appended noisy
+ * samples: Alignment uses x2[:B1], the others all rows, as the reference does).  ws: >= 8 + 2 D doubles of scratch.
+ * out4 = (dimension_covariance = cov_loss(x1) + cov_loss(x2),  batch_variance = x1.std(0).mean() + x2.std(0).mean(),
+ *         alignment = mean_i ||x1_i - x2_i||^alpha,  uniformity = (log mean_{i<j} exp(-t d_ij^2) over x1 + same over x2) / 2;
+ *         the reference's Uniformity always uses t = 2).  One pass over covariance / pair tiles instead of materialising
+ *         [D, D] and B(B-1)/2 tensors per metric. */
+int i3d_embedding_metrics(const float* x1, int64_t B1, const float* x2, int64_t B2, int D, float alpha, float t,
+                          double* ws, float* out4, void* stream);
 /* out[0] = scale * sum_i x[i]  (deterministic single-block reduction) */
 int i3d_sum_scaled(const float* x, int64_t n, float scale, float* out, void* stream);
 /* in: P (= p), dot recomputed as tau*log(p)*(n1n2+eps); out: P <- d loss / d dot; dn1[B], dn2[BcC] (caller-zeroed)

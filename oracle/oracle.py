@@ -546,3 +546,35 @@ def contrastive_metrics(x1, x2, threshold=0.5):
     tn = B * (B - 1) - (((~preds).long() - neg_mask) * neg_mask).count_nonzero()  # metrics.py:279-280
     tpr, tnr = tp / B, tn / (B * (B - 1))
     return torch.stack([positive_similarity, negative_similarity, tpr, tnr, (tpr + tnr) / 2])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The other four metrics the pre-training configs log (configs_clean/pre-train_QM9.yml: uniformity, alignment,
+# batch_variance, dimension_covariance): trainer/metrics.py:161-176, 212-230 with commons/losses.py:946-964.
+# Pinned on the reference's own classes by oracle/pin_metrics.py.
+# ---------------------------------------------------------------------------------------------------------------
+def _cov_loss(x):
+    """commons/losses.py:954-959"""
+    B, D = x.shape
+    x = x - x.mean(dim=0)
+    cov = (x.T @ x) / (B - 1)
+    off = cov.flatten()[:-1].view(D - 1, D + 1)[:, 1:].flatten()
+    return off.pow(2).sum() / D
+
+
+def _uniformity(x, t=2):
+    """one term of commons/losses.py:946-951"""
+    return torch.pdist(x, p=2).pow(2).mul(-t).exp().mean().log()
+
+
+def embedding_metrics(x1, x2, alpha=2):
+    """(dimension_covariance, batch_variance, alignment, uniformity) of embeddings x1 [B,D], x2 [>=B,D]:
+    DimensionCovariance = cov_loss(x1) + cov_loss(x2)                       (metrics.py:161-166)
+    BatchVariance       = x1.std(0).mean() + x2.std(0).mean()               (metrics.py:169-174)
+    Alignment(alpha)    = ||x1 - x2[:B]||_2^alpha averaged over the batch   (metrics.py:212-220)
+    Uniformity          = uniformity_loss(x1, x2) with its default t = 2    (metrics.py:223-229: self.t is not passed on)"""
+    dc = _cov_loss(x1) + _cov_loss(x2)
+    bv = x1.std(dim=0).mean() + x2.std(dim=0).mean()
+    al = (x1 - x2[:len(x1)]).norm(dim=1).pow(alpha).mean()
+    un = (_uniformity(x1) + _uniformity(x2)) / 2
+    return torch.stack([dc, bv, al, un])

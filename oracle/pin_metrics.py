@@ -34,7 +34,13 @@ def load_reference_metrics():
     mod("ogb"), mod("ogb.graphproppred", Evaluator=object), mod("ogb.lsc", PCQM4MEvaluator=object)
     c = mod("commons")
     c.__path__ = []
-    mod("commons.losses", cov_loss=None, uniformity_loss=None)
+    # cov_loss / uniformity_loss: the reference's own functions, cut out of commons/losses.py by source line (the module
+    # itself imports dgl); plain torch, executed unmodified
+    src = open(os.path.join(REF, "commons", "losses.py")).read()
+    start, end = src.index("def uniformity_loss"), src.index("class NTXentShuffled")
+    ns = {"torch": torch, "Tensor": torch.Tensor}
+    exec(compile(src[start:end], "commons/losses.py[946-966]", "exec"), ns)
+    mod("commons.losses", cov_loss=ns["cov_loss"], uniformity_loss=ns["uniformity_loss"])
     d = mod("datasets")
     d.__path__ = []
     mod("datasets.geom_drugs_dataset", GEOMDrugs=object)
@@ -80,6 +86,13 @@ def main():
         out[name + "/ref"] = ref.numpy()
         out[name + "/cfg"] = np.array([seed, B, D, noisy])
         print("pinned metrics %s: %s — oracle == reference (bit exact)" % (name, [round(float(v), 6) for v in ref]))
+        # the other four logged metrics (uniformity, alignment, batch_variance, dimension_covariance)
+        ref4 = torch.stack([M.DimensionCovariance()(x1, x2), M.BatchVariance()(x1, x2), M.Alignment(alpha=2)(x1, x2),
+                            M.Uniformity(t=2)(x1, x2)])
+        mine4 = O.embedding_metrics(x1, x2, 2)
+        assert torch.equal(ref4, mine4), (name, ref4, mine4)
+        out[name + "/ref4"] = ref4.numpy()
+        print("pinned embedding metrics %s: %s — oracle == reference (bit exact)" % (name, [round(float(v), 6) for v in ref4]))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), threshold=THRESHOLD, **out)
 
 

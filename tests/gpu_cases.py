@@ -817,6 +817,30 @@ def case_contrastive_metrics():
                 ("metrics/%s/true_positive_rate" % name, abs(float(got[2] - ref[2])), 3.0 / B),
                 ("metrics/%s/true_negative_rate" % name, abs(float(got[3] - ref[3])), flip),
                 ("metrics/%s/contrastive_accuracy" % name, abs(float(got[4] - ref[4])), 0.5 * (3.0 / B + flip))]
+    # the other four logged metrics (dimension_covariance, batch_variance, alignment, uniformity) against the vectors of
+    # the reference's own classes; normalised embeddings give a finite uniformity (unnormalised ones underflow to -inf in
+    # fp32, in the reference and here alike)
+    for name, (seed, B, D, noisy) in CASES.items():
+        x1, x2 = embeddings(seed, B, D, noisy)
+        ref4 = g[name + "/ref4"]
+        got4 = i3d.embedding_metrics(x1.to(DEV), x2.to(DEV), 2.0).double().cpu().numpy()
+        for j, nm in enumerate(("dimension_covariance", "batch_variance", "alignment")):
+            out.append(("metrics/%s/%s" % (name, nm), abs(got4[j] - ref4[j]) / abs(ref4[j]), 2e-5))
+        if np.isfinite(ref4[3]):
+            out.append(("metrics/%s/uniformity" % name, abs(got4[3] - ref4[3]), 1e-3))
+        else:
+            out.append(("metrics/%s/uniformity(-inf like the reference)" % name, float(got4[3] != ref4[3]), 0))
+        n1, n2 = torch.nn.functional.normalize(x1, dim=1), torch.nn.functional.normalize(x2, dim=1)
+        want = O.embedding_metrics(n1, n2, 2)
+        got = i3d.embedding_metrics(n1.to(DEV), n2.to(DEV), 2.0).cpu()
+        out.append(("metrics/%s/normalised_embeddings(all four, relative)" % name,
+                    float(((got - want).abs() / want.abs()).max()), 5e-5))
+    a4, b4 = embeddings(12, 128, 64, 0)
+    a4, b4 = torch.nn.functional.normalize(a4, dim=1).to(DEV), torch.nn.functional.normalize(b4, dim=1).to(DEV)
+    vals4 = torch.stack([i3d.DimensionCovariance()(a4, b4), i3d.BatchVariance()(a4, b4), i3d.Alignment(alpha=2)(a4, b4),
+                         i3d.Uniformity(t=2)(a4, b4)]).cpu()
+    want4 = O.embedding_metrics(a4.cpu(), b4.cpu(), 2)
+    out.append(("metrics/modules4_vs_oracle", float(((vals4 - want4).abs() / want4.abs().clamp(min=1e-6)).max()), 5e-5))
     # module surface of trainer/metrics.py: five metric objects share one fused evaluation
     x1, x2 = embeddings(9, 256, 64, 0)
     a, b = x1.to(DEV), x2.to(DEV)

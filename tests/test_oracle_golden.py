@@ -114,6 +114,9 @@ def test_contrastive_metrics_oracle_matches_reference_vectors(golden_dir):
         x1, x2 = embeddings(seed, B, D, noisy)
         got = O.contrastive_metrics(x1, x2, thr).numpy()
         assert np.array_equal(got, g[name + "/ref"]), name
+        # uniformity / alignment / batch_variance / dimension_covariance (the rest of the pre-training metric list)
+        got4 = O.embedding_metrics(x1, x2, 2).numpy()
+        assert np.array_equal(got4, g[name + "/ref4"]), name
 
 
 def test_finetune_config_oracle_matches_reference_vectors(golden_dir):
