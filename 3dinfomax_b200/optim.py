@@ -181,8 +181,7 @@ class FusedAdam:
         for st in (streams or [torch.cuda.current_stream(dev)]):
             comm.wait_stream(st)
         with torch.cuda.stream(comm):
-            if os.environ.get("I3D_EXP_SKIP_AR", "0") != "1":        # (timing experiment only: wrong results)
-                torch.distributed.all_reduce(fl["g"][s:e], group=self.process_group)
+            torch.distributed.all_reduce(fl["g"][s:e], group=self.process_group)
         self._reduced.append((fi, s, e))
 
     def _allreduce_rest(self, fi, fl):
@@ -190,7 +189,7 @@ class FusedAdam:
         done = sorted((s, e) for f, s, e in self._reduced if f == fi)
         pos, n = 0, fl["g"].numel()
         for s, e in done + [(n, n)]:
-            if s > pos and os.environ.get("I3D_EXP_SKIP_AR", "0") != "1":
+            if s > pos:
                 torch.distributed.all_reduce(fl["g"][pos:s], group=self.process_group)
             pos = max(pos, e)
 
