@@ -22,10 +22,10 @@ from .net3d import Net3D  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .pna import PNA  # noqa: F401
 from .pna_original import PNAOriginal  # noqa: F401
-from .trainer import BucketedStep, BucketLadder, CapturedStep, SelfSupervisedTrainer  # noqa: F401
+from .trainer import BucketedStep, BucketLadder, CapturedStep, SelfSupervisedTrainer, Trainer  # noqa: F401
 from . import lib, synthetic  # noqa: F401
 
 __all__ = ["PNA", "PNAOriginal", "Net3D", "NTXent", "NTXentMultiplePositives", "PositiveSimilarity", "NegativeSimilarity",
-           "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "DimensionCovariance", "BatchVariance", "Alignment", "Uniformity", "embedding_metrics", "SelfSupervisedTrainer", "CapturedStep", "BucketedStep", "BucketLadder", "FusedAdam",
+           "TruePositiveRate", "TrueNegativeRate", "ContrastiveAccuracy", "contrastive_metrics", "DimensionCovariance", "BatchVariance", "Alignment", "Uniformity", "embedding_metrics", "SelfSupervisedTrainer", "Trainer", "CapturedStep", "BucketedStep", "BucketLadder", "FusedAdam",
            "GraphBatch", "GraphStructure", "PackedMoleculeStore", "Fingerprinter", "fold_batch_norm", "annotate_max_in_degree", "batch_from_numpy",
            "graph_structure", "lib", "synthetic"]

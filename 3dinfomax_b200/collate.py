@@ -109,6 +109,10 @@ class PackedMoleculeStore:
         conf = store.get("conformations") if hasattr(store, "get") else None
         self.conformations = self.coordinates if conf is None else t(conf, np.float32)
         self.n_conformers = int(self.conformations.shape[1]) // 3
+        # regression targets of the fine-tuning configs ([M, T] fp32; `targets` of the processed file, already
+        # normalised by the dataset — datasets/qm9_dataset.py:176-187); absent for pre-training stores
+        tg = store.get("targets") if hasattr(store, "get") else None
+        self.targets = None if tg is None else t(np.asarray(tg).reshape(self.M, -1), np.float32)
         self.CA = int(self.atom_features.shape[1])
         self.CE = int(self.edge_features.shape[1])
         # molecule-local CSR arrays: the structure of a batch is emitted by the collate kernel without any sort

@@ -16,3 +16,13 @@ PRETRAIN_QM9_MODEL3D_PARAMETERS = dict(
 
 PRETRAIN_QM9 = dict(loss_func="NTXent", loss_params={"tau": 0.1}, optimizer="Adam", optimizer_params={"lr": 8.0e-5},
                     batch_size=500, model_type="PNA", model3d_type="Net3D")
+
+# configs_clean/tune_QM9_homo.yml:10-74 (fine-tuning on the QM9 'homo' target from a pre-trained checkpoint)
+TUNE_QM9_HOMO_MODEL_PARAMETERS = dict(
+    target_dim=1, hidden_dim=200, mid_batch_norm=True, last_batch_norm=True, readout_batchnorm=True,
+    batch_norm_momentum=0.1, readout_hidden_dim=200, readout_layers=2, dropout=0.0, propagation_depth=7,
+    aggregators=["mean", "max", "min", "std"], scalers=["identity", "amplification", "attenuation"],
+    readout_aggregators=["min", "max", "mean", "sum"], pretrans_layers=2, posttrans_layers=1, residual=True)
+
+TUNE_QM9_HOMO = dict(loss_func="L1Loss", optimizer="Adam", optimizer_params={"lr": 7.0e-5, "weight_decay": 1.0e-11},
+                     batch_size=128, model_type="PNA", transfer_layers=["gnn"], exclude_from_transfer=["batch_norm"])

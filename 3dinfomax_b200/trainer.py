@@ -23,29 +23,60 @@ from .kernels import StatsArena, WeightPrep
 from .optim import FusedAdam
 
 
-class SelfSupervisedTrainer:
-    def __init__(self, model, model3d, loss_func, device="cuda", optimizer_params=None, lr_scheduler=None,
-                 process_group=None, graph_safe=False, overlap_encoders=True):
+class Trainer:
+    """The reference's supervised trainer (trainer/trainer.py:26-124) for the fine-tuning configs
+    (configs_clean/tune_QM9_homo.yml: PNA with target_dim 1, torch's own L1Loss, Adam): ``forward_pass`` is
+    trainer/trainer.py:111-114 — the last entry of the batch tuple is the targets, the first the model's arguments —
+    and ``process_batch`` :116-124.  ``SelfSupervisedTrainer`` below adds the second encoder."""
+
+    def __init__(self, model, loss_func, device="cuda", optimizer_params=None, lr_scheduler=None, process_group=None,
+                 graph_safe=False, transfer_layers=(), exclude_from_transfer=(), frozen_layers=(), transferred_lr=None):
         self.device = torch.device(device)
         self.model = model.to(self.device)
-        self.model3d = model3d.to(self.device)      # moved before the optimizer is built (self_supervised_trainer.py:16)
+        self.model3d = None
+        self._init_common(loss_func, lr_scheduler, process_group)
+        self.stream3d = None
+        self.transfer_layers, self.exclude_from_transfer = tuple(transfer_layers), tuple(exclude_from_transfer)
+        self.frozen_layers, self.transferred_lr = tuple(frozen_layers), transferred_lr
+        self.initialize_optimizer(optimizer_params or {"lr": 1e-3}, graph_safe)
+
+    def _init_common(self, loss_func, lr_scheduler, process_group):
         self.loss_func = loss_func
         self.process_group = process_group
         self.world = torch.distributed.get_world_size(process_group) if D.is_distributed() else 1
         self.rank = torch.distributed.get_rank(process_group) if D.is_distributed() else 0
         self.optim_steps = 0
         self.lr_scheduler = lr_scheduler
-        # the 2-D and 3-D encoders share nothing until the loss: the 3-D one (small, latency-bound kernels) runs on
-        # its own stream, forward and backward (autograd replays a node on the stream its forward ran on), and fills
-        # the SMs the 2-D encoder's one-CTA-per-SM GEMMs leave idle.  Inside a captured step this is a forked branch.
-        self.stream3d = torch.cuda.Stream(device=self.device) if overlap_encoders else None
-        self.initialize_optimizer(optimizer_params or {"lr": 8e-5}, graph_safe)
+
+    def encoders(self):
+        return [self.model] if self.model3d is None else [self.model, self.model3d]
+
+    def param_groups(self, named, optimizer_params):
+        """trainer/trainer.py:216-238: BatchNorm parameters without weight decay, new parameters, parameters transferred
+        from a pre-trained checkpoint (own learning rate), frozen parameters (lr 0) — in this order, which is the order
+        the reference's ordered warm-up walks through"""
+        keys = list(self.model.state_dict().keys())
+        transferred = {k for k in keys if any(t in k for t in self.transfer_layers)
+                       and not any(x in k for x in self.exclude_from_transfer)}
+        frozen = {k for k in keys if any(f in k for f in self.frozen_layers)}
+        frozen_params = [v for k, v in named if k in frozen]
+        transferred_params = [v for k, v in named if k in transferred]
+        new_params = [v for k, v in named if k not in transferred and "batch_norm" not in k and k not in frozen]
+        batch_norm_params = [v for k, v in named if "batch_norm" in k and k not in transferred and k not in frozen]
+        transfer_lr = optimizer_params.get("lr", 1e-3) if self.transferred_lr is None else self.transferred_lr
+        groups = []
+        if batch_norm_params:
+            groups.append({"params": batch_norm_params, "weight_decay": 0})
+        groups.append({"params": new_params})
+        if transferred_params:
+            groups.append({"params": transferred_params, "lr": transfer_lr})
+        if frozen_params:
+            groups.append({"params": frozen_params, "lr": 0})
+        return groups
 
     def initialize_optimizer(self, optimizer_params, graph_safe=False):
-        named = list(chain(self.model.named_parameters(), self.model3d.named_parameters()))
-        normal_params = [v for k, v in named if "batch_norm" not in k]
-        batch_norm_params = [v for k, v in named if "batch_norm" in k]
-        self.optim = FusedAdam([{"params": batch_norm_params, "weight_decay": 0}, {"params": normal_params}],
+        named = list(chain(*[m.named_parameters() for m in self.encoders()]))
+        self.optim = FusedAdam(self.param_groups(named, optimizer_params),
                                process_group=self.process_group if self.world > 1 else None, graph_safe=graph_safe,
                                **optimizer_params)
         # FC weights get their tf32 hi/lo operand copies (plain and transposed) from one launch per step
@@ -71,7 +102,7 @@ class SelfSupervisedTrainer:
         """Copies of everything ``process_batch`` mutates: parameters, Adam moments and step counters, BatchNorm
         buffers.  ``restore_state`` puts them back (same storage: views handed to modules / captured graphs stay valid)."""
         o = self.optim
-        bufs = [b for m in (self.model, self.model3d) for b in m.buffers()]
+        bufs = [b for m in self.encoders() for b in m.buffers()]
         return {"flat": [None if fl is None else (fl["p"].clone(), fl["m"].clone(), fl["v"].clone()) for fl in o._flat],
                 "step": o._step, "step_dev": None if o._step_dev is None else o._step_dev.clone(),
                 "bufs": [b.clone() for b in bufs], "optim_steps": self.optim_steps}
@@ -85,11 +116,52 @@ class SelfSupervisedTrainer:
         o._step = snap["step"]
         if o._step_dev is not None:
             o._step_dev.copy_(snap["step_dev"])
-        bufs = [b for m in (self.model, self.model3d) for b in m.buffers()]
+        bufs = [b for m in self.encoders() for b in m.buffers()]
         for b, c in zip(bufs, snap["bufs"]):
             b.copy_(c)
         self.optim_steps = snap["optim_steps"]
         self.prep.invalidate()
+
+    def forward_pass(self, batch):
+        self.arena.reset()
+        self.prep.refresh()
+        targets = batch[-1]                       # the last entry of the batch tuple is always the targets
+        predictions = self.model(*batch[0])
+        return self.loss_func(predictions, targets), predictions, targets
+
+    def process_batch(self, batch, optim=True):
+        loss, predictions, targets = self.forward_pass(batch)
+        if optim:
+            loss.backward()
+            self.optim.step()
+            self.after_optim_step()
+            self.optim.zero_grad()
+            self.optim_steps += 1
+        return loss, predictions.detach(), targets.detach()
+
+    def after_optim_step(self):
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+
+
+class SelfSupervisedTrainer(Trainer):
+    def __init__(self, model, model3d, loss_func, device="cuda", optimizer_params=None, lr_scheduler=None,
+                 process_group=None, graph_safe=False, overlap_encoders=True):
+        self.device = torch.device(device)
+        self.model = model.to(self.device)
+        self.model3d = model3d.to(self.device)      # moved before the optimizer is built (self_supervised_trainer.py:16)
+        self._init_common(loss_func, lr_scheduler, process_group)
+        # the 2-D and 3-D encoders share nothing until the loss: the 3-D one (small, latency-bound kernels) runs on
+        # its own stream, forward and backward (autograd replays a node on the stream its forward ran on), and fills
+        # the SMs the 2-D encoder's one-CTA-per-SM GEMMs leave idle.  Inside a captured step this is a forked branch.
+        self.stream3d = torch.cuda.Stream(device=self.device) if overlap_encoders else None
+        self.initialize_optimizer(optimizer_params or {"lr": 8e-5}, graph_safe)
+
+    def param_groups(self, named, optimizer_params):
+        """trainer/self_supervised_trainer.py:78-86 over both encoders"""
+        normal_params = [v for k, v in named if "batch_norm" not in k]
+        batch_norm_params = [v for k, v in named if "batch_norm" in k]
+        return [{"params": batch_norm_params, "weight_decay": 0}, {"params": normal_params}]
 
     def forward_pass(self, batch):
         self.arena.reset()
@@ -123,20 +195,6 @@ class SelfSupervisedTrainer:
         else:
             loss = self.loss_func(view2d, view3d, nodes_per_graph=None)
         return loss, view2d, view3d
-
-    def process_batch(self, batch, optim=True):
-        loss, predictions, targets = self.forward_pass(batch)
-        if optim:
-            loss.backward()
-            self.optim.step()
-            self.after_optim_step()
-            self.optim.zero_grad()
-            self.optim_steps += 1
-        return loss, predictions.detach(), targets.detach()
-
-    def after_optim_step(self):
-        if self.lr_scheduler is not None:
-            self.lr_scheduler.step()
 
 
 class CapturedStep:
@@ -288,6 +346,9 @@ class BucketedStep:
     def __init__(self, trainer, store, conformers=1, sigma_step=1.0, dp_levels=6, keep_graph_outputs=True):
         if not trainer.optim.graph_safe:
             raise ValueError("BucketedStep needs SelfSupervisedTrainer(..., graph_safe=True)")
+        self.supervised = trainer.model3d is None       # Trainer: batch = ([2-D graph], targets[idx])
+        if self.supervised and store.targets is None:
+            raise ValueError("supervised steps need `targets` [M, T] in the packed store")
         self.tr, self.store, self.C = trainer, store, int(conformers)
         self.sigma_step, self.dp_levels = float(sigma_step), int(dp_levels)
         self.pool = torch.cuda.graph_pool_handle()
@@ -298,7 +359,7 @@ class BucketedStep:
         self.predictions = self.targets = None
         self._out = {}
         self.stats = {"steps": 0, "captures": 0, "eager": 0, "levels": {}}
-        for m in (trainer.model, trainer.model3d):
+        for m in trainer.encoders():
             gnn = getattr(m, "node_gnn", None)
             if gnn is not None and hasattr(gnn, "keep_edge_side_effects"):
                 gnn.keep_edge_side_effects = False        # nobody sees the graph object of a captured step
@@ -314,14 +375,19 @@ class BucketedStep:
         tr = self.tr
         if train:
             tr.optim.zero_grad(set_to_none=True)
-        g2, g3 = self.store.collate_padded(bk.meta, B, *bk.caps, conformers=self.C)
+        g2, g3 = self.store.collate_padded(bk.meta, B, *bk.caps, conformers=self.C, need_3d=not self.supervised)
+        if self.supervised:
+            from .collate import metadata_views
+            batch = ([g2], self.store.targets.index_select(0, metadata_views(bk.meta, B)["idx"]))
+        else:
+            batch = ([g2], [g3])
         if train:
-            loss, z2, z3 = tr.forward_pass(([g2], [g3]))
+            loss, z2, z3 = tr.forward_pass(batch)
             loss.backward()
             tr.optim.step()
         else:
             with torch.no_grad():
-                loss, z2, z3 = tr.forward_pass(([g2], [g3]))
+                loss, z2, z3 = tr.forward_pass(batch)
         self.loss.copy_(loss.detach())
         if self.keep_outputs:
             o2, o3 = self._outputs(B, z2, z3)
@@ -420,11 +486,16 @@ class BucketedStep:
         if self.C != 1:
             raise RuntimeError("batch beyond the captured ladder: the eager fallback handles one conformer per molecule")
         g2, g3 = self.store.collate(idx)
+        if self.supervised:
+            ix = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self.tr.device)
+            batch = ([g2], self.store.targets.index_select(0, ix))
+        else:
+            batch = ([g2], [g3])
         if train:
-            loss, z2, z3 = self.tr.process_batch(([g2], [g3]))
+            loss, z2, z3 = self.tr.process_batch(batch)
         else:
             with torch.no_grad():
-                loss, z2, z3 = self.tr.forward_pass(([g2], [g3]))
+                loss, z2, z3 = self.tr.forward_pass(batch)
         self.loss.copy_(loss.detach())
         self.predictions, self.targets = z2.detach(), z3.detach()
         return self.loss

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — molecules/s of the 3DInfomax pre-training step (PNA + Net3D + NTXent, fwd + bwd + Adam) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|3|4] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 1|3|4|5] [--batch B]
                     [--mode bucketed|eager] [--store-size M]
 
 Workloads (BASELINE.json `configs`):
@@ -12,6 +12,10 @@ Workloads (BASELINE.json `configs`):
              over the GPUs (strong scaling: 2048 / N molecules per GPU).
   --config 4: configs_clean/pre-train_QMugs.yml shape — QMugs-shaped molecules (~40 atoms), 3 conformers, batch 512
              per GPU (weak scaling).
+
+  --config 5: configs_clean/tune_QM9_homo.yml — the fine-tuning step: PNA with the regression head (target_dim 1,
+             readout min/max/mean/sum), torch's L1Loss, Adam (lr 7e-5, weight_decay 1e-11), batch 128, through the
+             supervised trainer (trainer/trainer.py:111-124); no 3-D encoder.
 
 A "step" is what `train.py` does per batch (train.py:595-598 -> trainer/trainer.py:116-124): build the batch, both
 encoders, loss, backward, [NCCL all-gather / reduce-scatter of embeddings + all-reduce of gradients when N > 1], Adam.
@@ -53,7 +57,15 @@ CONFIGS = {
     4: dict(shape="qmugs", conformers=3, loss="NTXentMultiplePositives", per_gpu=512, global_batch=None, scaling="weak",
             name="configs[3]: configs_clean/pre-train_QMugs.yml — PNA+Net3D NTXentMultiplePositives(3 conformers) Adam, "
                  "QMugs-shaped synthetic (~40 atoms), batch %d per GPU"),
+    5: dict(shape="qm9", conformers=1, loss="L1Loss", per_gpu=128, global_batch=None, scaling="weak", finetune=True,
+            name="configs[4]: configs_clean/tune_QM9_homo.yml — PNA(target_dim 1, readout min/max/mean/sum) L1Loss "
+                 "Adam(lr 7e-5, weight_decay 1e-11) fine-tuning step, QM9-shaped synthetic, batch %d per GPU"),
 }
+METRIC_FINETUNE = "molecules/sec PNA QM9 fine-tune (fwd+bwd+Adam)"
+
+
+def metric_name(args):
+    return METRIC_FINETUNE if CONFIGS[args.config].get("finetune") else METRIC
 
 
 def parse_args():
@@ -155,7 +167,8 @@ def make_store(args, M):
     import numpy as np
     syn = importlib.import_module("3dinfomax_b200.synthetic")
     c = CONFIGS[args.config]
-    path = os.path.join(tempfile.gettempdir(), "i3d_store_%s_c%d_m%d.npz" % (c["shape"], c["conformers"], M))
+    path = os.path.join(tempfile.gettempdir(), "i3d_store_%s_c%d_m%d%s.npz" % (c["shape"], c["conformers"], M,
+                                                                              "_y" if c.get("finetune") else ""))
     if os.path.isfile(path):
         try:
             with np.load(path) as z:
@@ -163,6 +176,8 @@ def make_store(args, M):
         except Exception:
             pass
     store = syn.make_store(7, M, c["shape"], conformers=c["conformers"])
+    if c.get("finetune"):        # normalised regression targets (datasets/qm9_dataset.py:176-187 standardises them)
+        store["targets"] = np.random.default_rng(8).normal(size=(M, 1)).astype(np.float32)
     try:
         tmp = path + ".%d.tmp.npz" % os.getpid()
         np.savez(tmp, **store)
@@ -195,12 +210,14 @@ def cpu_oracle_throughput(args, batch, steps, warmup, threads=None):
     if threads:
         torch.set_num_threads(threads)
     c = CONFIGS[args.config]
-    c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
-    tr = O.OracleTrainer(c2, c3, O.init_pna_state(c2, 1), O.init_net3d_state(c3, 2), loss=c["loss"], tau=TAU, lr=LR)
     M = max(4 * batch, 256)
     store = make_store(args, M)
     rng = np.random.default_rng(5)
     C = c["conformers"]
+    if c.get("finetune"):
+        return cpu_oracle_finetune_throughput(store, M, batch, steps, warmup, rng)
+    c2, c3 = O.pna_cfg(**O.PRETRAIN_QM9_PNA), O.net3d_cfg(**O.PRETRAIN_QM9_NET3D)
+    tr = O.OracleTrainer(c2, c3, O.init_pna_state(c2, 1), O.init_net3d_state(c3, 2), loss=c["loss"], tau=TAU, lr=LR)
     mk = (lambda ix: CO.collate_reference_conformers(store, ix, C)) if C > 1 else (lambda ix: CO.collate_reference(store, ix))
     batches = [O.graphs_from_batch(mk(ix)) for ix in epoch_batches(rng, M, batch, 3)]
     for i in range(warmup):
@@ -208,6 +225,39 @@ def cpu_oracle_throughput(args, batch, steps, warmup, threads=None):
     t0 = time.perf_counter()
     for i in range(steps):
         tr.step(*batches[i % 3])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def cpu_oracle_finetune_throughput(store, M, batch, steps, warmup, rng):
+    """the fine-tuning step of config 5 with the CPU oracle's PNA: forward, torch's L1Loss, backward, torch's Adam with
+    the reference's parameter groups (trainer/trainer.py:111-124, 216-238)"""
+    import torch
+    from oracle import collate_oracle as CO
+    from oracle import oracle as O
+    cfg = importlib.import_module("3dinfomax_b200.configs")
+    c2 = O.pna_cfg(**cfg.TUNE_QM9_HOMO_MODEL_PARAMETERS)
+    st = O.as_leaf_params(O.init_pna_state(c2, 1))
+    named = [(k, st[k]) for k in O.param_keys(st)]
+    opt = torch.optim.Adam([{"params": [v for k, v in named if "batch_norm" in k], "weight_decay": 0},
+                            {"params": [v for k, v in named if "batch_norm" not in k]}],
+                           **cfg.TUNE_QM9_HOMO["optimizer_params"])
+    batches = []
+    for ix in epoch_batches(rng, M, batch, 3):
+        g2, xa, ea, _, _ = O.graphs_from_batch(CO.collate_reference(store, ix))
+        batches.append((g2, xa, ea, torch.from_numpy(store["targets"][ix])))
+
+    def step(g2, xa, ea, y):
+        loss = torch.nn.L1Loss()(O.pna_forward(st, c2, g2, xa, ea, True), y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+
+    for i in range(warmup):
+        step(*batches[i % 3])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(*batches[i % 3])
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps, torch.get_num_threads()
 
@@ -229,7 +279,7 @@ def run_reference(args):
         b //= 2
     val, per_step, threads = cpu_oracle_throughput(args, b, args.steps, args.warmup, cores)
     sample = "%d timed + %d warm-up oracle steps on batches of %d molecules" % (args.steps, args.warmup, b)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": CONFIGS[args.config]["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, world),
@@ -261,11 +311,18 @@ def run_b200(args):
     B, C = per_gpu_batch(args, world), c["conformers"]
 
     torch.manual_seed(123)                                   # identical replicas on every rank (train.py:235 seed_all)
-    pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
-    n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
     bucketed = args.mode == "bucketed"
-    tr = i3d.SelfSupervisedTrainer(pna, n3, getattr(i3d, c["loss"])(tau=TAU), dev, {"lr": LR},
-                                   process_group=dist.group.WORLD if world > 1 else None, graph_safe=bucketed)
+    finetune = bool(c.get("finetune"))
+    pg = dist.group.WORLD if world > 1 else None
+    if finetune:
+        pna = i3d.PNA(avg_d=1, device=dev, **cfg.TUNE_QM9_HOMO_MODEL_PARAMETERS)
+        tr = i3d.Trainer(pna, torch.nn.L1Loss(), dev, dict(cfg.TUNE_QM9_HOMO["optimizer_params"]), process_group=pg,
+                         graph_safe=bucketed)
+    else:
+        pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
+        n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
+        tr = i3d.SelfSupervisedTrainer(pna, n3, getattr(i3d, c["loss"])(tau=TAU), dev, {"lr": LR}, process_group=pg,
+                                       graph_safe=bucketed)
 
     M = args.store_size or max(16 * B, 4096)
     if rank == 0:
@@ -303,7 +360,11 @@ def run_b200(args):
         if C != 1:
             raise RuntimeError("--mode eager supports one conformer per molecule")
         g2, g3 = store.collate(ix)
-        loss, _, _ = tr.process_batch(([g2], [g3]))
+        if finetune:
+            y = store.targets.index_select(0, torch.from_numpy(ix).to(dev))
+            loss, _, _ = tr.process_batch(([g2], y))
+        else:
+            loss, _, _ = tr.process_batch(([g2], [g3]))
         return loss
 
     def step_e2e(i):
@@ -439,7 +500,7 @@ def run_b200(args):
 
     if rank == 0:
         mols = B * world * args.steps
-        line = {"metric": METRIC, "value": mols / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(args), "value": mols / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": c["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, world),

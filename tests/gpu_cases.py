@@ -1122,11 +1122,12 @@ def case_full_size_properties():
 
 from gpu_cases_dp import case_sharded_equals_full  # noqa: E402
 from gpu_cases_bucketed import (case_bucketed_step, case_bucketed_step_conformers, case_collate_struct,  # noqa: E402
-                                case_edge_factored, case_epoch_many_shapes, case_inference, case_staging_ring, case_step_b512, case_step_config3)
+                                case_edge_factored, case_epoch_many_shapes, case_finetune_step, case_inference, case_staging_ring, case_step_b512,
+                                case_step_config3)
 
 ALL_CASES = [case_csr, case_embed, case_gemm, case_gemm_tc, case_weight_prep, case_bn, case_aggregate, case_segment_ops, case_net3d_elementwise,
              case_ntxent, case_adam, case_fc, case_degree_plan, case_fc_merged, case_golden, case_golden_qmugs,
              case_golden_merged, case_train_steps, case_train_steps_captured, case_train_steps_merged,
              case_dw_side_stream, case_full_size_properties, case_collate, case_contrastive_metrics, case_pna_original, case_finetune_config, case_sharded_equals_full,
              case_collate_struct, case_edge_factored, case_staging_ring, case_bucketed_step, case_bucketed_step_conformers, case_step_b512,
-             case_step_config3, case_epoch_many_shapes, case_inference]
+             case_step_config3, case_epoch_many_shapes, case_inference, case_finetune_step]

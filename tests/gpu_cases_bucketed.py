@@ -609,6 +609,106 @@ def case_inference():
     return out
 
 
+class _OracleFinetune:
+    """PNA + torch's L1Loss + Adam with the parameter groups of trainer/trainer.py:216-238 (nothing transferred)"""
+
+    def __init__(self, c, st, lr, weight_decay, dtype=torch.float32):
+        self.c = c
+        self.st = O.as_leaf_params({k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in st.items()})
+        named = [(k, self.st[k]) for k in O.param_keys(self.st)]
+        self.optim = torch.optim.Adam([{"params": [v for k, v in named if "batch_norm" in k], "weight_decay": 0},
+                                       {"params": [v for k, v in named if "batch_norm" not in k]}], lr=lr,
+                                      weight_decay=weight_decay)
+
+    def step(self, batch, y):
+        g2, xa, ea, _, _ = O.graphs_from_batch(batch)
+        z = O.pna_forward(self.st, self.c, g2, xa, ea, True)
+        loss = torch.nn.L1Loss()(z, y.to(z.dtype))
+        loss.backward()
+        grads = {k: self.st[k].grad.detach().clone() for k in O.param_keys(self.st)}
+        self.optim.step()
+        self.optim.zero_grad()
+        return loss.detach(), z.detach(), grads
+
+
+def case_finetune_step():
+    """BASELINE config 5 (configs_clean/tune_QM9_homo.yml: PNA head with target_dim 1, readout min/max/mean/sum,
+    BatchNorm momentum 0.1, L1Loss, Adam lr 7e-5 / weight_decay 1e-11, batch 128) as whole optimisation steps through
+    the supervised ``Trainer`` (trainer/trainer.py:111-124): one eager step on a collated batch and captured
+    shape-bucketed steps fed by the device collate (targets gathered on the device), against the CPU oracle step."""
+    from oracle.pin_finetune import TUNE_QM9_HOMO
+    lr, wd = 7e-5, 1e-11
+    B, M = 128, 700
+    store = syn.make_store(61, M, "qm9")
+    store["targets"] = np.random.default_rng(62).normal(size=(M, 1)).astype(np.float32)
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    c = O.pna_cfg(**TUNE_QM9_HOMO)
+    st = O.init_pna_state(c, 81, True)
+    otr = _OracleFinetune(c, st, lr, wd)
+    pna = i3d.PNA(avg_d=1, device=DEV, **TUNE_QM9_HOMO)
+    pna.load_state_dict(st)
+    tr = i3d.Trainer(pna, torch.nn.L1Loss(), DEV, {"lr": lr, "weight_decay": wd}, graph_safe=True)
+    run = i3d.BucketedStep(tr, ps)
+    named = dict(pna.named_parameters())
+    rng = np.random.default_rng(9)
+    order = np.argsort(store["n_atoms"], kind="stable")
+    batches = [("eager", rng.integers(0, M, size=B)), ("bucketed", rng.integers(0, M, size=B)),
+               ("bucketed", order[-B:][::-1].copy()), ("bucketed", rng.integers(0, M, size=B // 2 + 3))]
+    out = []
+    for s, (how, idx) in enumerate(batches):
+        t = "finetune_step/%s/step%d(B=%d)" % (how, s, len(idx))
+        b = _ref_batch(store, idx, 1)
+        y = torch.from_numpy(store["targets"][idx])
+        o64 = _OracleFinetune(c, {k: v.detach() for k, v in otr.st.items()}, lr, wd, torch.float64)
+        tl, tz, tgrads = o64.step(b, y)
+        ol, oz, ograds = otr.step(b, y)
+        if how == "eager":
+            g2, _ = ps.collate(idx)
+            tr.optim.zero_grad()
+            l, z, yy = tr.forward_pass(([g2], y.to(DEV)))
+            l.backward()
+            tr.optim.step()
+            tr.optim_steps += 1
+            out.append((t + "/targets", exact(yy, y), 0))
+        else:
+            l = run.step(idx)
+            z = run.predictions
+            out.append((t + "/targets(gathered on the device)", exact(run.targets, y), 0))
+        torch.cuda.synchronize()
+        pg = tr.optim.packed_grads()
+        grads = {k: pg[p] for k, p in named.items()}
+        out.append((t + "/l1_loss(vs fp64 truth)", abs(l.item() - tl.item()), 5e-5))
+        out += _vs_truth(t, "prediction", z, oz, tz, 1e-4)
+        out += _grad_checks(t, grads, ograds, tgrads, tol_global=2e-3, tol_tensor=2e-2, tol_l2=5e-3)
+        worst = 0.0
+        for k, v in pna.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                worst = max(worst, rel(v, otr.st[k]))
+            elif k.endswith("num_batches_tracked"):
+                worst = max(worst, float(int(v.item()) != int(otr.st[k])))
+        out.append((t + "/bn_running_stats(all layers)", worst, 1e-4))
+        scale = max(float(g.abs().max()) for g in ograds.values())
+        bad = total = 0
+        med = 0.0
+        for k, p in named.items():
+            decisive = ograds[k].abs() > 1e-2 * scale
+            if not decisive.any():
+                continue
+            err = ((p.detach().cpu() - otr.st[k].detach()).abs() / lr)[decisive]
+            bad += int((err > 0.05).sum())
+            total += err.numel()
+            med = max(med, float(err.median()))
+        out += [(t + "/adam_update(decisive weights: %d)/fraction_off_by_>5%%_of_lr" % total, bad / max(total, 1), 1e-2),
+                (t + "/adam_update(decisive weights)/median_error_in_lr_units", med, 1e-2)]
+        with torch.no_grad():
+            for k, v in pna.state_dict().items():
+                v.copy_(torch.as_tensor(otr.st[k]))
+        tr.prep.invalidate()
+    out.append(("finetune_step/distinct_buckets_captured>=2", float(len(run.buckets) < 2), 0))
+    out.append(("finetune_step/no_eager_fallback", float(run.stats["eager"]), 0))
+    return out
+
+
 def case_epoch_many_shapes():
     """An 'epoch' of 40 distinct random batches through BucketedStep: every step replays a captured graph (no eager
     fallback), few buckets get captured, and the padded run tracks an unpadded eager run of the same batches (loss per
