@@ -84,16 +84,32 @@ __global__ void __launch_bounds__(256)
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(R, r0 + rows_per_cta);
   if (rg < RP) {
-    for (int64_t r = r0 + rg; r < r1; r += RP) {
-      const int64_t rr = perm ? (int64_t)perm[r] : r;
-      const int v = (int)idx[rr * C + c];
-      if (v < 0 || v >= dim) continue;
-      Vec<V> g;
-      g.load(gout + r * F + cgp * V);
-      float* dst = acc + v * F + cgp * V;
+    // kEmbRows rows in flight per thread: the chain perm -> idx is two dependent loads per row (and the gradient row a
+    // third, independent one); issued one row at a time the loop is pure memory latency
+    constexpr int kEmbRows = 8;
+    for (int64_t rb = r0 + rg; rb < r1; rb += (int64_t)RP * kEmbRows) {
+      int64_t rr[kEmbRows];
+      int v[kEmbRows];
+      Vec<V> g[kEmbRows];
 #pragma unroll
-      for (int i = 0; i < V; ++i) atomicAdd(dst + i, g.v[i]);
-      if (cgp == 0) atomicOr(&touched[v >> 5], 1u << (v & 31));
+      for (int u = 0; u < kEmbRows; ++u) {
+        const int64_t r = rb + (int64_t)u * RP;
+        rr[u] = -1;
+        if (r < r1) {
+          rr[u] = perm ? (int64_t)__ldg(perm + r) : r;
+          g[u].load(gout + r * F + cgp * V);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEmbRows; ++u) v[u] = rr[u] >= 0 ? (int)__ldg(idx + rr[u] * C + c) : -1;
+#pragma unroll
+      for (int u = 0; u < kEmbRows; ++u) {
+        if (v[u] < 0 || v[u] >= dim) continue;
+        float* dst = acc + v[u] * F + cgp * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(dst + i, g[u].v[i]);
+        if (cgp == 0) atomicOr(&touched[v[u] >> 5], 1u << (v[u] & 31));
+      }
     }
   }
   __syncthreads();

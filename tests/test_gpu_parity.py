@@ -42,3 +42,18 @@ def test_native_library_is_the_compute_path():
     assert lib.launch_count() == n0 + 1
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         K.add(torch.ones(8), torch.ones(8))
+
+
+def test_aggregate_tma_staged_variant():
+    """I3D_AGG_FWD=tma: the bulk-copy (TMA) staged forward aggregation kernel — the opt-in variant of
+    i3d_pna_aggregate_fwd — through the same parity cases as the default kernel (kernel level + whole models against
+    the reference's golden vectors).  The variant is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, I3D_AGG_FWD="tma")
+    r = subprocess.run([sys.executable, os.path.join(here, "gpu_diag.py"), "case_aggregate", "case_golden"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "TOTAL FAILURES: 0" in r.stdout, r.stdout[-4000:]
+    assert r.stdout.count("== case_") == 2, r.stdout[-2000:]
