@@ -652,8 +652,10 @@ def case_finetune_step():
     named = dict(pna.named_parameters())
     rng = np.random.default_rng(9)
     order = np.argsort(store["n_atoms"], kind="stable")
-    batches = [("eager", rng.integers(0, M, size=B)), ("bucketed", rng.integers(0, M, size=B)),
-               ("bucketed", order[-B:][::-1].copy()), ("bucketed", rng.integers(0, M, size=B // 2 + 3))]
+    # (the eager step comes last: tensors of an eager backward that are still alive would tie the parameters'
+    #  AccumulateGrad nodes to the eager stream and invalidate a later capture)
+    batches = [("bucketed", rng.integers(0, M, size=B)), ("bucketed", order[-B:][::-1].copy()),
+               ("bucketed", rng.integers(0, M, size=B // 2 + 3)), ("eager", rng.integers(0, M, size=B))]
     out = []
     for s, (how, idx) in enumerate(batches):
         t = "finetune_step/%s/step%d(B=%d)" % (how, s, len(idx))
@@ -669,6 +671,7 @@ def case_finetune_step():
             l.backward()
             tr.optim.step()
             tr.optim_steps += 1
+            l, z = l.detach(), z.detach()
             out.append((t + "/targets", exact(yy, y), 0))
         else:
             l = run.step(idx)
