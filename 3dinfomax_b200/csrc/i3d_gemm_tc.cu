@@ -18,6 +18,7 @@
 //
 // Tile: 128 (M) x BN (N, multiple of 16, <= 256) x 32 (K = one 128-byte swizzle atom of tf32), 2 smem stages,
 // 256 threads: all threads stage A, thread 0 issues TMA + MMAs, 8 warps drain TMEM through shared memory.
+#include <cooperative_groups.h>
 #include <cuda.h>
 
 #include <cstdlib>
@@ -45,7 +46,91 @@ struct TcParams {
   const int32_t* chunk_tab;
   int64_t c_bucket_stride;
   const int32_t* m_valid;   // optional device scalar: rows >= *m_valid are excluded from `stats`
+  int cluster;              // TN: CTAs per thread-block cluster along the split-K (z) dimension, 1 = no cluster
 };
+
+// Split-K reduction inside a thread-block cluster (TN).  The `splits` partial tiles of one output block used to be
+// reduced by float4 atomics from every CTA: ~74 CTAs finishing together and adding onto the same 128-byte sectors,
+// which L2 serialises (the epilogue cost as much as the MMA loop).  With a cluster of CL CTAs along z every CTA drains
+// its TMEM accumulator into its own shared memory, the cluster synchronises, and CTA r sums rows [r*128/CL, +128/CL) of
+// all CL partial tiles through distributed shared memory (fixed order: deterministic per cluster) and issues the
+// atomics for that slice only: CL times fewer atomics per output element.
+template <int BN>
+__device__ __forceinline__ void tn_cluster_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N,
+                                                    int64_t m0, int n0, float* __restrict__ C, int ldc,
+                                                    const float* __restrict__ bias, int accumulate, bool atomic) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+  constexpr int LDT = BN + 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  constexpr int HALF_COLS = BN / 2;
+  const int c_begin = half * HALF_COLS;
+  float* trow = ctile + (q * 32 + lane) * LDT;
+  for (int c = c_begin; c < c_begin + HALF_COLS; c += 16) {
+    float v[16];
+    if (has_acc) {
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    const int lim = min(16, c_begin + HALF_COLS - c);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      if (i < lim) *reinterpret_cast<float4*>(trow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  cluster.sync();                                   // every partial tile of the cluster is in shared memory
+  const float* peer[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) peer[r] = cluster.map_shared_rank(ctile, r < CL ? r : 0);
+  const int rows_per = TC_BM / CL, rbeg = cr * rows_per;
+  const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);
+  constexpr int QUADS = BN / 4;
+  for (int idx = tid; idx < rows_per * QUADS; idx += TC_THREADS) {
+    const int rl = idx / QUADS, c = (idx - rl * QUADS) * 4;
+    const int r = rbeg + rl;
+    const int64_t gm = m0 + r;
+    const int gn = n0 + c;
+    if (gm >= M || gn >= N) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int pr = 0; pr < 8; ++pr) {
+      if (pr < CL) {
+        const float4 w = *reinterpret_cast<const float4*>(peer[pr] + r * LDT + c);
+        v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+      }
+    }
+    float* out = C + gm * ldc + gn;
+    if (vec) {
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + gn));
+        v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+      }
+      if (atomic) {
+        atomicAdd(reinterpret_cast<float4*>(out), v);
+      } else {
+        if (accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(out);
+          v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(out) = v;
+      }
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (gn + i < N) {
+          const float o = e[i] + (bias ? __ldg(bias + gn + i) : 0.f);
+          if (atomic) atomicAdd(out + i, o);
+          else out[i] = accumulate ? out[i] + o : o;
+        }
+      }
+    }
+  }
+  cluster.sync();                                   // peers are done reading this CTA's tile
+}
 
 // =================================================================================================================
 // Generic kernel: both operands staged by threads.  NT without a workspace, and TN (transposes while staging).
@@ -233,6 +318,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
   };
 
+  // (a second register set — k-blocks it+1 and it+2 in flight — was measured: no gain, 20.4 -> 21.1 us for the
+  //  200 x 200 x E weight gradient; per k-block the 12 3xTF32 MMAs are ~0.7-0.9 us of the ~1.6 us, tools/tn_sweep.py)
   if (total > 0) prefetch();
   for (int it = 0; it < total; ++it) {
     const int st = it % TC_STAGES;
@@ -261,9 +348,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     tc_fence_after();
   }
   const bool atomic = (MODE == I3D_GEMM_TN) && p.splits > 1;
-  tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, Cout, p.ldc,
-                  (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic,
-                  MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act, nullptr, 0xffffffffu, p.m_valid);
+  bool clustered = false;
+  if constexpr (MODE == I3D_GEMM_TN) clustered = p.cluster > 1;
+  if (clustered) {
+    // (atomic unless this cluster is the only one working on the output block)
+    tn_cluster_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, Cout, p.ldc,
+                            (p.bias && blockIdx.z < (unsigned)p.cluster) ? p.bias : nullptr, p.accumulate,
+                            p.splits > p.cluster);
+  } else {
+    tc_epilogue<BN>(tmem, tiles, total > 0, M, N, m0, n0, Cout, p.ldc,
+                    (p.bias && !(atomic && blockIdx.z != 0)) ? p.bias : nullptr, p.accumulate, atomic,
+                    MODE == I3D_GEMM_NT ? p.stats : nullptr, p.stats_act, nullptr, 0xffffffffu, p.m_valid);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -300,6 +396,60 @@ static int launched(const char* what) {
   return I3D_OK;
 }
 
+// cluster launch (TN split-K reduction through distributed shared memory): CL CTAs along z per cluster
+template <typename... KArgs, typename... Args>
+static inline void launch_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    int cl, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = 1, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = (unsigned)cl;
+  ++n;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// CTAs of `kernel` (one per SM: launch bounds 1, ~170 KB of shared memory) that can be co-resident when they are
+// launched as clusters of `cl`: clusters live inside one GPC, so a few SMs per GPC stay empty (0 = query failed)
+template <typename Kern>
+static int cluster_capacity(Kern kernel, size_t smem, int cl) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(1, 1, (unsigned)cl), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = (unsigned)cl;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n * cl;
+}
+
+// I3D_TN_CLUSTER=c: largest cluster size tried for the split-K reduction of the weight-gradient GEMMs.  Default 1 (float4
+// atomics from every CTA): measured on B200 at batch 512 (tools/gemm_bench.py, us per launch, cluster 1 / 2 / 4 / 8):
+// dW 200x200 over K = E: 20.4 / 23.1 / 24.2 / 24.2; over K = N: 12.9 / 16.9 / 16.7 / 16.7; 200x800 over K = N:
+// 30.5 / 34.8 / 34.8 / 34.8; whole step 4.20 / - / 4.27 / 4.30 ms.  The atomics are not what bounds this kernel.
+static int tn_cluster_max() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("I3D_TN_CLUSTER");
+    v = e ? atoi(e) : 1;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 1;
+  }
+  return v;
+}
+
 template <int MODE, int BN>
 static int launch_generic(TcParams& p, cudaStream_t s) {
   using L = TcLayout<BN>;
@@ -308,30 +458,54 @@ static int launch_generic(TcParams& p, cudaStream_t s) {
   const int64_t gx = (p.M + TC_BM - 1) / TC_BM;
   const int gy = (p.N + BN - 1) / BN;
   int gz = 1;
+  p.cluster = 1;
   if (MODE == I3D_GEMM_TN) {
     const int K = p.seg[0].K;
-    int64_t want = (sm_count() + gx * gy - 1) / (gx * gy);          // ~one CTA per SM
-    {
-      // I3D_TN_SPLIT_DIV=d: 1/d of that (fewer, longer CTAs: less atomic traffic, SMs left to the main stream)
-      static int div = -1;
-      if (div < 0) {
-        const char* e = getenv("I3D_TN_SPLIT_DIV");
-        div = e ? atoi(e) : 1;
-        if (div < 1) div = 1;
-      }
-      want = (want + div - 1) / div;
-    }
+    const int64_t tiles = gx * gy;
     const int64_t max_splits = (K + 4 * TC_BK - 1) / (4 * TC_BK);   // at least 4 k-blocks per CTA
-    if (want > max_splits) want = max_splits;
-    if (want < 1) want = 1;
+    int64_t want = 0;
+    // largest cluster size that keeps (>= 85 % of) the split-K parallelism the machine offers without clusters
+    static int cap[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+    int64_t plain = (sm_count() + tiles - 1) / tiles;
+    if (plain > max_splits) plain = max_splits;
+    for (int cl = tn_cluster_max(); cl > 1; cl >>= 1) {
+      if (cap[cl] < 0) cap[cl] = cluster_capacity(gemm_tc_kernel<MODE, BN>, L::BYTES, cl);
+      int64_t sp = (cap[cl] / tiles / cl) * cl;
+      if (sp > max_splits) sp = (max_splits / cl) * cl;
+      if (sp >= cl && sp * 100 >= plain * 85) {
+        want = sp, p.cluster = cl;
+        break;
+      }
+    }
+    if (p.cluster == 1) {
+      want = (sm_count() + tiles - 1) / tiles;          // ~one CTA per SM
+      {
+        // I3D_TN_SPLIT_DIV=d: 1/d of that (fewer, longer CTAs: less atomic traffic, SMs left to the main stream)
+        static int div = -1;
+        if (div < 0) {
+          const char* e = getenv("I3D_TN_SPLIT_DIV");
+          div = e ? atoi(e) : 1;
+          if (div < 1) div = 1;
+        }
+        want = (want + div - 1) / div;
+      }
+      if (want > max_splits) want = max_splits;
+      if (want < 1) want = 1;
+    }
     int kchunk = (int)((K + want - 1) / want);
     kchunk = ((kchunk + TC_BK - 1) / TC_BK) * TC_BK;
     p.kchunk = kchunk;
-    p.splits = (K + kchunk - 1) / kchunk;
+    // (with a cluster the grid keeps `want` CTAs along z — a multiple of the cluster size — even when rounding the
+    //  K range per CTA up to whole k-blocks leaves the last ones without work: they contribute zero tiles)
+    p.splits = p.cluster > 1 ? (int)want : (K + kchunk - 1) / kchunk;
     gz = p.splits;
-    if (p.splits > 1 && !p.accumulate) {
+    if (p.splits > p.cluster && !p.accumulate) {
       launch(tc_zero_block_kernel, grid_for(p.M * p.N, 256), 256, 0, s, p.C, p.M, p.N, p.ldc);
       if (int rc = launched("zero")) return rc;
+    }
+    if (p.cluster > 1) {
+      launch_cluster_z(gemm_tc_kernel<MODE, BN>, dim3((unsigned)gx, gy, gz), TC_THREADS, L::BYTES, s, p.cluster, p);
+      return launched("gemm(tn, cluster)");
     }
   }
   launch(gemm_tc_kernel<MODE, BN>, dim3((unsigned)gx, gy, gz), TC_THREADS, L::BYTES, s, p);
