@@ -505,6 +505,24 @@ def case_ntxent():
             tag = "%s/B%d_C%d" % (name, B, C)
             out += [(tag + "/loss", abs(got.item() - ref.item()) / abs(ref.item()), 2e-6),
                     (tag + "/dz1", rel(ad.grad, a.grad), 2e-5), (tag + "/dz2", rel(bd.grad, b.grad), 2e-5)]
+    # with the optional regularisers (commons/losses.py:157-162, 250-258; pinned on the reference's functions by
+    # oracle/pin_regularisers.py): the CUDA loss + the regulariser terms against the oracle loss + the same terms on the CPU
+    for name, fn, C, kw in (("NTXent", O.ntxent, 1, dict(variance_reg=0.3, covariance_reg=0.2, uniformity_reg=0.1)),
+                            ("NTXentMultiplePositives", O.ntxent_multiple_positives, 3,
+                             dict(variance_reg=0.3, conformer_variance_reg=0.4))):
+        B, D = 40, 64
+        z1 = torch.randn(B, D, generator=g) * 0.8
+        z2 = torch.randn(B * C, D, generator=g) * 0.5 + 0.2 * z1.repeat_interleave(C, 0)
+        mod = getattr(i3d, name)(tau=0.1, **kw)
+        a, b = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+        ref = fn(a, b, tau=0.1) + mod.regularisers(a, b, C)
+        ref.backward()
+        ad, bd = z1.to(DEV).requires_grad_(True), z2.to(DEV).requires_grad_(True)
+        got = mod(ad, bd)
+        got.backward()
+        tag = "%s+regularisers/B%d_C%d" % (name, B, C)
+        out += [(tag + "/loss", abs(got.item() - ref.item()) / abs(ref.item()), 5e-6),
+                (tag + "/dz1", rel(ad.grad, a.grad), 2e-5), (tag + "/dz2", rel(bd.grad, b.grad), 2e-5)]
     # local rows against a gathered column set (data-parallel layout): rows 8..15 of a 24-molecule batch
     B, C, D = 24, 3, 256
     z1 = torch.randn(B, D, generator=g)

@@ -144,3 +144,26 @@ def test_pna_original_oracle_matches_reference_vectors(golden_dir):
         st = PO.init_state(c, wseed)
         z = PO.forward(O.as_leaf_params(st), c, g2, xa, ea, snorm(b["num_nodes"]), avg_d, False)
         assert np.abs(z.detach().numpy() - g["z_eval"]).max() == 0.0, name
+
+
+def test_ntxent_regularisers_match_reference_vectors(golden_dir):
+    """variance / covariance / uniformity / conformer-variance terms of NTXent and NTXentMultiplePositives
+    (commons/losses.py:157-162, 250-258, 946-964) against vectors written by the reference's own functions
+    (oracle/pin_regularisers.py): values and both gradients."""
+    import importlib
+    from oracle import pin_regularisers as P
+    L = importlib.import_module("3dinfomax_b200.losses")
+    g = np.load(os.path.join(golden_dir, "regularisers.npz"))
+    z1, z2, z2c = P.inputs()
+    for key, loss, zb, C in (("ntxent", L.NTXent(tau=0.1, **P.WEIGHTS), z2, 1),
+                             ("mp", L.NTXentMultiplePositives(tau=0.1, **P.WEIGHTS_MP), z2c, P.CASE["C"])):
+        a, b = z1.clone().requires_grad_(True), zb.clone().requires_grad_(True)
+        assert loss.has_regularisers()
+        val = loss.regularisers(a, b, C)
+        val.backward()
+        assert abs(val.item() - float(g[key])) <= 1e-6 * abs(float(g[key]))
+        for mine, ref in ((a.grad, g[key + "_dz1"]), (b.grad, g[key + "_dz2"])):
+            assert np.abs(mine.numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert not L.NTXent(tau=0.1).has_regularisers()
+    with pytest.raises(NotImplementedError):
+        L.NTXent(tau=0.1, variance_reg=0.1)._with_regularisers(torch.zeros(()), z1, z2, 1, 8, 96)
