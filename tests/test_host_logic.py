@@ -58,8 +58,10 @@ def test_unsupported_configs_fail_loudly():
         i3d.Net3D(node_dim=0, edge_dim=1, **dict(O.PRETRAIN_QM9_NET3D, reduce_func="max"))
     with pytest.raises(AssertionError):
         i3d.PNA(**dict(O.PRETRAIN_QM9_PNA, activation="not_an_activation"))
+    # regularisers are supported on one process's embeddings, rejected under data parallelism (row_offset / total_rows)
+    reg = i3d.NTXent(tau=0.1, variance_reg=1.0)
     with pytest.raises(NotImplementedError):
-        i3d.NTXent(tau=0.1, variance_reg=1.0)
+        reg._with_regularisers(torch.zeros(()), torch.zeros(4, 8), torch.zeros(4, 8), 1, 4, 16)
 
 
 def test_no_cpu_fallback():
