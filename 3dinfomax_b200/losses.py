@@ -97,3 +97,41 @@ class NTXentMultiplePositives(_NTXentBase):
             conformers = z2.shape[0] // rows
         loss = ops.ntxent(z1, z2, conformers, self.tau, self.norm, 0.0, row_offset, total_rows)
         return self._with_regularisers(loss, z1, z2, conformers, row_offset, total_rows)
+
+
+class NTXentMultiplePositivesV3(_NTXentBase):
+    """commons/losses.py:646-689 — every conformer slot u is its own NTXent term (no epsilon in the cosine):
+    l_iu = -log(p_iiu / (sum_j p_iju - p_iiu)), mean over molecules and slots = the mean over u of the single-positive
+    loss of z1 against conformer u of every molecule.  One pass of the NTXent kernels per conformer slot."""
+
+    def __init__(self, norm=True, tau=0.5, uniformity_reg=0, variance_reg=0, covariance_reg=0):
+        super().__init__(norm, tau, uniformity_reg, variance_reg, covariance_reg)
+
+    def forward(self, z1, z2, **kwargs):
+        B, D = z1.shape
+        z2v = z2.view(B, -1, D)
+        C = z2v.shape[1]
+        loss = sum(ops.ntxent(z1, z2v[:, u, :].contiguous(), 1, self.tau, self.norm, 0.0) for u in range(C)) / C
+        return self._with_regularisers(loss, z1, z2, C, 0, None)
+
+
+class NTXentMultiplePositivesV2(_NTXentBase):
+    """commons/losses.py:598-643 — positives: all conformers of the molecule, negatives: the FIRST conformer of the other
+    molecules: l_i = -log(sum_u p_iiu / sum_{j != i} p_ij0).  With the single-positive loss of z1 against conformer 0,
+    NTXent_i = -log(p_ii0 / sum_{j != i} p_ij0), this is NTXent_i - (log sum_u p_iiu - log p_ii0): the NTXent kernels
+    on conformer 0 plus a [B, C] row-wise correction (plain tensor arithmetic on B*C cosines)."""
+
+    def __init__(self, norm=True, tau=0.5, uniformity_reg=0, variance_reg=0, covariance_reg=0):
+        super().__init__(norm, tau, uniformity_reg, variance_reg, covariance_reg)
+
+    def forward(self, z1, z2, **kwargs):
+        B, D = z1.shape
+        z2v = z2.view(B, -1, D)
+        C = z2v.shape[1]
+        base = ops.ntxent(z1, z2v[:, 0, :].contiguous(), 1, self.tau, self.norm, 0.0)
+        pos = (z1[:, None, :] * z2v).sum(dim=2)
+        if self.norm:
+            pos = pos / (z1.norm(dim=1)[:, None] * z2v.norm(dim=2))
+        pos = pos / self.tau
+        loss = base - (torch.logsumexp(pos, dim=1) - pos[:, 0]).mean()
+        return self._with_regularisers(loss, z1, z2, C, 0, None)

@@ -523,6 +523,19 @@ def case_ntxent():
         tag = "%s+regularisers/B%d_C%d" % (name, B, C)
         out += [(tag + "/loss", abs(got.item() - ref.item()) / abs(ref.item()), 5e-6),
                 (tag + "/dz1", rel(ad.grad, a.grad), 2e-5), (tag + "/dz2", rel(bd.grad, b.grad), 2e-5)]
+    # NTXentMultiplePositivesV2 / V3 (commons/losses.py:598-689) against vectors of the reference's own classes
+    from oracle import pin_loss_variants as PV
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "loss_variants.npz"))
+    z1, z2 = PV.inputs()
+    for tag, cls, kw in (("v2", i3d.NTXentMultiplePositivesV2, {}), ("v3", i3d.NTXentMultiplePositivesV3, {}),
+                         ("v3_reg", i3d.NTXentMultiplePositivesV3, PV.REG)):
+        ad, bd = z1.to(DEV).requires_grad_(True), z2.to(DEV).requires_grad_(True)
+        got = cls(tau=PV.CASE["tau"], **kw)(ad, bd)
+        got.backward()
+        out += [("NTXentMultiplePositives_%s/loss_vs_reference" % tag,
+                 abs(got.item() - float(gold[tag])) / abs(float(gold[tag])), 5e-6),
+                ("NTXentMultiplePositives_%s/dz1_vs_reference" % tag, rel(ad.grad, gold[tag + "_dz1"]), 2e-5),
+                ("NTXentMultiplePositives_%s/dz2_vs_reference" % tag, rel(bd.grad, gold[tag + "_dz2"]), 2e-5)]
     # local rows against a gathered column set (data-parallel layout): rows 8..15 of a 24-molecule batch
     B, C, D = 24, 3, 256
     z1 = torch.randn(B, D, generator=g)

@@ -167,3 +167,22 @@ def test_ntxent_regularisers_match_reference_vectors(golden_dir):
     assert not L.NTXent(tau=0.1).has_regularisers()
     with pytest.raises(NotImplementedError):
         L.NTXent(tau=0.1, variance_reg=0.1)._with_regularisers(torch.zeros(()), z1, z2, 1, 8, 96)
+
+
+def test_ntxent_v2_v3_composition_matches_reference_vectors(golden_dir):
+    """NTXentMultiplePositivesV2 / V3 (commons/losses.py:598-689): the composition around the NTXent kernels, with the CPU
+    oracle's single-positive loss standing in for them, against vectors written by the reference's own classes."""
+    import importlib
+    from oracle import pin_loss_variants as P
+    L = importlib.import_module("3dinfomax_b200.losses")
+    g = np.load(os.path.join(golden_dir, "loss_variants.npz"))
+    z1, z2 = P.inputs()
+    for tag, cls, kw in (("v2", L.NTXentMultiplePositivesV2, {}), ("v3", L.NTXentMultiplePositivesV3, {}),
+                         ("v3_reg", L.NTXentMultiplePositivesV3, P.REG)):
+        a, b = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+        with P.cpu_stand_in():
+            val = cls(tau=P.CASE["tau"], **kw)(a, b)
+        val.backward()
+        assert abs(val.item() - float(g[tag])) <= 2e-6 * abs(float(g[tag]))
+        assert np.abs(a.grad.numpy() - g[tag + "_dz1"]).max() <= 2e-5 * np.abs(g[tag + "_dz1"]).max()
+        assert np.abs(b.grad.numpy() - g[tag + "_dz2"]).max() <= 2e-5 * np.abs(g[tag + "_dz2"]).max()
