@@ -533,7 +533,7 @@ def case_ntxent():
         got = cls(tau=PV.CASE["tau"], **kw)(ad, bd)
         got.backward()
         out += [("NTXentMultiplePositives_%s/loss_vs_reference" % tag,
-                 abs(got.item() - float(gold[tag])) / abs(float(gold[tag])), 5e-6),
+                 abs(got.item() - float(gold[tag])), 5e-6),      # absolute: V2 is a difference of two O(1) terms
                 ("NTXentMultiplePositives_%s/dz1_vs_reference" % tag, rel(ad.grad, gold[tag + "_dz1"]), 2e-5),
                 ("NTXentMultiplePositives_%s/dz2_vs_reference" % tag, rel(bd.grad, gold[tag + "_dz2"]), 2e-5)]
     # local rows against a gathered column set (data-parallel layout): rows 8..15 of a 24-molecule batch
