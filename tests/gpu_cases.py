@@ -511,8 +511,10 @@ def case_ntxent():
                             ("NTXentMultiplePositives", O.ntxent_multiple_positives, 3,
                              dict(variance_reg=0.3, conformer_variance_reg=0.4))):
         B, D = 40, 64
-        z1 = torch.randn(B, D, generator=g) * 0.8
-        z2 = torch.randn(B * C, D, generator=g) * 0.5 + 0.2 * z1.repeat_interleave(C, 0)
+        # (small embeddings: the uniformity term is log mean exp(-2 ||x_i - x_j||^2), which underflows to log(0) in fp32
+        #  — in the reference as well — once the squared distances pass ~45)
+        z1 = torch.randn(B, D, generator=g) * 0.25
+        z2 = torch.randn(B * C, D, generator=g) * 0.2 + 0.2 * z1.repeat_interleave(C, 0)
         mod = getattr(i3d, name)(tau=0.1, **kw)
         a, b = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
         ref = fn(a, b, tau=0.1) + mod.regularisers(a, b, C)
