@@ -21,6 +21,17 @@
 #include <cstdlib>
 #include <type_traits>
 
+namespace i3d {
+__device__ unsigned long long g_ws_dbg[16];     // cycle counters of the -DI3D_WS_DEBUG build (see below)
+__device__ long long g_ws_dbg_t0;
+}
+#ifdef I3D_WS_DEBUG
+// epilogue phase marks of CTA (0,0), thread 0: cycles since the epilogue started at [9] tile in shared memory,
+// [10] statistics done, [11] stores issued
+#define I3D_TC_EPI_MARK(slot)                                                                     \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)                                     \
+  atomicAdd(&::i3d::g_ws_dbg[slot], (unsigned long long)(clock64() - ::i3d::g_ws_dbg_t0))
+#endif
 #include "i3d_tc.cuh"
 
 namespace i3d {
@@ -43,7 +54,6 @@ constexpr int WS_PREFETCH = I3D_WS_PREFETCH;   // k-blocks of A held in register
 // adds the clock64() cycles each role spends blocked on each barrier.  [0] kernel total, [1] MMA waits a_full,
 // [2] MMA waits b_full, [3] MMA issue, [4] TMA producer waits mma_done, [5] stager warp 0 waits mma_done,
 // [6] stager warp 0 total main loop, [7] epilogue, [8] launches
-__device__ unsigned long long g_ws_dbg[16];
 #ifdef I3D_WS_DEBUG
 #define WS_DBG_T0() const long long dbg_t0__ = clock64()
 #define WS_DBG_ADD(slot) if (dbg_on) atomicAdd(&g_ws_dbg[slot], (unsigned long long)(clock64() - dbg_t0__))
@@ -342,6 +352,8 @@ __global__ void __launch_bounds__(WS_THREADS, OCC) gemm_tc_nt_ws_kernel(const __
   __syncthreads();      // every role has left the operand ring before it is reused as the output tile
 #ifdef I3D_WS_DEBUG
   const long long dbg_epi_t0 = clock64();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_ws_dbg_t0 = dbg_epi_t0;
+  __syncthreads();
 #endif
   tc_epilogue<BN, WS_STAGER_THREADS>(tmem, tiles, total > 0, M, N, m0, n0, p.C, p.ldc, p.bias, p.accumulate, false,
                                      p.stats, p.stats_act, row_map, L::DUAL ? tmem + L::ACC_COLS : 0xffffffffu,

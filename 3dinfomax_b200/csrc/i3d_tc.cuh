@@ -149,6 +149,11 @@ struct TcLayout {
 // ---- epilogue shared by all tensor-core kernels -----------------------------------------------------------------
 // TMEM -> registers (tcgen05.ld 32x32b: warp w owns lanes [32*(w&3), +32) and column half w>>2) -> row-major tile in
 // shared memory (the operand stages are dead by now) -> coalesced float4 stores / vector atomics to global.
+// phase timers of the epilogue (only the -DI3D_WS_DEBUG build of the warp-specialised NT kernel defines them)
+#ifndef I3D_TC_EPI_MARK
+#define I3D_TC_EPI_MARK(slot)
+#endif
+
 template <int BN, int NTHR = TC_THREADS>
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool has_acc, int64_t M, int N, int64_t m0,
                                             int n0, float* __restrict__ C, int ldc, const float* __restrict__ bias,
@@ -191,6 +196,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       if (i < lim) *reinterpret_cast<float4*>(trow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
   __syncthreads();
+  I3D_TC_EPI_MARK(9);
   if (stats) {
     // fused FCLayer statistics (models/base_layers.py:102-110): column sums of act(y) and act(y)^2 over the valid rows
     // of this tile, accumulated in fp64 (BatchNorm inputs with mean^2 >> var), one atomic pair per column and CTA
@@ -200,7 +206,10 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
     for (int c = tid; tid < NTHR && c < BN; c += NTHR) {
       if (n0 + c >= N) continue;
       const float b = bias ? __ldg(bias + n0 + c) : 0.f;
-      // four independent fp64 chains (the loop is bound by the DADD/DFMA dependency, not by the shared-memory reads)
+      // four independent fp64 chains (the loop is bound by the DADD/DFMA dependency, not by the shared-memory reads).
+      // Measured with the I3D_WS_DEBUG counters: 4.3 k cycles per 128 x 208 tile (F2F + DADD + DFMA per element on the
+      // fp64 pipe).  Summing groups of 4 rows in fp32 first would cut that ~3x, but the squares must stay exact: Net3D's
+      // BatchNorm inputs have mean^2 >> var, and fp32 partial sums of h^2 put ~1e-4 relative error on the variance.
       double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
       int r = 0;
       for (; r + 4 <= rows; r += 4) {
@@ -222,6 +231,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       atomicAdd(stats + (int64_t)(N + n0 + c) * I3D_STATS_STRIDE, (s2[0] + s2[1]) + (s2[2] + s2[3]));
     }
   }
+  I3D_TC_EPI_MARK(10);
   const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && ((N & 3) == 0);
   constexpr int QUADS = BN / 4;
   for (int idx = tid; tid < NTHR && idx < TC_BM * QUADS; idx += NTHR) {
@@ -262,6 +272,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, float* ctile, bool ha
       }
     }
   }
+  I3D_TC_EPI_MARK(11);
 }
 
 }  // namespace i3d

@@ -87,7 +87,8 @@ def main():
         import ctypes
         L = importlib.import_module("3dinfomax_b200.lib").load()
         names = ["kernel_total", "mma_wait_a_full", "mma_wait_b_full", "mma_issue", "tma_wait_mma_done",
-                 "stager_wait_mma_done", "stager_main_loop", "epilogue", "launches"]
+                 "stager_wait_mma_done", "stager_main_loop", "epilogue", "launches", "epi_tile_in_smem", "epi_stats_done",
+                 "epi_stores_issued"]
 
         def counters(tag, fn):
             buf = (ctypes.c_ulonglong * 16)()
@@ -98,7 +99,8 @@ def main():
             torch.cuda.synchronize()
             L.i3d_gemm_debug_counters(buf)
             n = max(int(buf[8]), 1)
-            print(tag, {k: int(buf[i]) // n for i, k in enumerate(names[:8])}, "launches", int(buf[8]), flush=True)
+            print(tag, {k: int(buf[i]) // n for i, k in enumerate(names) if k != "launches"}, "launches", int(buf[8]),
+                  flush=True)
 
         counters("merged_K1000", lambda: K.gemm_nt_bucketed(st.plan, F, msegs, Yn, b, merged.fwd_hi, merged.fwd_lo, stats_act=0))
         counters("edge_fc1_K600", lambda: K.gemm(K.NT, E, F, segs1, Ye, bias=b, stats_act=1))

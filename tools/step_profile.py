@@ -2,6 +2,7 @@
 """In-situ per-kernel GPU time of the pre-training step (warm caches, real launch order) via torch.profiler (CUPTI).
 
     python tools/step_profile.py [--batch 512] [--steps 5] [--mode eager|graph] > gpurun_out/step_profile.txt
+    ncu --nvtx --nvtx-include "timed_step/" ... python tools/step_profile.py --nvtx     # one eager step inside an NVTX range
 
 ncu serialises launches and flushes caches before each one, so its per-launch times overstate kernels whose inputs
 are L2-resident in the real step; this table is what the step actually spends.  Not a bench: no number printed here
@@ -23,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--mode", default="eager", choices=["eager", "graph"])
+    ap.add_argument("--nvtx", action="store_true", help="no CUPTI profile: one step inside the NVTX range 'timed_step' (for ncu)")
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -59,6 +61,12 @@ def main():
     for i in range(3):
         step(i)
     torch.cuda.synchronize()
+    if args.nvtx:
+        torch.cuda.nvtx.range_push("timed_step")
+        step(3)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for i in range(args.steps):
             step(i)
