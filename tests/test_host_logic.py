@@ -238,3 +238,38 @@ def test_fold_batch_norm_algebra():
     f = inf.fold_batch_norm(pna)
     assert f.folded_batch_norms == 22 and not any("batch_norm" in k for k in f.state_dict())
     assert any("batch_norm" in k for k in pna.state_dict())          # the original is untouched
+
+
+def test_supervised_trainer_parameter_groups_follow_the_reference():
+    """trainer/trainer.py:216-238: BatchNorm (no weight decay) / new / transferred (own lr) / frozen (lr 0), in this order;
+    transfer_layers ['gnn'] with exclude_from_transfer ['batch_norm'] as in configs_clean/tune_QM9_homo.yml"""
+    cfg = importlib.import_module("3dinfomax_b200.configs")
+    T = importlib.import_module("3dinfomax_b200.trainer")
+    model = i3d.PNA(avg_d=1, **cfg.TUNE_QM9_HOMO_MODEL_PARAMETERS)
+    tr = object.__new__(T.Trainer)                       # the grouping is host logic; the constructor needs a GPU
+    tr.model, tr.model3d = model, None
+    tr.transfer_layers, tr.exclude_from_transfer = ("gnn",), ("batch_norm",)
+    tr.frozen_layers, tr.transferred_lr = ("output.fully_connected.1",), 1e-5
+    named = list(model.named_parameters())
+    groups = tr.param_groups(named, {"lr": 7e-5, "weight_decay": 1e-11})
+    ids = lambda ps: {id(p) for p in ps}
+    by_name = dict(named)
+    assert [sorted(k for k in g if k != "params") for g in groups] == [["weight_decay"], [], ["lr"], ["lr"]]
+    bn, new, transferred, frozen = (ids(g["params"]) for g in groups)
+    assert groups[0]["weight_decay"] == 0 and groups[2]["lr"] == 1e-5 and groups[3]["lr"] == 0
+    for k, p in by_name.items():
+        in_gnn = "gnn" in k
+        is_bn = "batch_norm" in k
+        is_frozen = "output.fully_connected.1" in k
+        want = {"transferred": in_gnn and not is_bn, "frozen": is_frozen,
+                "bn": is_bn and not is_frozen, "new": not (in_gnn and not is_bn) and not is_bn and not is_frozen}
+        assert (id(p) in transferred) == want["transferred"], k
+        assert (id(p) in frozen) == want["frozen"], k
+        assert (id(p) in bn) == want["bn"], k
+        assert (id(p) in new) == want["new"], k
+    # every parameter is optimised exactly once
+    assert sum(len(g["params"]) for g in groups) == len(named)
+    # the contrastive trainer keeps the two groups of trainer/self_supervised_trainer.py:78-86
+    ss = object.__new__(T.SelfSupervisedTrainer)
+    g2 = ss.param_groups(named, {"lr": 8e-5})
+    assert len(g2) == 2 and g2[0]["weight_decay"] == 0 and ids(g2[0]["params"]) == {id(p) for k, p in named if "batch_norm" in k}
