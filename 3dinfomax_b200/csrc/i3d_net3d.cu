@@ -101,6 +101,27 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
     y[i] = __fadd_rn(a[i], b[i]);
 }
 
+// y[m, :] = a[m, :] + b[m, :] for row-major matrices with their own leading dimensions (V floats per thread)
+template <int V>
+__global__ void add_rows_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, int64_t M,
+                                int F, float* __restrict__ y, int ldy) {
+  pdl_grid_sync();
+  const int FV = F / V;
+  const int64_t total = M * FV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / FV;
+    const int c = (int)(t - m * FV) * V;
+    if (V == 4) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(a + m * lda + c));
+      const float4 w = __ldg(reinterpret_cast<const float4*>(b + m * ldb + c));
+      *reinterpret_cast<float4*>(y + m * ldy + c) =
+          make_float4(__fadd_rn(u.x, w.x), __fadd_rn(u.y, w.y), __fadd_rn(u.z, w.z), __fadd_rn(u.w, w.w));
+    } else {
+      y[m * ldy + c] = __fadd_rn(a[m * lda + c], b[m * ldb + c]);
+    }
+  }
+}
+
 }  // namespace i3d
 
 using namespace i3d;
@@ -139,6 +160,19 @@ int i3d_broadcast_rows(const float* vec, int64_t M, int F, float* out, void* str
   I3D_REQUIRE(M >= 0 && F > 0 && vec && (M == 0 || out), "invalid argument");
   if (M == 0) return I3D_OK;
   launch(broadcast_rows_kernel, grid_for(M * F, 256), 256, 0, as_stream(stream), vec, M, F, out);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_add_rows(const float* a, int lda, const float* b, int ldb, int64_t M, int F, float* y, int ldy, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && lda >= F && ldb >= F && ldy >= F && (M == 0 || (a && b && y)), "invalid argument");
+  if (M == 0) return I3D_OK;
+  const bool v4 = !(F & 3) && !(lda & 3) && !(ldb & 3) && !(ldy & 3) &&
+                  !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15u);
+  if (v4)
+    launch(add_rows_kernel<4>, grid_for(M * (F / 4), 256), 256, 0, as_stream(stream), a, lda, b, ldb, M, F, y, ldy);
+  else
+    launch(add_rows_kernel<1>, grid_for(M * F, 256), 256, 0, as_stream(stream), a, lda, b, ldb, M, F, y, ldy);
   I3D_LAUNCHED();
   return I3D_OK;
 }

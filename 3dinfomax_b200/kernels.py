@@ -741,6 +741,18 @@ def add(a, b):
     return y
 
 
+def add_rows(a, b):
+    """a + b for two [M, F] fp32 matrices that may be column slices of wider buffers (unit column stride)"""
+    pa, lda = _mat(a, "a")
+    pb, ldb = _mat(b, "b")
+    M, F = a.shape
+    if tuple(b.shape) != (M, F):
+        raise ValueError("add_rows: shapes differ")
+    y = torch.empty(M, F, dtype=torch.float32, device=a.device)
+    _lib.check(_L().i3d_add_rows(pa, lda, pb, ldb, M, F, _p(y), F, _s()), "i3d_add_rows")
+    return y
+
+
 # ------------------------------------------------------------------------------------------ loss
 def row_norms(z):
     _vec(z, torch.float32, "z")

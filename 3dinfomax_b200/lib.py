@@ -114,6 +114,7 @@ SIGNATURES = {
     "i3d_broadcast_rows": (_I, [_P, _L, _I, _P, _P]),
     "i3d_colsum": (_I, [_P, _I, _L, _I, _P, _P]),
     "i3d_add": (_I, [_P, _P, _L, _P, _P]),
+    "i3d_add_rows": (_I, [_P, _I, _P, _I, _L, _I, _P, _I, _P]),
     "i3d_row_norms": (_I, [_P, _L, _I, _P, _P]),
     "i3d_ntxent_rows_fwd": (_I, [_P, _L, _L, _I, _P, _P, _I, _F, _F, _L, _P, _P, _P]),
     "i3d_contrastive_metrics": (_I, [_P, _L, _P, _P, _F, _P, _P, _P]),

@@ -183,7 +183,7 @@ class _FC(torch.autograd.Function):
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
                                                    need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
-                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
+                db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:
             # (padded batches: the pass also writes the exact zeros of the padding rows)
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
@@ -305,6 +305,7 @@ class _FCPostMerged(torch.autograd.Function):
                 O = K.add(O, residual)
         ctx.cfg, ctx.plan, ctx.merged, ctx.w_param = cfg, plan, merged, W
         ctx.has_res = residual is not None
+        ctx.res_is_h = residual is h
         ctx.save_for_backward(W, Y, save, gamma, h, agg)
         return O
 
@@ -329,7 +330,7 @@ class _FCPostMerged(torch.autograd.Function):
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
                                                    need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
-                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
+                db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:
@@ -358,6 +359,10 @@ class _FCPostMerged(torch.autograd.Function):
                                merged.bwd_lo)
             dh, dagg = buf[:, :F], buf[:, F:]
         dres = dO if (ctx.has_res and ctx.needs_input_grad[7]) else None
+        if dres is not None and dh is not None and ctx.res_is_h:
+            # the residual IS the layer input h (models/pna.py:211): both gradients go to the same tensor, summed here by
+            # one kernel instead of autograd's strided add (dh is a column slice of the [N, 5F] buffer)
+            dh, dres = K.add_rows(dh, dres), None
         return None, None, None, dW, db, dgamma, dbeta, dres, dh, dagg
 
 
@@ -484,7 +489,7 @@ class _FCEdgeFactored(torch.autograd.Function):
             dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
                                                    need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
-                db = dbz.view(Fout, K.DBIAS_STRIDE)[:, 0]
+                db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:
             dY, db, _, _ = K.bn_bwd_apply(dO, Y, cfg.act, False, False, None, None, None, need_b, valid=cfg.valid)
         else:

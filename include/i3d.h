@@ -405,6 +405,10 @@ int i3d_broadcast_rows(const float* vec, int64_t M, int F, float* out, void* str
 int i3d_colsum(const float* x, int ldx, int64_t M, int F, float* out, void* stream);
 /* y = a + b (n elements) */
 int i3d_add(const float* a, const float* b, int64_t n, float* y, void* stream);
+/* y[m, :F] = a[m, :F] + b[m, :F], every matrix with its own leading dimension: the gradient of a layer input that arrives
+ * through two paths of ONE backward node — the residual `+ h` and the first K-segment of the posttrans GEMM, a column
+ * slice of the [N, 5F] dx buffer (models/pna.py:207-211) — summed without a strided framework kernel */
+int i3d_add_rows(const float* a, int lda, const float* b, int ldb, int64_t M, int F, float* y, int ldy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * NTXent / NTXentMultiplePositives  [commons/losses.py:143-155, 225-246]
