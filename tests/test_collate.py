@@ -56,3 +56,40 @@ def test_store_layout_and_batch_metadata():
 def test_store_requires_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         C.PackedMoleculeStore(syn.make_store(1, 3), "cpu")
+
+
+def test_bucket_ladder_covers_an_epoch_with_few_levels():
+    """trainer.BucketLadder is host logic over the store's per-molecule sizes: capacities are aligned and monotone,
+    level_of returns the tightest level that holds a batch, and a shuffled epoch of QM9-shaped batches needs only a
+    handful of levels (the number of CUDA graphs a training run captures)."""
+    import types
+    T = importlib.import_module("3dinfomax_b200.trainer")
+    store = syn.make_store(3, 4096, "qm9")
+    n_atoms = np.asarray(store["n_atoms"], dtype=np.int64)
+    n_edges = np.diff(np.asarray(store["edge_slices"], dtype=np.int64))
+    stub = types.SimpleNamespace(n_atoms=n_atoms, n_edges=n_edges)
+    B = 512
+    lad = T.BucketLadder(stub, B, conformers=1)
+    caps = [lad.caps(k) for k in range(6)]
+    for k, c in enumerate(caps):
+        assert all(int(x) % 128 == 0 for x in c)
+        if k:
+            assert all(a >= b for a, b in zip(c, caps[k - 1]))
+    rng = np.random.default_rng(0)
+    levels = []
+    for _ in range(5):
+        perm = rng.permutation(len(n_atoms))
+        for i in range(0, len(perm) - B + 1, B):
+            ix = perm[i:i + B]
+            n = n_atoms[ix]
+            sizes = (int(n.sum()), int(n_edges[ix].sum()), int((n * (n - 1)).sum()))
+            lv = lad.level_of(sizes)
+            assert all(s <= c for s, c in zip(sizes, lad.caps(lv)))                 # the level holds the batch
+            assert lv == 0 or any(s > c for s, c in zip(sizes, lad.caps(lv - 1)))   # ... and is the tightest one
+            levels.append(lv)
+    assert max(levels) <= 4 and np.mean(np.asarray(levels) == 0) > 0.6
+    # padding of the common level stays small
+    assert lad.caps(0)[0] <= 1.05 * B * n_atoms.mean() + 128
+    # three conformers per molecule triple the 3-D edge capacity only
+    lad3 = T.BucketLadder(stub, B, conformers=3)
+    assert lad3.caps(0)[:2] == lad.caps(0)[:2] and lad3.caps(0)[2] > 2.5 * lad.caps(0)[2]
