@@ -26,3 +26,12 @@ TUNE_QM9_HOMO_MODEL_PARAMETERS = dict(
 
 TUNE_QM9_HOMO = dict(loss_func="L1Loss", optimizer="Adam", optimizer_params={"lr": 7.0e-5, "weight_decay": 1.0e-11},
                      batch_size=128, model_type="PNA", transfer_layers=["gnn"], exclude_from_transfer=["batch_norm"])
+
+# The tower PNA in the shape BASELINE.json configs[1] words ("hidden 200, 4 towers, 4 layers"): models/pna_original.py
+# with the contrastive settings of the reference's tower configs, inputs divided between the towers
+PNA_ORIGINAL_H200_T4_MODEL_PARAMETERS = dict(
+    target_dim=256, hidden_dim=200, last_layer_dim=200, mid_batch_norm=True, last_batch_norm=True, graph_norm=False,
+    readout_batchnorm=True, edge_hidden_dim=200, readout_hidden_dim=100, readout_layers=2, dropout=0.0,
+    in_feat_dropout=0.0, propagation_depth=4, towers=4, divide_input_first=True, divide_input_last=True,
+    aggregators=["mean", "max", "min", "std"], scalers=["identity", "amplification", "attenuation"],
+    readout_aggregators=["mean", "max", "min", "sum"], pretrans_layers=1, posttrans_layers=1, residual=True)

@@ -79,6 +79,9 @@ def parse_args():
     p.add_argument("--store-size", type=int, default=0, help="molecules in the synthetic dataset store")
     p.add_argument("--mode", default="bucketed", choices=["bucketed", "eager"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--towers", action="store_true",
+                   help="2-D encoder = PNAOriginal(hidden 200, 4 towers, 4 layers), the tower shape configs[1] words; "
+                        "eager launches (its column-sliced tower GEMMs run on the fp32 SIMT kernel)")
     return p.parse_args()
 
 
@@ -93,7 +96,11 @@ def config_dict(args, world):
     """identical in both arms (the driver compares them)"""
     c = CONFIGS[args.config]
     B = per_gpu_batch(args, world)
-    return {"workload": c["name"] % B, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+    name = c["name"] % B
+    if getattr(args, "towers", False):
+        name = ("configs[1] as worded: PNAOriginal(hidden 200, 4 towers, 4 layers; models/pna_original.py)+Net3D(hidden 20) "
+                "NTXent(tau 0.1) Adam, QM9-shaped synthetic, batch %d per GPU, eager launches" % B)
+    return {"workload": name, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
             "conformers": c["conformers"], "loss": c["loss"], "molecules": c["shape"] + "-shaped synthetic",
             "batches": "a fresh random index set every step (distinct N/E/E3), collate inside the timed region",
             "l2": "every step touches a different batch; per-step working set (activations ~1 GB at batch 512) exceeds "
@@ -319,7 +326,12 @@ def run_b200(args):
         tr = i3d.Trainer(pna, torch.nn.L1Loss(), dev, dict(cfg.TUNE_QM9_HOMO["optimizer_params"]), process_group=pg,
                          graph_safe=bucketed)
     else:
-        pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
+        if args.towers:
+            if bucketed or C != 1:
+                raise RuntimeError("--towers runs with --mode eager and one conformer per molecule")
+            pna = i3d.PNAOriginal(avg_d=1.0, device=dev, **cfg.PNA_ORIGINAL_H200_T4_MODEL_PARAMETERS)
+        else:
+            pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)
         n3 = i3d.Net3D(node_dim=0, edge_dim=1, avg_d=1, **cfg.PRETRAIN_QM9_MODEL3D_PARAMETERS)
         tr = i3d.SelfSupervisedTrainer(pna, n3, getattr(i3d, c["loss"])(tau=TAU), dev, {"lr": LR}, process_group=pg,
                                        graph_safe=bucketed)
@@ -363,6 +375,11 @@ def run_b200(args):
         if finetune:
             y = store.targets.index_select(0, torch.from_numpy(ix).to(dev))
             loss, _, _ = tr.process_batch(([g2], y))
+        elif args.towers:
+            # snorm_n of the reference's tower collate: 1 / sqrt(number of atoms of the node's molecule)
+            nn_ = g2.batch_num_nodes()
+            snorm = torch.repeat_interleave(nn_.float().rsqrt(), nn_, output_size=g2.number_of_nodes()).unsqueeze(1)
+            loss, _, _ = tr.process_batch(([g2, snorm], [g3]))
         else:
             loss, _, _ = tr.process_batch(([g2], [g3]))
         return loss
@@ -491,7 +508,8 @@ def run_b200(args):
                         "frac": gbs(b_b, t_b) / hbm, "traffic": AGG_TRAFFIC.get("bwd"),
                         "algorithmic_bytes_per_launch": b_b, "us_per_launch": t_b * 1e3,
                         "warm": {"us_per_launch": t_bw * 1e3, "frac": gbs(b_b, t_bw) / hbm}},
-                "launches_per_step": {"fwd": len(pna.node_gnn.mp_layers), "bwd": len(pna.node_gnn.mp_layers)},
+                "launches_per_step": {"fwd": len(getattr(pna.node_gnn, "mp_layers", getattr(pna.node_gnn, "layers", []))),
+                                      "bwd": len(getattr(pna.node_gnn, "mp_layers", getattr(pna.node_gnn, "layers", [])))},
                 "gemm": gemm_roof,
                 "how": "40 launches per CUDA graph on a timed batch's CSR (N=%d, E=%d, F=%d), 20 replays between two "
                        "CUDA events on the launch stream; achieved = cold (rotating over 8 buffer sets > L2), warm = "
@@ -511,10 +529,11 @@ def run_b200(args):
                            "bn": "local per-rank batch statistics", "last_loss": float(last_loss)},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                        "what": "BucketedStep.step(idx) + loss.item() per step: pinned-host metadata (molecule indices + "
-                                "offsets) -> device, device collate from the HBM-resident store, step, loss -> host"},
+                        "what": ("BucketedStep.step(idx)" if bucketed else "store.collate(idx) + trainer.process_batch") +
+                                " + loss.item() per step: pinned-host metadata (molecule indices + offsets) -> device, "
+                                "device collate from the HBM-resident store, step, loss -> host"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roof}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not args.towers:
             cores = os.cpu_count() or 1
             nb = min(B, 512)
             val, per, threads = cpu_oracle_throughput(args, nb, 5, 1, cores)
