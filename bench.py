@@ -526,7 +526,7 @@ def run_b200(args):
                            "distinct_batch_shapes_in_timed_loop": len(shapes), "store_molecules": M,
                            "bucket_levels_used": levels_used, "graphs_captured": captures, "eager_steps": eager_steps,
                            "host_wall_ms_per_step": wall / args.steps * 1e3,
-                           "bn": "local per-rank batch statistics", "last_loss": float(last_loss)},
+                           "bn": "local per-rank batch statistics", "last_loss": float(last_loss.detach())},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                         "what": ("BucketedStep.step(idx)" if bucketed else "store.collate(idx) + trainer.process_batch") +
