@@ -12,10 +12,20 @@ cat[h_t[src], h_t[dst], e] (rows emitted in CSR order), the fused multi-aggregat
 posttrans MLP runs over the virtual cat[h_t, A, A*amp, A*att] with amp = ln(D+1)/avg_d, att = avg_d/ln(D+1) (the
 SCALAR avg_d of this model, :28-35), then ``* snorm_n`` when ``graph_norm``.  Towers read column slices of ``h``
 in place (``divide_input``) — the slices are views, the GEMM loader takes their leading dimension.  Tower widths of
-the shipped configs (14 = 70/5, 50 = 200/4) are not multiples of 4, so these GEMMs take the fp32 SIMT kernel; the
-path is correctness-complete, not tuned.
+the shipped configs (14 = 70/5, 50 = 200/4) are not multiples of 4, so tower-by-tower these GEMMs take the fp32 SIMT
+kernel.
+
+Fused towers (default when the layer divides its input between >1 towers of single-FC MLPs and the total widths are
+multiples of 4, i.e. the "hidden 200, 4 towers" shape): T towers over disjoint column slices are ONE layer with
+block-diagonal weights.  The per-tower parameters stay what they are (state-dict parity); every step assembles
+``W_pre [F, 2F + Fe]`` and ``W_post [F_out, 13F]`` from them (two einsums against the TxT identity, differentiable, so
+the block gradients flow back to the tower parameters), and the layer runs as one tensor-core GEMM each over the full
+width — the aggregation and BatchNorm are column-wise, so concatenated towers are exactly the per-tower results.  The
+towers' BatchNorm buffers are re-homed as views of one [F_out] buffer (same keys, same values).  This path also takes
+the shape-bucketed (padded) batches of trainer.BucketedStep.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -114,7 +124,86 @@ class PNALayer(nn.Module):
         _linear_default_init(self.mixing_network, out_dim)
         self._leaky = activation_code("leakyrelu")
 
+    # ---- fused towers -------------------------------------------------------------------------------------
+    fuse_towers = True          # class default; set False on an instance (or I3D_TOWERS=loop) for the tower-by-tower path
+
+    def _fusable(self):
+        t0 = self.towers[0]
+        return (self.fuse_towers and os.environ.get("I3D_TOWERS", "fused") != "loop" and self.divide_input
+                and len(self.towers) > 1 and self.in_dim % 4 == 0 and self.out_dim % 4 == 0
+                and len(t0.pretrans.fully_connected) == 1 and len(t0.posttrans.fully_connected) == 1)
+
+    def _fused_bn(self, fcs, tag):
+        """(gamma, beta, running_mean, running_var, nbt, momentum, eps) over the concatenated towers, or None.  The
+        per-tower buffers become views of shared storage the first time (and again after a ``.to()`` replaced them)."""
+        bns = [fc.batch_norm for fc in fcs]
+        if bns[0] is None:
+            return None
+        T, w = len(bns), bns[0].running_mean.numel()
+        big = self.__dict__.get("_bn_big_" + tag)
+        ok = big is not None and big["rm"].device == bns[0].running_mean.device and all(
+            bn.running_mean.data_ptr() == big["rm"].data_ptr() + 4 * t * w
+            and bn.running_var.data_ptr() == big["rv"].data_ptr() + 4 * t * w
+            and bn.num_batches_tracked.data_ptr() == big["nbt"].data_ptr() + 8 * t for t, bn in enumerate(bns))
+        if not ok:
+            with torch.no_grad():
+                big = {"rm": torch.cat([bn.running_mean.reshape(-1) for bn in bns]).contiguous(),
+                       "rv": torch.cat([bn.running_var.reshape(-1) for bn in bns]).contiguous(),
+                       "nbt": torch.stack([bn.num_batches_tracked.reshape(()) for bn in bns]).contiguous()}
+                for t, bn in enumerate(bns):
+                    bn._buffers["running_mean"] = big["rm"][t * w:(t + 1) * w]
+                    bn._buffers["running_var"] = big["rv"][t * w:(t + 1) * w]
+                    bn._buffers["num_batches_tracked"] = big["nbt"][t]
+            self.__dict__["_bn_big_" + tag] = big
+        gamma = torch.cat([bn.weight for bn in bns])
+        beta = torch.cat([bn.bias for bn in bns])
+        return (gamma, beta, big["rm"], big["rv"], big["nbt"][0], bns[0].momentum, bns[0].eps)
+
+    def _block_diagonal(self, Ws, blocks, width):
+        """[T, rows, blocks * width] tower weights -> [T * rows, blocks * T * width]: block b of tower t lands on the
+        columns of tower t inside block b of the full-width operand (zeros elsewhere)"""
+        T, rows = Ws.shape[0], Ws.shape[1]
+        eye = torch.eye(T, dtype=Ws.dtype, device=Ws.device)
+        return torch.einsum("tobf,ts->tobsf", Ws.reshape(T, rows, blocks, width), eye).reshape(T * rows,
+                                                                                             blocks * T * width)
+
+    def _forward_fused(self, st, scalers, h, ef_csr, snorm_n):
+        T, ft, ot = len(self.towers), self.input_tower, self.output_tower
+        pre = [tw.pretrans.fully_connected[0] for tw in self.towers]
+        post = [tw.posttrans.fully_connected[0] for tw in self.towers]
+        t0 = self.towers[0]
+        # pretrans (:207-221): cat[h_t[src], h_t[dst], e] W_t^T for all towers = cat[h[src], h[dst], e] W_pre^T
+        Wp = torch.stack([fc.linear.weight for fc in pre])                   # [T, ft, 2 ft (+ Fe)]
+        W_pre = self._block_diagonal(Wp[:, :, :2 * ft], 2, ft)
+        segs = [ops.Seg(h, idx=st.src_csr, inv_rowptr=st.out_rowptr, inv_idx=st.out_pos),
+                ops.Seg(h, idx=st.dst_csr, inv_rowptr=st.rowptr)]
+        if t0.edge_features:
+            W_pre = torch.cat([W_pre, Wp[:, :, 2 * ft:].reshape(T * ft, -1)], dim=1)
+            segs.append(ops.Seg(ef_csr))
+        b_pre = torch.cat([fc.linear.bias for fc in pre])
+        msg = ops.fc(segs, W_pre.contiguous(), b_pre, pre[0].act, self._fused_bn(pre, "pre"), self.training, None,
+                     st.e_valid)
+        agg = ops.pna_aggregate(msg, st.rowptr)                              # :232-237, [N, 4 F], tower-major columns
+        amp, att = scalers
+        # posttrans (:252-255): 13 blocks [h | 4 aggregators x 3 scalers], each tower-major
+        W_post = self._block_diagonal(torch.stack([fc.linear.weight for fc in post]), 13, ft)
+        b_post = torch.cat([fc.linear.bias for fc in post])
+        bn = self._fused_bn(post, "post")
+        x = ops.fc([ops.Seg(h), ops.Seg(agg), ops.Seg(agg, scale=amp), ops.Seg(agg, scale=att)], W_post.contiguous(),
+                   b_post, post[0].act, bn, self.training, None, st.n_valid)
+        if bn is not None and self.training and T > 1:
+            with torch.no_grad():
+                self.__dict__["_bn_big_post"]["nbt"][1:] += 1      # the kernel counted the batch on tower 0's counter
+        if t0.graph_norm:
+            x = ops.scale_rows(x, snorm_n)                                   # :258-259
+        return ops.fc([ops.Seg(x)], self.mixing_network.weight, self.mixing_network.bias, self._leaky, None,
+                      self.training, h if self.residual else None, st.n_valid)    # :315-318
+
     def forward(self, st, scalers, h, ef_csr, snorm_n):
+        if self._fusable():
+            return self._forward_fused(st, scalers, h, ef_csr, snorm_n)
+        if st.n_valid is not None:
+            raise NotImplementedError("shape-bucketed (padded) batches need the fused-tower path of PNAOriginal")
         outs = []
         for t, tower in enumerate(self.towers):
             ht = h[:, t * self.input_tower:(t + 1) * self.input_tower] if self.divide_input else h      # :307-313
@@ -165,6 +254,8 @@ class PNAGNNOriginal(nn.Module):
 
 
 class PNAOriginal(nn.Module):
+    needs_snorm = True          # forward(graph, snorm_n): trainer.BucketedStep builds snorm_n on the device
+
     def __init__(self, hidden_dim, last_layer_dim, target_dim, in_feat_dropout, dropout, last_batch_norm,
                  mid_batch_norm, propagation_depth, readout_aggregators, readout_hidden_dim, readout_layers,
                  aggregators, scalers, avg_d, residual, posttrans_layers, pretrans_layers, device, edge_hidden_dim,

@@ -376,11 +376,12 @@ class BucketedStep:
         if train:
             tr.optim.zero_grad(set_to_none=True)
         g2, g3 = self.store.collate_padded(bk.meta, B, *bk.caps, conformers=self.C, need_3d=not self.supervised)
+        info2d = [g2] + ([self._snorm(g2)] if getattr(tr.model, "needs_snorm", False) else [])
         if self.supervised:
             from .collate import metadata_views
-            batch = ([g2], self.store.targets.index_select(0, metadata_views(bk.meta, B)["idx"]))
+            batch = (info2d, self.store.targets.index_select(0, metadata_views(bk.meta, B)["idx"]))
         else:
-            batch = ([g2], [g3])
+            batch = (info2d, [g3])
         if train:
             loss, z2, z3 = tr.forward_pass(batch)
             loss.backward()
@@ -392,6 +393,17 @@ class BucketedStep:
         if self.keep_outputs:
             o2, o3 = self._outputs(B, z2, z3)
             o2.copy_(z2.detach()), o3.copy_(z3.detach())
+
+    @staticmethod
+    def _snorm(g2):
+        """snorm_n of the tower models (graph_collate, datasets/custom_collate.py:96-98): sqrt(1 / atoms of the node's
+        molecule) per node, [N, 1] — fixed-shape device ops (capturable); padding nodes get the last molecule's value"""
+        nn_ = g2.batch_num_nodes()
+        B, n = nn_.numel(), g2.number_of_nodes()
+        ends = torch.cumsum(nn_, 0)
+        node = torch.arange(n, device=nn_.device, dtype=ends.dtype)
+        gid = torch.searchsorted(ends, node, right=True).clamp_(max=B - 1)
+        return nn_.to(torch.float32).rsqrt()[gid].unsqueeze(1)
 
     def _outputs(self, B, z2, z3):
         o = self._out.get(B)
@@ -486,11 +498,12 @@ class BucketedStep:
         if self.C != 1:
             raise RuntimeError("batch beyond the captured ladder: the eager fallback handles one conformer per molecule")
         g2, g3 = self.store.collate(idx)
+        info2d = [g2] + ([self._snorm(g2)] if getattr(self.tr.model, "needs_snorm", False) else [])
         if self.supervised:
             ix = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self.tr.device)
-            batch = ([g2], self.store.targets.index_select(0, ix))
+            batch = (info2d, self.store.targets.index_select(0, ix))
         else:
-            batch = ([g2], [g3])
+            batch = (info2d, [g3])
         if train:
             loss, z2, z3 = self.tr.process_batch(batch)
         else:

@@ -81,7 +81,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--towers", action="store_true",
                    help="2-D encoder = PNAOriginal(hidden 200, 4 towers, 4 layers), the tower shape configs[1] words; "
-                        "eager launches (its column-sliced tower GEMMs run on the fp32 SIMT kernel)")
+                        "the towers run fused as one block-diagonal layer on the tensor-core path")
     return p.parse_args()
 
 
@@ -99,7 +99,7 @@ def config_dict(args, world):
     name = c["name"] % B
     if getattr(args, "towers", False):
         name = ("configs[1] as worded: PNAOriginal(hidden 200, 4 towers, 4 layers; models/pna_original.py)+Net3D(hidden 20) "
-                "NTXent(tau 0.1) Adam, QM9-shaped synthetic, batch %d per GPU, eager launches" % B)
+                "NTXent(tau 0.1) Adam, QM9-shaped synthetic, batch %d per GPU" % B)
     return {"workload": name, "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
             "conformers": c["conformers"], "loss": c["loss"], "molecules": c["shape"] + "-shaped synthetic",
             "batches": "a fresh random index set every step (distinct N/E/E3), collate inside the timed region",
@@ -327,8 +327,8 @@ def run_b200(args):
                          graph_safe=bucketed)
     else:
         if args.towers:
-            if bucketed or C != 1:
-                raise RuntimeError("--towers runs with --mode eager and one conformer per molecule")
+            if C != 1:
+                raise RuntimeError("--towers runs with one conformer per molecule (config 1)")
             pna = i3d.PNAOriginal(avg_d=1.0, device=dev, **cfg.PNA_ORIGINAL_H200_T4_MODEL_PARAMETERS)
         else:
             pna = i3d.PNA(avg_d=1, device=dev, **cfg.PRETRAIN_QM9_MODEL_PARAMETERS)

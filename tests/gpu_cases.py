@@ -943,6 +943,48 @@ def case_pna_original():
                     if k.startswith("buf/"):
                         out.append((tag + "/" + k, rel(sd[k[4:]], gold[k]), 1e-4))
         out.append((name + "/state_dict_keys_identical", float(len(missing.missing_keys) + len(missing.unexpected_keys)), 0))
+    # the "hidden 200, 4 towers" shape runs FUSED by default (one block-diagonal layer on the tensor-core path, checked
+    # against the reference vectors above); here: the tower-by-tower path on the same weights, and the fused path on a
+    # shape-bucketed (padded) batch against the unpadded one
+    name = "pna_original_h200_t4"
+    bseed, B, shape, wseed, avg_d, c = PCASES[name]
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    kw = {k: v for k, v in c.items() if k != "gru"}
+    st = PO.init_state(c, wseed)
+    b = syn.make_batch(bseed, B, shape=shape)
+    m = i3d.PNAOriginal(avg_d=avg_d, device=DEV, **kw)
+    m.load_state_dict(st, strict=True)
+    m = m.to(DEV).train()
+    out.append((name + "/fused_path_is_the_default", float(not all(L._fusable() for L in m.node_gnn.layers)), 0))
+    for L in m.node_gnn.layers:
+        L.fuse_towers = False
+    g2, _ = i3d.batch_from_numpy(b, DEV)
+    out.append((name + "/train/z(tower-by-tower path)", rel(m(g2, snorm(b["num_nodes"])), gold["z_train"]), 1e-4))
+    # padded vs unpadded, fused, train mode (BatchNorm statistics must ignore the padding rows), incl. gradients
+    store = syn.make_store(77, 60, "qm9")
+    ps = i3d.PackedMoleculeStore(store, DEV)
+    idx = np.random.default_rng(3).integers(0, 60, size=12)
+    res = {}
+    for how in ("plain", "padded"):
+        m = i3d.PNAOriginal(avg_d=avg_d, device=DEV, **kw)
+        m.load_state_dict(st, strict=True)
+        m = m.to(DEV).train()
+        if how == "plain":
+            g2, _ = ps.collate(idx)
+        else:
+            meta, (N, E, E3) = ps.stage_metadata(idx)
+            g2, _ = ps.collate_padded(meta, len(idx), N + 200, E + 300, E3 + 128, need_3d=False)
+        z = m(g2, i3d.BucketedStep._snorm(g2))
+        w = torch.randn(z.shape, generator=torch.Generator().manual_seed(6)).to(DEV)
+        (z * w).sum().backward()
+        res[how] = (z.detach(), {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None},
+                    {k: v.detach().clone() for k, v in m.state_dict().items() if "running_" in k})
+    out.append((name + "/padded_vs_plain/z", rel(res["padded"][0], res["plain"][0]), 2e-5))
+    gs = max(float(v.abs().max()) for v in res["plain"][1].values())
+    out.append((name + "/padded_vs_plain/param_grads(all, global scale)",
+                max(float((res["padded"][1][k] - v).abs().max()) for k, v in res["plain"][1].items()) / gs, 2e-4))
+    out.append((name + "/padded_vs_plain/bn_running_stats",
+                max(rel(res["padded"][2][k], v) for k, v in res["plain"][2].items()), 1e-5))
     return out
 
 

@@ -186,3 +186,48 @@ def test_ntxent_v2_v3_composition_matches_reference_vectors(golden_dir):
         assert abs(val.item() - float(g[tag])) <= 2e-6 * abs(float(g[tag]))
         assert np.abs(a.grad.numpy() - g[tag + "_dz1"]).max() <= 2e-5 * np.abs(g[tag + "_dz1"]).max()
         assert np.abs(b.grad.numpy() - g[tag + "_dz2"]).max() <= 2e-5 * np.abs(g[tag + "_dz2"]).max()
+
+
+def test_fused_tower_algebra_equals_the_tower_oracle():
+    """PNAOriginal's fused-tower path: T towers over disjoint column slices as ONE block-diagonal layer.  The weight
+    assembly of the product (pna_original.PNALayer._block_diagonal / _fused_bn) is evaluated here with dense torch
+    arithmetic and compared with the tower-by-tower oracle (pinned on the reference's models/pna_original.py)."""
+    import importlib
+    import torch.nn.functional as F
+    from oracle import pna_original_oracle as PO
+    from oracle.pin_pna_original import CASES as PCASES, snorm
+    i3d = importlib.import_module("3dinfomax_b200")
+    bseed, B, shape, wseed, avg_d, c = PCASES["pna_original_h200_t4"]
+    b = i3d.synthetic.make_batch(bseed, B, shape=shape)
+    st = PO.init_state(c, wseed)
+    g, xa, ea, _, _ = O.graphs_from_batch(b)
+    sn = snorm(b["num_nodes"])
+    ref = PO.forward(st, c, g, xa, ea, sn, avg_d, training=False)
+    m = i3d.PNAOriginal(avg_d=avg_d, device="cpu", **{k: v for k, v in c.items() if k != "gru"})
+    m.load_state_dict(st, strict=True)
+    m.eval()
+    h = O.embed_sum(xa, st, "node_gnn.embedding_h.atom_embedding_list.%d.weight", xa.shape[1])
+    e = O.embed_sum(ea, st, "node_gnn.embedding_e.bond_embedding_list.%d.weight", ea.shape[1])
+    for L in m.node_gnn.layers:
+        assert L._fusable()
+        T, ft = len(L.towers), L.input_tower
+        pre = [tw.pretrans.fully_connected[0] for tw in L.towers]
+        post = [tw.posttrans.fully_connected[0] for tw in L.towers]
+        Wp = torch.stack([fc.linear.weight for fc in pre])
+        W_pre = torch.cat([L._block_diagonal(Wp[:, :, :2 * ft], 2, ft), Wp[:, :, 2 * ft:].reshape(T * ft, -1)], 1)
+        msg = torch.cat([h[g.src], h[g.dst], e], 1) @ W_pre.t() + torch.cat([fc.linear.bias for fc in pre])
+        agg = PO.reduce_scalar_avg(g, msg, c["aggregators"], c["scalers"], avg_d)
+        W_post = L._block_diagonal(torch.stack([fc.linear.weight for fc in post]), 13, ft)
+        x = torch.cat([h, agg], 1) @ W_post.t() + torch.cat([fc.linear.bias for fc in post])
+        gamma, beta, rm, rv, nbt, mom, eps = L._fused_bn(post, "post")
+        x = F.batch_norm(x, rm, rv, gamma, beta, False, mom, eps)
+        ho = F.leaky_relu(F.linear(x, L.mixing_network.weight, L.mixing_network.bias))
+        h = h + ho if L.residual else ho
+    ro = torch.cat([O.segment_readout(h, g, op) for op in c["readout_aggregators"]], -1)
+    out = PO.mlp_readout(ro, st, "output")
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    # the towers' BatchNorm buffers are views of the fused buffer now; keys and values of the state dict are unchanged
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(st.keys())
+    for k, v in st.items():
+        assert torch.equal(sd[k].cpu(), torch.as_tensor(v)), k
