@@ -208,6 +208,9 @@ class CapturedStep:
         if not trainer.optim.graph_safe:
             raise ValueError("CapturedStep needs SelfSupervisedTrainer(..., graph_safe=True): with host-side "
                              "hyper-parameters the learning rate and Adam's step count would be frozen into the graph")
+        if getattr(trainer.model, "needs_snorm", False):
+            raise NotImplementedError("CapturedStep feeds forward(graph) models; the tower models' forward(graph, snorm_n) "
+                                      "is driven by BucketedStep, which builds snorm_n on the device")
         self.tr = trainer
         dev = trainer.device
         self.static = {
