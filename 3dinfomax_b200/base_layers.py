@@ -86,33 +86,17 @@ class FCLayer(nn.Module):
         return ops.fc_edge_factored(g, h, table, self.linear.weight, self.linear.bias, self.act, self._bn_tuple(),
                                     self.training, valid, combo)
 
-    def _merged_weights(self, plan, F):
+    def forward_merged(self, plan, h, agg, residual=None, valid=None):
+        """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""
         from .kernels import MergedPosttransWeights
         W = self.linear.weight
         # one persistent scratch per (bucket count, device): a captured CUDA graph keeps pointing at the one it was
         # recorded with, so scratch is never re-allocated or shared between different bucket counts
         cache = self.__dict__.setdefault("_merged", {})
-        key = (plan.n_buckets, F, str(W.device))
+        key = (plan.n_buckets, h.shape[1], str(W.device))
         m = cache.get(key)
         if m is None:
-            m = cache[key] = MergedPosttransWeights(self.out_dim, F, plan.n_buckets, W.device)
-        return m
-
-    def premerge(self, plan, F, side):
-        """Build this layer's degree-merged operands NOW on the CURRENT stream (the encoder calls it for all its layers
-        on a side stream at the start of forward: the merge depends on the weights only, 7 x 8 us off the main stream);
-        ``forward_merged`` then joins ``side`` instead of merging."""
-        m = self._merged_weights(plan, F)
-        m.refresh(self.linear.weight)
-        m.fresh_on = side
-
-    def forward_merged(self, plan, h, agg, residual=None, valid=None):
-        """This layer applied to cat[h, agg, agg*amp, agg*att] through the degree-merged weights (ops._FCPostMerged)."""
-        W = self.linear.weight
-        m = self._merged_weights(plan, h.shape[1])
-        side = getattr(m, "fresh_on", None)
-        if side is not None:
-            torch.cuda.current_stream(W.device).wait_stream(side)      # operands were merged ahead of time
+            m = cache[key] = MergedPosttransWeights(self.out_dim, h.shape[1], plan.n_buckets, W.device)
         bn = None
         if self.batch_norm is not None:
             b = self.batch_norm

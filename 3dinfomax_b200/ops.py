@@ -287,9 +287,7 @@ class _FCPostMerged(torch.autograd.Function):
         Fout = W.shape[0]
         if agg.shape != (N, 4 * F) or W.shape[1] != 13 * F:
             raise ValueError("merged posttrans expects agg [N,4F] and a [Fout,13F] weight")
-        if getattr(merged, "fresh_on", None) is None:
-            merged.refresh(W)
-        merged.fresh_on = None        # (premerged operands are good for this one forward)
+        merged.refresh(W)
         Y = torch.empty(N, Fout, dtype=torch.float32, device=W.device)
         segs = [{"A": h, "K": F, "a_idx": plan.perm}, {"A": agg, "K": 4 * F, "a_idx": plan.perm}]
         sums = save = None

@@ -58,9 +58,6 @@ class AtomEncoder(_SummedEmbedding):
         super().__init__(ATOM_FEATURE_DIMS, emb_dim, "atom_embedding_list")
 
 
-_MERGE_STREAMS = {}          # device -> side stream of the ahead-of-time posttrans merges (PNAGNN.forward)
-
-
 class BondEncoder(_SummedEmbedding):
     def __init__(self, emb_dim):
         super().__init__(BOND_FEATURE_DIMS, emb_dim, "bond_embedding_list")
@@ -177,16 +174,6 @@ class PNAGNN(nn.Module):
         if self.keep_edge_side_effects:
             with torch.no_grad():
                 graph.edata["feat"] = self.bond_encoder(e_attr)    # edge-id order, as the reference leaves it
-        if st.plan is not None and h.is_cuda and os.environ.get("I3D_PREMERGE", "1") != "0":
-            # the degree-merged posttrans operands depend on the weights only: all layers' merges run on a side stream
-            # beside the first layer's edge MLP instead of on the critical path in front of every posttrans GEMM
-            side = _MERGE_STREAMS.get(h.device)
-            if side is None:
-                side = _MERGE_STREAMS[h.device] = torch.cuda.Stream(device=h.device)
-            side.wait_stream(torch.cuda.current_stream(h.device))
-            with torch.cuda.stream(side):
-                for layer in self.mp_layers:
-                    layer.posttrans.fully_connected[0].premerge(st.plan, h.shape[1], side)
         msg = None
         for li, layer in enumerate(self.mp_layers):
             h, msg = layer(st, h, ef_csr, edge_codes, None if tables is None else tables[li], combo if factored else None)
