@@ -378,6 +378,168 @@ __global__ void __launch_bounds__(kColThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// BatchNorm backward in ONE launch: the column reduction (bn_bwd_reduce_kernel) and the element-wise pass
+// (bn_bwd_apply_kernel) separated by a grid-wide barrier instead of a kernel boundary.  Same row mapping and the same
+// arithmetic as the two kernels; every thread keeps its rows of dO in shared memory between the phases (Y is re-read, it
+// is L2 resident), the column totals come back through L2.  The barrier is a ticket counter (zeroed by the caller) with
+// acquire polling, which needs every CTA of the grid resident at once: the host caps the grid at the occupancy of this
+// kernel and only takes this path on ONE stream at a time (two such grids spinning beside each other could starve each
+// other of SMs; kernels.bn_bwd), everything else — other streams, wider problems — runs the two-kernel path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxRows = 16;      // rows of dO per thread kept in shared memory
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int V>
+__global__ void __launch_bounds__(kColThreads, 2)
+    bn_bwd_fused_kernel(const float* __restrict__ dO, int ldd, const float* __restrict__ Y, int ldy, int64_t M, int F,
+                        int act, int training, const float* __restrict__ save_mean_rstd,
+                        const float* __restrict__ gamma, double* __restrict__ sums2, float* __restrict__ dY, int lddy,
+                        float* __restrict__ dbias, int db_stride, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        float* __restrict__ zero_buf, int zero_n, const int32_t* __restrict__ m_valid,
+                        unsigned* __restrict__ barrier) {
+  pdl_grid_sync();
+  extern __shared__ double sh[];                                           // [2][V][kColThreads] doubles, then the slab
+  float* slab = reinterpret_cast<float*>(sh + 2 * V * kColThreads);        // [kFusedMaxRows][kColThreads][V] floats
+  const int64_t Mrows = M;
+  if (m_valid) M = min(M, (int64_t)*m_valid);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_buf[i] = 0.f;
+  const int FV = F / V;
+  const ColMap m = col_map(FV);
+  const int64_t stride = (int64_t)gridDim.x * m.RP;
+  const int64_t r_first = (int64_t)blockIdx.x * m.RP + m.rg;
+  const float* yp = Y + m.cg * V;
+  const float* dp = dO + m.cg * V;
+  float* mine = slab + (size_t)threadIdx.x * V;
+  // ---------------- phase 1: column sums of dO and dO * xhat (identical to bn_bwd_reduce_kernel) ----------------
+  {
+    double acc[2][V];
+    float mean[V], rstd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      acc[0][i] = 0.0, acc[1][i] = 0.0;
+      mean[i] = m.active ? save_mean_rstd[m.cg * V + i] : 0.f;
+      rstd[i] = m.active ? save_mean_rstd[F + m.cg * V + i] : 0.f;
+    }
+    if (m.active) {
+      int64_t r = r_first;
+      int k = 0;
+      for (; r + (kColBatch - 1) * stride < M; r += kColBatch * stride, k += kColBatch) {
+        Vec<V> y[kColBatch], d[kColBatch];
+#pragma unroll
+        for (int j = 0; j < kColBatch; ++j) {
+          y[j].load(yp + (r + j * stride) * ldy);
+          d[j].load(dp + (r + j * stride) * ldd);
+        }
+        float s0[V], s1[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) s0[i] = 0.f, s1[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kColBatch; ++j) {
+          d[j].store(mine + (size_t)(k + j) * kColThreads * V);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float xhat = (act_apply(y[j].v[i], act) - mean[i]) * rstd[i];
+            s0[i] += d[j].v[i];
+            s1[i] = fmaf(d[j].v[i], xhat, s1[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[0][i] += (double)s0[i], acc[1][i] += (double)s1[i];
+      }
+      for (; r < M; r += stride, ++k) {
+        Vec<V> y, d;
+        y.load(yp + r * ldy);
+        d.load(dp + r * ldd);
+        d.store(mine + (size_t)k * kColThreads * V);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xhat = (act_apply(y.v[i], act) - mean[i]) * rstd[i];
+          acc[0][i] += (double)d.v[i];
+          acc[1][i] += (double)d.v[i] * (double)xhat;
+        }
+      }
+    }
+    block_col_reduce_f64<V, 2>(acc, m, FV, F, sums2);
+  }
+  // ---------------- grid barrier: every CTA's partial sums (and CTA 0's zero fill) are in L2 ----------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(barrier, 1u);
+    while (ld_acquire_u32(barrier) < gridDim.x) __nanosleep(32);
+  }
+  __syncthreads();
+  // ---------------- phase 2: dY (identical to bn_bwd_apply_kernel with has_bn = 1) ----------------
+  float mean[V], rstd[V], k1[V], k2[V], gr[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    db[i] = 0.f;
+    mean[i] = 0.f, rstd[i] = 1.f, k1[i] = 0.f, k2[i] = 0.f, gr[i] = 1.f;
+    if (m.active) {
+      const int c = m.cg * V + i;
+      mean[i] = save_mean_rstd[c];
+      rstd[i] = save_mean_rstd[F + c];
+      gr[i] = gamma[c] * rstd[i];
+      const double s_do = __ldcg(sums2 + (int64_t)c * I3D_STATS_STRIDE);
+      const double s_dx = __ldcg(sums2 + (int64_t)(F + c) * I3D_STATS_STRIDE);
+      if (training) {
+        k1[i] = (float)(s_do / (double)M);
+        k2[i] = (float)(s_dx / (double)M);
+      }
+      if (blockIdx.x == 0 && m.rg == 0) {
+        dbeta[c] = (float)s_do;
+        dgamma[c] = (float)s_dx;
+      }
+    }
+  }
+  if (m.active) {
+    float* op = dY + m.cg * V;
+    int k = 0;
+    for (int64_t r = r_first; r < M; r += stride, ++k) {
+      Vec<V> y, d, o;
+      y.load(yp + r * ldy);
+      d.load_shared(mine + (size_t)k * kColThreads * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xhat = (act_apply(y.v[i], act) - mean[i]) * rstd[i];
+        const float dh = gr[i] * (d.v[i] - k1[i] - xhat * k2[i]);
+        const float dy = dh * act_grad(y.v[i], act);
+        o.v[i] = dy;
+        db[i] += dy;
+      }
+      o.store(op + r * lddy);
+    }
+    if (Mrows > M) {
+      Vec<V> z;
+      z.fill(0.f);
+      int64_t rz = r_first;
+      if (rz < M) rz += ((M - rz + stride - 1) / stride) * stride;
+      for (; rz < Mrows; rz += stride) z.store(op + rz * lddy);
+    }
+  }
+  if (dbias) {
+    float* shf = reinterpret_cast<float*>(sh);  // [V][kColThreads] (the reduction scratch of phase 1 is free again)
+#pragma unroll
+    for (int i = 0; i < V; ++i) shf[i * kColThreads + threadIdx.x] = m.active ? db[i] : 0.f;
+    __syncthreads();
+    if (m.active && m.rg == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float s = 0.f;
+        for (int r = 0; r < m.RP; ++r) s += shf[i * kColThreads + r * FV + m.cg];
+        atomicAdd(dbias + (int64_t)(m.cg * V + i) * db_stride, s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Factored first layer of the edge MLP (models/pna.py:237-252).  cat[h[src], h[dst], e] W^T splits by columns of W into
 // (h W_s^T)[src] + (h W_d^T)[dst] + e W_e^T: the two h terms are ONE node-level GEMM P = h [W_s;W_d]^T
 // (N rows instead of E, K = F instead of 3F) and, because the bond features take only prod(5,6,2) = 60 distinct values
@@ -661,6 +823,68 @@ int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_
     launch(bn_bwd_apply_kernel<1>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, has_bn, training,
                                                                      save_mean_rstd, gamma, sums2, dY, lddy, dbias,
                                                                      dgamma, dbeta, m_valid, slots, counter, dbias_stride);
+  I3D_LAUNCHED();
+  return I3D_OK;
+}
+
+int i3d_bn_bwd_fused_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int training,
+                       const float* save_mean_rstd, const float* gamma, double* sums2, float* dY, int lddy,
+                       float* dbias, int dbias_stride, float* dgamma, float* dbeta, float* zero_buf, int zero_n,
+                       const int32_t* m_valid, unsigned int* barrier, void* stream) {
+  I3D_REQUIRE(M >= 0 && F > 0 && ldy >= F && ldd >= F && lddy >= F && sums2 && save_mean_rstd && gamma && dgamma &&
+                  dbeta && (M == 0 || (Y && dO && dY)) && dbias_stride >= 1 && zero_n >= 0 && (zero_n == 0 || zero_buf),
+              "invalid argument");
+  cudaStream_t s = as_stream(stream);
+  const bool v4 = can_vec4({Y, dO, dY}, {F, ldy, ldd, lddy});
+  const int V = v4 ? 4 : 1, FV = F / V;
+  bool fused = barrier != nullptr && M > 0 && FV <= kColThreads;
+  int grid = 0;
+  size_t smem = 0;
+  if (fused) {
+    static int mode = -1;      // I3D_BN_BWD=split: always the two-kernel path
+    if (mode < 0) {
+      const char* e = getenv("I3D_BN_BWD");
+      mode = (e && e[0] == 's') ? 0 : 1;
+    }
+    fused = mode == 1;
+  }
+  if (fused) {
+    smem = sizeof(double) * 2 * V * kColThreads + sizeof(float) * (size_t)kFusedMaxRows * kColThreads * V;
+    static int per_sm[2] = {-1, -1};       // resident CTAs per SM of the two instantiations (0 = unusable)
+    int& nb = per_sm[v4 ? 1 : 0];
+    if (nb < 0) {
+      nb = 0;
+      cudaError_t e = v4 ? cudaFuncSetAttribute(bn_bwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(bn_bwd_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int n = 0;
+      if (e == cudaSuccess)
+        e = v4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_bwd_fused_kernel<4>, kColThreads, smem)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_bwd_fused_kernel<1>, kColThreads, smem);
+      if (e == cudaSuccess) nb = n;
+      else cudaGetLastError();
+    }
+    const int RP = kColThreads / FV;
+    const int64_t cap = (int64_t)nb * sm_count();
+    grid = col_grid(M, FV);
+    if (grid > cap) grid = (int)cap;
+    // every thread must be able to keep its rows of dO: ceil(M / (grid * RP)) <= kFusedMaxRows
+    fused = grid >= 1 && (M + (int64_t)grid * RP - 1) / ((int64_t)grid * RP) <= kFusedMaxRows;
+  }
+  if (!fused) {
+    if (int rc = i3d_bn_bwd_reduce_v(dO, ldd, Y, ldy, M, F, act, save_mean_rstd, sums2, zero_buf, zero_n, m_valid,
+                                     nullptr, stream))
+      return rc;
+    return i3d_bn_bwd_apply_v(dO, ldd, Y, ldy, M, F, act & 0xff, 1, training, save_mean_rstd, gamma, sums2, dY, lddy,
+                              dbias, dbias_stride, dgamma, dbeta, m_valid, nullptr, stream);
+  }
+  if (!(act & I3D_STATS_PREZEROED)) I3D_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * F * I3D_STATS_STRIDE, s));
+  act &= 0xff;
+  if (v4)
+    launch(bn_bwd_fused_kernel<4>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, training, save_mean_rstd,
+           gamma, sums2, dY, lddy, dbias, dbias_stride, dgamma, dbeta, zero_buf, zero_n, m_valid, barrier);
+  else
+    launch(bn_bwd_fused_kernel<1>, grid, kColThreads, smem, s, dO, ldd, Y, ldy, M, F, act, training, save_mean_rstd,
+           gamma, sums2, dY, lddy, dbias, dbias_stride, dgamma, dbeta, zero_buf, zero_n, m_valid, barrier);
   I3D_LAUNCHED();
   return I3D_OK;
 }

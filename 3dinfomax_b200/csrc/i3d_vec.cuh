@@ -18,6 +18,16 @@ struct Vec {
       for (int i = 0; i < V; ++i) v[i] = __ldg(p + i);
     }
   }
+  // plain (coherent) load, e.g. from shared memory
+  __device__ __forceinline__ void load_shared(const float* p) {
+    if constexpr (V == 4) {
+      float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = p[i];
+    }
+  }
   __device__ __forceinline__ void store(float* p) const {
     if constexpr (V == 4) {
       *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -603,6 +603,48 @@ def bn_bwd_apply(dO, Y, act, has_bn, training, save, gamma, sums2, want_dbias=Tr
     return dY, dbias, dgamma, dbeta
 
 
+# streams on which the one-launch BatchNorm backward is NOT used: its grid barrier spins, so at most one stream per device
+# may run it (two such grids beside each other could starve each other of SMs).  The trainer registers the 3-D encoder's
+# stream here; the 2-D encoder's (main) stream takes the fused path.
+NO_FUSED_BN_BWD_STREAMS = set()
+
+
+def bn_bwd(dO, Y, act, training, save, gamma, want_dbias=True, dbias_zeroed=None, valid=None, arena=None):
+    """Backward of activation -> BatchNorm: (dY, dbias, dgamma, dbeta).  ``bn_bwd_reduce`` + ``bn_bwd_apply`` in one
+    call; one LAUNCH (i3d_bn_bwd_fused_v) under a trainer (``arena``) on a stream that may spin on a grid barrier."""
+    fused_ok = (arena is not None and os.environ.get("I3D_TWO_STAGE", "0") != "1"
+                and torch.cuda.current_stream(Y.device).cuda_stream not in NO_FUSED_BN_BWD_STREAMS)
+    bar = arena.take(STATS_STRIDE) if fused_ok else None          # 128 zeroed bytes: the barrier's ticket counter
+    if bar is None:
+        sums2 = bn_bwd_reduce(dO, Y, act, save, arena=arena, zero=dbias_zeroed, valid=valid)
+        return bn_bwd_apply(dO, Y, act, True, training, save, gamma, sums2, want_dbias, dbias_zeroed=dbias_zeroed,
+                            valid=valid, arena=arena)
+    pd, ldd = _mat(dO, "dO")
+    py, ldy = _mat(Y, "Y")
+    M, F = Y.shape
+    dev = Y.device
+    sums2, flag = _stats_buffer(arena, 2 * F, dev)
+    dY = torch.empty(M, F, dtype=torch.float32, device=dev)
+    db_stride = 1
+    if not want_dbias:
+        dbias = None
+    elif dbias_zeroed is not None:
+        dbias = dbias_zeroed                     # cleared by the kernel's first phase
+        db_stride = dbias.numel() // F
+    else:
+        dbias = torch.zeros(F, dtype=torch.float32, device=dev)
+    dgamma = torch.empty(F, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(F, dtype=torch.float32, device=dev)
+    zero = dbias_zeroed
+    _lib.check(_L().i3d_bn_bwd_fused_v(pd, ldd, py, ldy, M, F, act | flag, 1 if training else 0, _p(save), _p(gamma),
+                                       _p(sums2), _p(dY), F, _p(dbias), db_stride, _p(dgamma), _p(dbeta), _p(zero),
+                                       0 if zero is None else zero.numel(), _valid(valid), _p(bar), _s()),
+               "i3d_bn_bwd_fused")
+    if dbias is not None and db_stride > 1:
+        dbias = dbias.view(F, db_stride)[:, 0]
+    return dY, dbias, dgamma, dbeta
+
+
 def act_fwd(x, act):
     _req(x, torch.float32, "x")
     x = x.contiguous()

@@ -78,6 +78,7 @@ SIGNATURES = {
     "i3d_act_colstats_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "i3d_bn_apply_v": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_bn_bwd_reduce_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "i3d_bn_bwd_fused_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "i3d_bn_bwd_apply_v": (_I, [_P, _I, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
     "i3d_embed_sum_fwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _P]),
     "i3d_embed_sum_bwd": (_I, [_P, _L, _I, _P, _P, _P, _I, _P, _I, _I, _P]),

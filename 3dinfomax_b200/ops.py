@@ -175,13 +175,12 @@ class _FC(torch.autograd.Function):
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
             dbz = K.dbias_buffer(Fout, W.device) if need_b else None
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
             # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
             # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
             zero_db = need_b and cfg.training and cfg.act == 0
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
-                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            dY, db, dgamma, dbeta = K.bn_bwd(dO, Y, cfg.act, cfg.training, save, gamma, need_b and not zero_db,
+                                             dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
                 db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:
@@ -322,13 +321,12 @@ class _FCPostMerged(torch.autograd.Function):
         if cfg.has_bn:
             arena = getattr(ctx.w_param, "_i3d_arena", None)
             dbz = K.dbias_buffer(Fout, W.device) if need_b else None
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
             # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
             # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
             zero_db = need_b and cfg.training and cfg.act == 0
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
-                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            dY, db, dgamma, dbeta = K.bn_bwd(dO, Y, cfg.act, cfg.training, save, gamma, need_b and not zero_db,
+                                             dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
                 db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:
@@ -481,13 +479,12 @@ class _FCEdgeFactored(torch.autograd.Function):
         arena = getattr(ctx.w_param, "_i3d_arena", None)
         if cfg.has_bn:
             dbz = K.dbias_buffer(Fout, dev) if need_b else None
-            sums2 = K.bn_bwd_reduce(dO, Y, cfg.act, save, arena=arena, zero=dbz, valid=cfg.valid)
             # Linear -> (no activation) -> train-mode BatchNorm: the bias is cancelled by the mean subtraction, its
             # gradient is EXACTLY zero (sum over rows of gr (dO - mean(dO) - xhat mean(dO xhat)) = 0); the reference's
             # value is the fp32 rounding noise of that sum.  dbz was zeroed by bn_bwd_reduce: no second reduction needed.
             zero_db = need_b and cfg.training and cfg.act == 0
-            dY, db, dgamma, dbeta = K.bn_bwd_apply(dO, Y, cfg.act, True, cfg.training, save, gamma, sums2,
-                                                   need_b and not zero_db, dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
+            dY, db, dgamma, dbeta = K.bn_bwd(dO, Y, cfg.act, cfg.training, save, gamma, need_b and not zero_db,
+                                             dbias_zeroed=dbz, valid=cfg.valid, arena=arena)
             if zero_db:
                 db = dbz[:Fout]          # (contiguous zeros: autograd keeps it as .grad without a layout copy)
         elif cfg.act != 0 or cfg.valid is not None:

@@ -155,6 +155,9 @@ class SelfSupervisedTrainer(Trainer):
         # its own stream, forward and backward (autograd replays a node on the stream its forward ran on), and fills
         # the SMs the 2-D encoder's one-CTA-per-SM GEMMs leave idle.  Inside a captured step this is a forked branch.
         self.stream3d = torch.cuda.Stream(device=self.device) if overlap_encoders else None
+        if self.stream3d is not None:
+            from . import kernels as _K
+            _K.NO_FUSED_BN_BWD_STREAMS.add(self.stream3d.cuda_stream)     # one spinning grid barrier per device at a time
         self.initialize_optimizer(optimizer_params or {"lr": 8e-5}, graph_safe)
 
     def param_groups(self, named, optimizer_params):

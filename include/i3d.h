@@ -327,6 +327,17 @@ int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_
                        int training, const float* save_mean_rstd, const float* gamma, const double* sums2, float* dY,
                        int lddy, float* dbias, int dbias_stride, float* dgamma, float* dbeta, const int32_t* m_valid,
                        const i3d_reduce_ws* rws, void* stream);
+/* i3d_bn_bwd_reduce_v followed by i3d_bn_bwd_apply_v (has_bn = 1) as ONE call — the backward of activation ->
+ * BatchNorm1d [models/base_layers.py:102-110] — and, when the problem fits, as ONE launch: the two phases are separated
+ * by a grid-wide barrier on `barrier` (DEVICE counter, zero on entry, not reset) instead of a kernel boundary, every
+ * thread keeping its rows of dO in shared memory.  barrier == NULL, I3D_BN_BWD=split or a problem that does not fit
+ * (more than 16 rows per thread at full occupancy) take the two-kernel path.  The barrier spins: callers run at most one
+ * such launch at a time per device (3dinfomax_b200.kernels.bn_bwd keeps it to one stream).  act may carry
+ * I3D_STATS_PREZEROED for sums2; zero_buf / zero_n as in i3d_bn_bwd_reduce_v. */
+int i3d_bn_bwd_fused_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int training,
+                       const float* save_mean_rstd, const float* gamma, double* sums2, float* dY, int lddy,
+                       float* dbias, int dbias_stride, float* dgamma, float* dbeta, float* zero_buf, int zero_n,
+                       const int32_t* m_valid, unsigned int* barrier, void* stream);
 /* Factored first layer of the edge MLP [models/pna.py:237-252]: cat[h[src], h[dst], e] W^T =
  * (h W_s^T)[src] + (h W_d^T)[dst] + e W_e^T.  P [N, >=2F] = h [W_s; W_d]^T comes from ONE node-level GEMM; the bond
  * features take prod(5,6,2) = 60 distinct values [commons/mol_encoder.py:4-7], so e W_e^T is a table T [n_codes, F]
