@@ -611,8 +611,10 @@ NO_FUSED_BN_BWD_STREAMS = set()
 
 def bn_bwd(dO, Y, act, training, save, gamma, want_dbias=True, dbias_zeroed=None, valid=None, arena=None):
     """Backward of activation -> BatchNorm: (dY, dbias, dgamma, dbeta).  ``bn_bwd_reduce`` + ``bn_bwd_apply`` in one
-    call; one LAUNCH (i3d_bn_bwd_fused_v) under a trainer (``arena``) on a stream that may spin on a grid barrier."""
-    fused_ok = (arena is not None and os.environ.get("I3D_TWO_STAGE", "0") != "1"
+    call; with I3D_BN_BWD=fused one LAUNCH (i3d_bn_bwd_fused_v) under a trainer (``arena``) on a stream that may spin
+    on a grid barrier (measured: 4.130 vs 4.146 ms per step, i.e. nothing; off by default)."""
+    fused_ok = (arena is not None and os.environ.get("I3D_BN_BWD", "split") == "fused"
+                and os.environ.get("I3D_TWO_STAGE", "0") != "1"
                 and torch.cuda.current_stream(Y.device).cuda_stream not in NO_FUSED_BN_BWD_STREAMS)
     bar = arena.take(STATS_STRIDE) if fused_ok else None          # 128 zeroed bytes: the barrier's ticket counter
     if bar is None:

@@ -330,8 +330,9 @@ int i3d_bn_bwd_apply_v(const float* dO, int ldd, const float* Y, int ldy, int64_
 /* i3d_bn_bwd_reduce_v followed by i3d_bn_bwd_apply_v (has_bn = 1) as ONE call — the backward of activation ->
  * BatchNorm1d [models/base_layers.py:102-110] — and, when the problem fits, as ONE launch: the two phases are separated
  * by a grid-wide barrier on `barrier` (DEVICE counter, zero on entry, not reset) instead of a kernel boundary, every
- * thread keeping its rows of dO in shared memory.  barrier == NULL, I3D_BN_BWD=split or a problem that does not fit
- * (more than 16 rows per thread at full occupancy) take the two-kernel path.  The barrier spins: callers run at most one
+ * thread keeping its rows of dO in shared memory — opt-in with I3D_BN_BWD=fused (measured 0.4 % of the step, within
+ * noise: the default is the two-kernel path).  barrier == NULL or a problem that does not fit (more than 16 rows per
+ * thread at full occupancy) always take the two-kernel path.  The barrier spins: callers run at most one
  * such launch at a time per device (3dinfomax_b200.kernels.bn_bwd keeps it to one stream).  act may carry
  * I3D_STATS_PREZEROED for sums2; zero_buf / zero_n as in i3d_bn_bwd_reduce_v. */
 int i3d_bn_bwd_fused_v(const float* dO, int ldd, const float* Y, int ldy, int64_t M, int F, int act, int training,
