@@ -57,3 +57,19 @@ def test_aggregate_tma_staged_variant():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "TOTAL FAILURES: 0" in r.stdout, r.stdout[-4000:]
     assert r.stdout.count("== case_") == 2, r.stdout[-2000:]
+
+
+def test_opt_in_kernel_variants():
+    """The measured-and-kept-off variants stay correct: I3D_TN_CLUSTER=4 (split-K reduction of the weight-gradient GEMM
+    through a thread-block cluster) and I3D_BN_BWD=fused (BatchNorm backward as one launch with a grid barrier), through
+    the GEMM cases and whole training steps (eager, captured, shape-bucketed).  Both switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, I3D_TN_CLUSTER="4", I3D_BN_BWD="fused")
+    cases = ["case_gemm_tc", "case_train_steps", "case_train_steps_captured", "case_bucketed_step"]
+    r = subprocess.run([sys.executable, os.path.join(here, "gpu_diag.py")] + cases, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "TOTAL FAILURES: 0" in r.stdout, r.stdout[-4000:]
+    assert r.stdout.count("== case_") == len(cases), r.stdout[-2000:]
